@@ -1,0 +1,146 @@
+/*
+ * paligemma_b200.h -- C ABI of libpaligemma_b200.so: the sm_100a kernels behind the PaliGemma inference hot path.
+ *
+ * The reference (prtk1729/Paligemma-MultiModal-System) has no FFI: its boundary is the Python module API
+ * (modeling_paligemma.py:257-307 forward, modeling_gemma.py:8-64 KVCache, inference.py:29-106 loop).  The host side of
+ * this repo keeps that API in Python (paligemma_multimodal_system_b200/*.py) and reaches the GPU only through the
+ * entry points below (ctypes).  Every function:
+ *   - takes raw DEVICE pointers, sizes and a cudaStream_t (as void*); no torch types;
+ *   - is asynchronous on `stream`; returns PG_OK or a negative PG_ERR_* code (never throws, never falls back to CPU);
+ *   - cites the reference call site(s) it replaces.
+ * Tensors are row-major; "ld" arguments are row pitches in ELEMENTS.
+ */
+#ifndef PALIGEMMA_B200_H
+#define PALIGEMMA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_ARG (-1)    /* bad shape / alignment / enum */
+#define PG_ERR_CUDA (-2)   /* launch or attribute failure (cudaGetLastError) */
+#define PG_ERR_DRIVER (-3) /* cuTensorMapEncodeTiled entry point not found */
+#define PG_ERR_TMAP (-4)   /* tensor-map encode rejected the geometry */
+#define PG_ERR_ARCH (-5)   /* device is not sm_100 */
+
+/* GEMM epilogues */
+#define PG_EPI_BF16 0       /* out_bf16[t,f] = act((acc + bias[f]) * scale)                */
+#define PG_EPI_F32 1        /* out_f32[t,f]  = (acc + bias[f]) * scale + resid_f32[t,f]    */
+#define PG_EPI_ATOMIC_F32 2 /* out_f32[t,f] += (acc + bias[f]) * scale   (split-K, red.add) */
+#define PG_EPI_GEGLU 3      /* out_bf16[t,g] = gelu_tanh(gate[t,g]) * up[t,g]; weight rows packed [64 gate | 64 up] */
+
+/* Library / device info.  Returns the ABI version (>0) or PG_ERR_ARCH when the current device is not sm_100. */
+int pg_abi_version(void);
+int pg_check_device(void);
+
+/*
+ * acc[t,f] = sum_k x[t,k] * w[f,k]  (bf16 in, fp32 accumulate on tcgen05 tensor cores, accumulator in TMEM).
+ * Replaces every nn.Linear on the path: modeling_siglip.py:59-62,71-75,156,177-185; modeling_paligemma.py:57,64;
+ * modeling_gemma.py:205-218,255-259,274-278,356,484,523; and nn.Conv2d (modeling_siglip.py:258-263) after pg_im2col.
+ *   swap:   0 = tokens on the UMMA M axis (prefill), 1 = features on the M axis (decode, tokens <= 128), -1 = auto
+ *   split_k: >1 only with PG_EPI_ATOMIC_F32
+ */
+int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                 const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
+                 int act_gelu, float scale, int swap, int split_k, void* stream);
+
+/* Packs gate_proj / up_proj [F,K] bf16 into the [64 gate | 64 up] row-interleaved [2F,K] layout PG_EPI_GEGLU expects.
+ * (modeling_gemma.py:205-206 weights; F % 64 == 0) */
+int pg_pack_gate_up(const void* gate, const void* up, void* packed, int F, int K, void* stream);
+
+/* fp32 -> bf16 cast (weight packing, pixel staging). */
+int pg_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* nn.LayerNorm (modeling_siglip.py:199-204,310,319): x fp32 [rows, D] -> y bf16 (and/or fp32 if y_f32 != NULL). */
+int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int D,
+                 float eps, void* stream);
+
+/* GemmaRMSNorm (modeling_gemma.py:157-182): y = x * rsqrt(mean(x^2) + eps) * (1 + w); x fp32 -> y bf16.
+ * Optionally zero-fills `zero_buf` (zero_count floats) for a following split-K atomic GEMM. */
+int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
+               long long zero_count, void* stream);
+
+/* SiglipVisionEmbeddings im2col (modeling_siglip.py:258-263,285-297): pixel fp32 [B,C,H,W] -> patches bf16
+ * [B*(H/P)*(W/P), Kpad], column order (c, py, px) = Conv2d weight order, zero padded to Kpad. */
+int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream);
+
+/* x[b*N + n, :] += pos[n, :]  (positional_embeddings add, modeling_siglip.py:289-298); x fp32 [B*N, D]. */
+int pg_add_pos_emb(float* x, const float* pos, int B, int N, int D, void* stream);
+
+/*
+ * Non-causal softmax(Q K^T * scale) V, flash style (modeling_siglip.py:96-136; modeling_gemma.py:307-339 prefill
+ * with the all-zero mask of modeling_paligemma.py:154-156).  bf16 in/out, fp32 softmax.
+ * Row r of batch b, head h:  q + b*q_bs + (r / group)*q_ts + (r % group)*q_hs + h*q_head_off ; K/V rows: k + b*kv_bs + n*kv_ts + h*kv_head_off.
+ * out: o + b*o_bs + r*o_rs + h*o_head_off.   dh in {64, 72, 256}.
+ */
+int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
+                         int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off,
+                         long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_rs,
+                         long long o_head_off, float scale, void* stream);
+
+/*
+ * RoPE + KV append (modeling_gemma.py:116-151,285-302 and KVCache.update :18-57): reads qkv [T, (Hq+2Hkv)*dh]
+ * (bf16, or fp32 when qkv_is_f32), rotates q and k (rotate-half, fp32 angle = pos[t] * inv_freq[i], inv_freq fp32 [dh/2] built by the host exactly as
+ * GemmaRotaryEmbedding.__init__ does), writes q_out bf16
+ * [T, Hq*dh], optional k_out/v_out bf16 [T, Hkv*dh] (dense, for prefill attention) and appends k/v into the paged
+ * cache: page = page_table[b*max_pages + slot/page_size], slot = slot_base[b] + (t - b*tokens_per_seq).
+ */
+int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos, void* q_out, void* k_out, void* v_out,
+                      void* k_pages, void* v_pages, const int* page_table, const int* slot_base, int B,
+                      int tokens_per_seq, int Hq, int Hkv, int dh, int page_size, int max_pages,
+                      const float* inv_freq, void* stream);
+
+/*
+ * Decode attention (modeling_gemma.py:307-339 with q_len == 1): one query token per sequence, the Hq/Hkv query heads
+ * of a group share one KV head read from the paged bf16 cache (page_size must be 64), split over the KV length
+ * (partials in the fp32 workspace) and combined by a second kernel.  kv_len[b] is read on the device (CUDA-graph
+ * friendly).  q bf16 [B, Hq*dh] (post-RoPE); pages bf16 [num_pages, 64, Hkv*dh]; out bf16 [B, Hq*dh].
+ */
+int pg_attention_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table,
+                        const int* kv_len, void* out, float* workspace, int B, int Hq, int Hkv, int dh, int page_size,
+                        int max_pages, int num_splits, float scale, void* stream);
+long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_splits);
+
+/* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
+ * views, modeling_gemma.py:8-64). */
+int pg_kv_gather(const void* pages, const int* page_table, void* dense, int B, int len, int Hkv, int dh, int page_size,
+                 int max_pages, void* stream);
+
+/*
+ * Embedding gather + image-feature merge (+ position ids)
+ * (modeling_paligemma.py:93-128,195,288 and the *sqrt(hidden) of modeling_gemma.py:510-511):
+ *   text token : h[b,s,:] = embed[id,:] * text_scale      image token (j-th in row b): h = img[b,j,:] * img_scale
+ *   pad token  : 0                                         pos[b,s] = cumsum(mask)[s], 1 where mask == 0
+ * embed bf16 [V,D]; img fp32 [B,N,D]; h fp32 [B,S,D]; src_scratch int32 [B,S].  err_flag[0] is set to 1 when a row
+ * does not hold exactly N image tokens (the reference leaves this unchecked, modeling_paligemma.py:120-121).
+ */
+int pg_merge_embeddings(const long long* input_ids, const long long* attn_mask, const void* embed, const float* img,
+                        float* h, int* pos, int* src_scratch, int* err_flag, int B, int S, int D, int N,
+                        long long image_token, long long pad_token, float text_scale, float img_scale, void* stream);
+
+/* Decode-step embedding with the same merge rules at q_len = 1; tokens are int32 on the device; img may be NULL. */
+int pg_embed_tokens(const int* tokens, const void* embed, const float* img, float* h, int B, int D, int N,
+                    float text_scale, float img_scale, long long pad_token, long long image_token, void* stream);
+
+/* Greedy argmax over fp32 logits [B, V] (inference.py:68); ties -> lowest index.  out int32 [B]. */
+int pg_argmax(const float* logits, long long ld, int* out, int B, int V, void* stream);
+
+/*
+ * Top-p sampling (inference.py:65,90-106) from fp32 logits [B, V]: probs = softmax(logits * inv_temperature);
+ * keep every token whose strictly-greater probability mass is <= top_p (= the reference's exclusive-cumsum rule; tied
+ * probabilities are kept or dropped together); sample from the renormalised kept set by inverse CDF in vocabulary
+ * order with a counter-based RNG keyed by (seed, *step_ptr, row).  out int32 [B]; kept_count optional int32 [B].
+ */
+int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count, int B, int V, float inv_temperature,
+                    float top_p, unsigned long long seed, const int* step_ptr, void* stream);
+
+/* After sampling (device-side loop state, CUDA-graph friendly): tok_hist[step*B + b] = next[b]; cur_tok[b] = next[b];
+ * counters[c*B + b] += 1 for c < n_counters (position ids, KV write slots, KV lengths); step += 1.  B <= 1024. */
+int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counters, int n_counters, int* step, int B,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PALIGEMMA_B200_H */

@@ -1,0 +1,115 @@
+"""ctypes binding of libpaligemma_b200.so (the C ABI declared in include/paligemma_b200.h).
+
+There is no CPU fallback: `lib()` raises if the shared library is missing, and every wrapper raises RuntimeError on a
+non-zero return code.  Tensors are passed as raw device pointers (`tensor.data_ptr()`); torch only owns the memory and
+the stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpaligemma_b200.so")
+
+EPI_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_GEGLU = 0, 1, 2, 3
+
+_ERRORS = {-1: "PG_ERR_ARG", -2: "PG_ERR_CUDA", -3: "PG_ERR_DRIVER", -4: "PG_ERR_TMAP", -5: "PG_ERR_ARCH"}
+
+p, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
+
+# name -> argtypes (restype is int unless noted); must match include/paligemma_b200.h
+SIGNATURES = {
+    "pg_abi_version": [],
+    "pg_check_device": [],
+    "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
+    "pg_pack_gate_up": [p, p, p, i32, i32, p],
+    "pg_cast_f32_bf16": [p, p, i64, p],
+    "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],
+    "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p],
+    "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
+    "pg_add_pos_emb": [p, p, i32, i32, i32, p],
+    "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
+    "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
+    "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
+    "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],
+    "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
+    "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
+    "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
+    "pg_argmax": [p, i64, p, i32, i32, p],
+    "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
+    "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
+}
+_RESTYPE = {"pg_attention_decode_workspace_floats": i64}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m paligemma_multimodal_system_b200.build` "
+                "(there is no CPU / PyTorch fallback for the kernels)")
+        l = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, i32)
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {_ERRORS.get(rc, rc)}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require_device():
+    """The product path needs an sm_100 GPU and the compiled kernels; anything else is an error, not a fallback."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("paligemma_multimodal_system_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")
+    check(lib().pg_check_device(), "pg_check_device")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin typed wrappers (argument checking that needs tensor metadata lives here; kernels check the rest)
+# ------------------------------------------------------------------------------------------------------------------
+def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, swap=-1, split_k=1, features=None):
+    """out[t,f] (mode-dependent) from x [T,K] bf16 and w [F,K] bf16 (nn.Linear layout)."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda and w.is_cuda
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1 and x.shape[1] == w.shape[1]
+    T, K = x.shape
+    F = w.shape[0] if features is None else features
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    if resid is not None:
+        assert resid.dtype == torch.float32 and resid.stride(-1) == 1
+    check(lib().pg_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
+                             ptr(resid), 0 if resid is None else resid.stride(0), T, F, K, mode, int(act_gelu), float(scale),
+                             swap, split_k, stream()), "pg_gemm_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out_bf16=None, out_f32=None):
+    rows, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(lib().pg_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ptr(out_bf16), ptr(out_f32), rows, D, float(eps),
+                             stream()), "pg_layernorm")
+
+
+def rmsnorm(x, w, out_bf16, eps=1e-6, zero_buf=None):
+    rows, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(lib().pg_rmsnorm(x.data_ptr(), w.data_ptr(), out_bf16.data_ptr(), rows, D, float(eps), ptr(zero_buf),
+                           0 if zero_buf is None else zero_buf.numel(), stream()), "pg_rmsnorm")

@@ -1,0 +1,482 @@
+// Attention kernels (bf16 in/out, fp32 online softmax).
+//
+//  * attn_prefill_kernel : non-causal flash attention for the SigLIP tower (modeling_siglip.py:96-136, dh = 72) and for
+//    the Gemma prefill (modeling_gemma.py:307-339 with the all-zero mask of modeling_paligemma.py:154-156, dh = 256,
+//    MQA: the Hq query heads of one token are stacked as consecutive rows against the single KV head, so repeat_kv
+//    (modeling_gemma.py:185-196) never materialises).
+//  * attn_decode_kernel  : q_len = 1 decode over the paged bf16 KV cache, split over the KV length, K/V tiles staged
+//    through shared memory with 16-byte cp.async, warp-shuffle softmax reductions, + a combine kernel.
+//
+// Round-1 implementation: mma.sync m16n8k16 tensor-core tiles (attention is 1.4 % of the 224-px prefill FLOPs); the
+// tcgen05/TMEM version for the 448/896-px configs is the next step for this file.
+#include "common.cuh"
+#include "paligemma_b200.h"
+
+namespace pg {
+
+typedef __nv_bfloat16 bf16;
+
+struct AttnPrefillParams {
+  const bf16* q;
+  const bf16* k;
+  const bf16* v;
+  bf16* o;
+  int rows, keys, group;
+  long long q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts, kv_head_off, o_bs, o_rs, o_head_off;
+  float sl2;  // softmax scale * log2(e)
+};
+
+template <int DH>
+struct AttnCfg {
+  static constexpr int DHP = (DH + 15) / 16 * 16;  // padded to the mma K granularity (72 -> 80), pad lanes are zero
+  static constexpr int LDS = DHP + 8;              // +16 B row padding: conflict-free ldmatrix
+  static constexpr int CHUNKS = DHP / 8;           // 16-byte chunks per (padded) row
+  static constexpr int VALID_CHUNKS = DH / 8;
+};
+
+// cooperative tile load: `nrows` rows of DH bf16 (row i from src_row(i), nullptr => zero row) into smem [nrows][LDS]
+template <int DH, int NTHREADS, typename RowPtr>
+PG_DEVINL void load_tile(bf16* smem, int nrows, RowPtr src_row) {
+  using C = AttnCfg<DH>;
+  for (int idx = threadIdx.x; idx < nrows * C::CHUNKS; idx += NTHREADS) {
+    const int r = idx / C::CHUNKS, c = idx % C::CHUNKS;
+    const bf16* src = src_row(r);
+    const bool valid = (src != nullptr) && (c < C::VALID_CHUNKS);
+    // keep the (unused) address in bounds when not valid
+    cp_async16(smem_u32(smem + r * C::LDS + c * 8), valid ? static_cast<const void*>(src + c * 8) : static_cast<const void*>(smem), valid);
+  }
+}
+
+template <int DH, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) attn_prefill_kernel(const AttnPrefillParams p) {
+  using C = AttnCfg<DH>;
+  constexpr int BLOCK_M = NWARPS * 16;
+  constexpr int BLOCK_N = 64;
+  constexpr int NT = NWARPS * 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Ks = Qs + BLOCK_M * C::LDS;
+  bf16* Vs = Ks + 2 * BLOCK_N * C::LDS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const bf16* qb = p.q + b * p.q_bs + h * p.q_head_off;
+  const bf16* kb = p.k + b * p.kv_bs + h * p.kv_head_off;
+  const bf16* vb = p.v + b * p.kv_bs + h * p.kv_head_off;
+
+  load_tile<DH, NT>(Qs, BLOCK_M, [&](int r) -> const bf16* {
+    const int row = m0 + r;
+    return row < p.rows ? qb + (row / p.group) * p.q_ts + (row % p.group) * p.q_hs : nullptr;
+  });
+  auto load_kv = [&](int tile, int buf) {
+    const int n0 = tile * BLOCK_N;
+    load_tile<DH, NT>(Ks + buf * BLOCK_N * C::LDS, BLOCK_N, [&](int r) -> const bf16* {
+      return (n0 + r) < p.keys ? kb + static_cast<long long>(n0 + r) * p.kv_ts : nullptr;
+    });
+    load_tile<DH, NT>(Vs + buf * BLOCK_N * C::LDS, BLOCK_N, [&](int r) -> const bf16* {
+      return (n0 + r) < p.keys ? vb + static_cast<long long>(n0 + r) * p.kv_ts : nullptr;
+    });
+  };
+  const int ntiles = (p.keys + BLOCK_N - 1) / BLOCK_N;
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o[C::DHP / 8][4];
+#pragma unroll
+  for (int i = 0; i < C::DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  const uint32_t q_addr = smem_u32(Qs + (warp * 16 + (lane & 15)) * C::LDS + (lane >> 4) * 8);
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) {
+      load_kv(it + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    const bf16* Kt = Ks + buf * BLOCK_N * C::LDS;
+    const bf16* Vt = Vs + buf * BLOCK_N * C::LDS;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int ks = 0; ks < C::DHP / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(k_addr + (np * 16 * C::LDS + ks * 16) * 2, b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * np], a, b0, b1);
+        mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+      }
+    }
+    // mask the tail keys of the last tile
+    const int n0 = it * BLOCK_N;
+    if (n0 + BLOCK_N > p.keys) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = n0 + nt * 8 + (lane & 3) * 2;
+        if (key >= p.keys) s[nt][0] = s[nt][2] = -INFINITY;
+        if (key + 1 >= p.keys) s[nt][1] = s[nt][3] = -INFINITY;
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float alpha[2], msc[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      alpha[r] = exp2f((m_run[r] - m_safe) * p.sl2);
+      msc[r] = m_safe * p.sl2;
+      m_run[r] = m_new;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] * p.sl2 - msc[0]);
+      s[nt][1] = exp2f(s[nt][1] * p.sl2 - msc[0]);
+      s[nt][2] = exp2f(s[nt][2] * p.sl2 - msc[1]);
+      s[nt][3] = exp2f(s[nt][3] * p.sl2 - msc[1]);
+      rs[0] += s[nt][0] + s[nt][1];
+      rs[1] += s[nt][2] + s[nt][3];
+    }
+    l_run[0] = l_run[0] * alpha[0] + rs[0];
+    l_run[1] = l_run[1] * alpha[1] + rs[1];
+#pragma unroll
+    for (int i = 0; i < C::DHP / 8; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+    }
+    const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < C::DHP / 16; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(v_addr + (kk * 16 * C::LDS + dp * 16) * 2, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], a, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+  const int row0 = m0 + warp * 16 + (lane >> 2);
+  bf16* ob = p.o + b * p.o_bs + h * p.o_head_off;
+#pragma unroll
+  for (int nt = 0; nt < C::DHP / 8; ++nt) {
+    const int col = nt * 8 + (lane & 3) * 2;
+    if (col < DH) {
+      if (row0 < p.rows)
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row0) * p.o_rs + col) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (row0 + 8 < p.rows)
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row0 + 8) * p.o_rs + col) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------------------
+struct AttnDecodeParams {
+  const bf16* q;        // [B, Hq*dh]
+  const bf16* k_pages;  // [pages, 64, Hkv*dh]
+  const bf16* v_pages;
+  const int* page_table;  // [B, max_pages]
+  const int* kv_len;      // [B]
+  float* ws;              // partial O / (m, l)
+  int B, Hq, Hkv, max_pages, num_splits;
+  float sl2;
+};
+
+// workspace layout: o_part [B][Hq][splits][dh], ml_part [B][Hq][splits][2]
+template <int DH>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const AttnDecodeParams p) {
+  using C = AttnCfg<DH>;
+  constexpr int BLOCK_N = 64;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);  // [16][LDS]
+  bf16* Ks = Qs + 16 * C::LDS;                   // [2][64][LDS]
+  bf16* Vs = Ks + 2 * BLOCK_N * C::LDS;
+  float* red = reinterpret_cast<float*>(Ks);     // reused after the main loop: [4 warps][16][DH+2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int b = blockIdx.y / p.Hkv, hk = blockIdx.y % p.Hkv;
+  const int group = p.Hq / p.Hkv;
+  const int len = p.kv_len[b];
+  const int n_tiles = (len + BLOCK_N - 1) / BLOCK_N;
+  const int tps = (n_tiles + p.num_splits - 1) / p.num_splits;
+  const int t_begin = split * tps, t_end = min(n_tiles, t_begin + tps);
+  const long long kv_ts = static_cast<long long>(p.Hkv) * DH;
+
+  const bf16* qb = p.q + (static_cast<long long>(b) * p.Hq + hk * group) * DH;
+  load_tile<DH, 128>(Qs, 16, [&](int r) -> const bf16* { return r < group ? qb + r * DH : nullptr; });
+  auto load_kv = [&](int tile, int buf) {
+    const int page = p.page_table[b * p.max_pages + tile];
+    const bf16* kb = p.k_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+    const bf16* vb = p.v_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+    const int n0 = tile * BLOCK_N;
+    load_tile<DH, 128>(Ks + buf * BLOCK_N * C::LDS, BLOCK_N, [&](int r) -> const bf16* { return (n0 + r) < len ? kb + r * kv_ts : nullptr; });
+    load_tile<DH, 128>(Vs + buf * BLOCK_N * C::LDS, BLOCK_N, [&](int r) -> const bf16* { return (n0 + r) < len ? vb + r * kv_ts : nullptr; });
+  };
+  if (t_begin < t_end) load_kv(t_begin, 0);
+  cp_async_commit();
+
+  float o[C::DHP / 8][4];
+#pragma unroll
+  for (int i = 0; i < C::DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const uint32_t q_addr = smem_u32(Qs + (lane & 15) * C::LDS + (lane >> 4) * 8);
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) {
+      load_kv(t + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // this warp owns keys [16*warp, 16*warp+16) of the tile
+    const bf16* Kt = Ks + (buf * BLOCK_N + warp * 16) * C::LDS;
+    const bf16* Vt = Vs + (buf * BLOCK_N + warp * 16) * C::LDS;
+    float s[2][4];
+    s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+    const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int ks = 0; ks < C::DHP / 16; ++ks) {
+      uint32_t a[4], b0, b1, b2, b3;
+      ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
+      ldmatrix_x4(k_addr + ks * 32, b0, b1, b2, b3);
+      mma_bf16_16816(s[0], a, b0, b1);
+      mma_bf16_16816(s[1], a, b2, b3);
+    }
+    const int kbase = t * BLOCK_N + warp * 16;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int key = kbase + nt * 8 + (lane & 3) * 2;
+      if (key >= len) s[nt][0] = s[nt][2] = -INFINITY;
+      if (key + 1 >= len) s[nt][1] = s[nt][3] = -INFINITY;
+    }
+    float alpha[2], msc[2], rs[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run[r], mx);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      alpha[r] = exp2f((m_run[r] - m_safe) * p.sl2);
+      msc[r] = m_safe * p.sl2;
+      m_run[r] = m_new;
+      s[0][2 * r] = exp2f(s[0][2 * r] * p.sl2 - msc[r]);
+      s[0][2 * r + 1] = exp2f(s[0][2 * r + 1] * p.sl2 - msc[r]);
+      s[1][2 * r] = exp2f(s[1][2 * r] * p.sl2 - msc[r]);
+      s[1][2 * r + 1] = exp2f(s[1][2 * r + 1] * p.sl2 - msc[r]);
+      rs[r] = s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
+      l_run[r] = l_run[r] * alpha[r] + rs[r];
+    }
+#pragma unroll
+    for (int i = 0; i < C::DHP / 8; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+    }
+    uint32_t a[4];
+    a[0] = pack_bf16(s[0][0], s[0][1]);
+    a[1] = pack_bf16(s[0][2], s[0][3]);
+    a[2] = pack_bf16(s[1][0], s[1][1]);
+    a[3] = pack_bf16(s[1][2], s[1][3]);
+    const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
+#pragma unroll
+    for (int dp = 0; dp < C::DHP / 16; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(v_addr + dp * 32, b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * dp], a, b0, b1);
+      mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- combine the 4 warps (each saw a disjoint key subset) through shared memory ----
+  constexpr int RLD = DH + 2;  // [.., DH] = m (scaled), [.., DH+1] = l
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  {
+    const int row = lane >> 2;  // only rows < group (<= 8 of 16) matter; row+8 is padding when group <= 8
+    float* dst0 = red + (warp * 16 + row) * RLD;
+    float* dst1 = red + (warp * 16 + row + 8) * RLD;
+#pragma unroll
+    for (int nt = 0; nt < C::DHP / 8; ++nt) {
+      const int col = nt * 8 + (lane & 3) * 2;
+      if (col < DH) {
+        dst0[col] = o[nt][0]; dst0[col + 1] = o[nt][1];
+        dst1[col] = o[nt][2]; dst1[col + 1] = o[nt][3];
+      }
+    }
+    if ((lane & 3) == 0) {
+      dst0[DH] = m_run[0] * p.sl2; dst0[DH + 1] = l_run[0];
+      dst1[DH] = m_run[1] * p.sl2; dst1[DH + 1] = l_run[1];
+    }
+  }
+  __syncthreads();
+  float* ws_o = p.ws;
+  float* ws_ml = p.ws + static_cast<long long>(p.B) * p.Hq * p.num_splits * DH;
+  for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
+    const int row = idx / DH, col = idx % DH;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 16 + row) * RLD + DH]);
+    const float Ms = (M == -INFINITY) ? 0.f : M;
+    float acc = 0.f, L = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float wgt = exp2f(red[(w * 16 + row) * RLD + DH] - Ms);
+      acc += red[(w * 16 + row) * RLD + col] * wgt;
+      L += red[(w * 16 + row) * RLD + DH + 1] * wgt;
+    }
+    const long long hrow = (static_cast<long long>(b) * p.Hq + hk * group + row) * p.num_splits + split;
+    ws_o[hrow * DH + col] = acc;
+    if (col == 0) {
+      ws_ml[hrow * 2] = M;
+      ws_ml[hrow * 2 + 1] = L;
+    }
+  }
+}
+
+// out[b, h*dh + c] = sum_s O_s w_s / sum_s L_s w_s,  w_s = 2^(m_s - max m)
+__global__ void attn_decode_combine_kernel(const float* ws, bf16* out, int B, int Hq, int dh, int num_splits) {
+  const int bh = blockIdx.x;
+  const float* ws_o = ws + static_cast<long long>(bh) * num_splits * dh;
+  const float* ws_ml = ws + static_cast<long long>(B) * Hq * num_splits * dh + static_cast<long long>(bh) * num_splits * 2;
+  float M = -INFINITY;
+  for (int s = 0; s < num_splits; ++s) M = fmaxf(M, ws_ml[2 * s]);
+  float L = 0.f;
+  for (int s = 0; s < num_splits; ++s) L += ws_ml[2 * s + 1] * exp2f(ws_ml[2 * s] - M);
+  const float inv = 1.f / L;
+  for (int c = threadIdx.x; c < dh; c += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < num_splits; ++s) acc += ws_o[s * dh + c] * exp2f(ws_ml[2 * s] - M);
+    out[static_cast<long long>(bh) * dh + c] = __float2bfloat16(acc * inv);
+  }
+}
+
+template <int DH, int NWARPS>
+static int launch_prefill(const AttnPrefillParams& p, int B, int H, cudaStream_t st) {
+  using C = AttnCfg<DH>;
+  constexpr int BLOCK_M = NWARPS * 16;
+  constexpr int smem = (BLOCK_M + 4 * 64) * C::LDS * 2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_prefill_kernel<DH, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PG_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((p.rows + BLOCK_M - 1) / BLOCK_M, H, B);
+  attn_prefill_kernel<DH, NWARPS><<<grid, NWARPS * 32, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
+template <int DH>
+static int launch_decode(const AttnDecodeParams& p, bf16* out, cudaStream_t st) {
+  using C = AttnCfg<DH>;
+  constexpr int smem_main = (16 + 4 * 64) * C::LDS * 2;
+  constexpr int smem_red = 16 * C::LDS * 2 + 4 * 16 * (DH + 2) * 4;
+  constexpr int smem = smem_main > smem_red ? smem_main : smem_red;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_decode_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PG_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid(p.num_splits, p.B * p.Hkv);
+  attn_decode_kernel<DH><<<grid, 128, smem, st>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return PG_ERR_CUDA;
+  attn_decode_combine_kernel<<<p.B * p.Hq, DH >= 128 ? 128 : 64, 0, st>>>(p.ws, out, p.B, p.Hq, DH, p.num_splits);
+  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys,
+                                    int dh, int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off,
+                                    long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_rs,
+                                    long long o_head_off, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || rows <= 0 || keys <= 0 || group <= 0) return PG_ERR_ARG;
+  if ((q_bs | q_ts | q_hs | q_head_off | kv_bs | kv_ts | kv_head_off) & 7) return PG_ERR_ARG;  // 16 B cp.async granularity
+  if ((o_bs | o_rs | o_head_off) & 1) return PG_ERR_ARG;
+  if (B > 65535 || H > 65535) return PG_ERR_ARG;
+  AttnPrefillParams p;
+  p.q = static_cast<const bf16*>(q); p.k = static_cast<const bf16*>(k); p.v = static_cast<const bf16*>(v);
+  p.o = static_cast<bf16*>(o);
+  p.rows = rows; p.keys = keys; p.group = group;
+  p.q_bs = q_bs; p.q_ts = q_ts; p.q_hs = q_hs; p.q_head_off = q_head_off;
+  p.kv_bs = kv_bs; p.kv_ts = kv_ts; p.kv_head_off = kv_head_off;
+  p.o_bs = o_bs; p.o_rs = o_rs; p.o_head_off = o_head_off;
+  p.sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dh) {
+    case 64: return launch_prefill<64, 8>(p, B, H, st);
+    case 72: return launch_prefill<72, 8>(p, B, H, st);
+    case 256: return launch_prefill<256, 8>(p, B, H, st);
+    default: return PG_ERR_ARG;
+  }
+}
+
+extern "C" long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_splits) {
+  return static_cast<long long>(B) * Hq * num_splits * (dh + 2);
+}
+
+extern "C" int pg_attention_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table,
+                                   const int* kv_len, void* out, float* workspace, int B, int Hq, int Hkv, int dh,
+                                   int page_size, int max_pages, int num_splits, float scale, void* stream) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || num_splits <= 0) return PG_ERR_ARG;
+  AttnDecodeParams p;
+  p.q = static_cast<const bf16*>(q);
+  p.k_pages = static_cast<const bf16*>(k_pages);
+  p.v_pages = static_cast<const bf16*>(v_pages);
+  p.page_table = page_table; p.kv_len = kv_len; p.ws = workspace;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages; p.num_splits = num_splits;
+  p.sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dh) {
+    case 64: return launch_decode<64>(p, static_cast<bf16*>(out), st);
+    case 256: return launch_decode<256>(p, static_cast<bf16*>(out), st);
+    default: return PG_ERR_ARG;
+  }
+}

@@ -1,0 +1,473 @@
+// tcgen05 / TMEM / TMA GEMM for every Linear on the PaliGemma hot path.
+//
+//   acc[t, f] = sum_k X[t, k] * W[f, k]          X: activations [tokens, K] bf16, W: nn.Linear weight [features, K] bf16
+//
+// Replaces the reference's nn.Linear / nn.Conv2d(im2col) call sites:
+//   modeling_siglip.py:59-62,71-75,156,177-185,258-263   modeling_paligemma.py:57,64
+//   modeling_gemma.py:205-218,255-259,274-278,356,484,523
+//
+// One persistent, warp-specialised kernel (warp 0 = TMA producer, warp 1 = tcgen05.mma issuer + TMEM owner,
+// warps 2..5 = epilogue).  Operands are staged by TMA into 128B-swizzled shared memory; the fp32 accumulator
+// lives in TMEM (double buffered, so the epilogue of tile i overlaps the main loop of tile i+1).
+//
+//   SWAP = false (prefill, many tokens):  UMMA M = 128 tokens,   N = BN features
+//   SWAP = true  (decode, tokens <= 128): UMMA M = 128 features, N = BN tokens  (weight streaming, HBM bound),
+//                                         optional split-K with fp32 red.global.add into the output
+#include "common.cuh"
+#include "paligemma_b200.h"
+
+namespace pg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int ACC_STAGES = 2;
+
+__host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
+__host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * (BN + 1) * 4 : 0; }
+__host__ __device__ constexpr int num_stages(int BN, bool swap) {
+  int s = (200 * 1024 - xch_bytes(BN, swap)) / stage_bytes(BN);
+  return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int tmem_cols(int BN) {
+  int c = ACC_STAGES * BN;
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+__host__ __device__ constexpr int smem_bytes(int BN, bool swap) {
+  return num_stages(BN, swap) * stage_bytes(BN) + xch_bytes(BN, swap) + 256 /*barriers*/ + 1024 /*alignment slack*/;
+}
+
+struct GemmArgs {
+  int tokens, features, K;
+  int split_k;
+  int mode, act_gelu;
+  float scale;
+  void* out;
+  long long ldo;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+};
+
+struct TileInfo {
+  int m_blk, n_blk, kb0, kb1;
+};
+
+PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_kb, int split_k) {
+  TileInfo t;
+  t.m_blk = tile % m_blocks;
+  int rest = tile / m_blocks;
+  t.n_blk = rest % n_blocks;
+  int split = rest / n_blocks;
+  int kb_per = (total_kb + split_k - 1) / split_k;
+  t.kb0 = split * kb_per;
+  t.kb1 = min(total_kb, t.kb0 + kb_per);
+  return t;
+}
+
+PG_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int BN, bool SWAP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const GemmArgs args) {
+  constexpr int STAGES = num_stages(BN, SWAP);
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  constexpr int STAGE_BYTES = stage_bytes(BN);
+  constexpr int TMEM_COLS = tmem_cols(BN);
+  constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024 B alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* xch = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES);
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + xch_bytes(BN, SWAP);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + xch_bytes(BN, SWAP) + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int rowsA = SWAP ? args.features : args.tokens;
+  const int rowsB = SWAP ? args.tokens : args.features;
+  const int m_blocks = (rowsA + BM - 1) / BM;
+  const int n_blocks = (rowsB + BN - 1) / BN;
+  const int total_kb = (args.K + BK - 1) / BK;
+  const int num_tiles = m_blocks * n_blocks * args.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // =================================== TMA producer ===================================
+    if (lane == 0) {
+      // weights are streamed once in decode (evict first); activations are re-read by every CTA (evict last)
+      const uint64_t hintA = SWAP ? kEvictFirst : kEvictNormal;
+      const uint64_t hintB = SWAP ? kEvictLast : kEvictNormal;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
+          tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== MMA issuer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_sdesc_k_sw128(sa);
+          const uint64_t bdesc = make_sdesc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (kb == t.kb1 - 1) umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =================================== epilogue warps =================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int mode = args.mode;
+    __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
+    float* out_f = reinterpret_cast<float*>(args.out);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const int rl = q * 32 + lane;  // row inside the tile
+      const bool first_split = (t.kb0 == 0);
+
+      if constexpr (!SWAP) {
+        const int tok = t.m_blk * BM + rl;
+        const bool row_ok = tok < args.tokens;
+        if (mode == PG_EPI_GEGLU) {
+          // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c
+#pragma unroll 1
+          for (int blk = 0; blk < BN / 128; ++blk) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+              uint32_t g[16], u[16];
+              tmem_ld16(taddr + blk * 128 + c0, g);
+              tmem_ld16(taddr + blk * 128 + 64 + c0, u);
+              tmem_ld_wait();
+              const int f0 = t.n_blk * (BN / 2) + blk * 64 + c0;
+              if (row_ok && f0 < args.features / 2) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float a = gelu_tanh(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
+                  float b = gelu_tanh(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
+                  pk[i] = pack_bf16(a, b);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out_bf + static_cast<long long>(tok) * args.ldo + f0);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            const int f0 = t.n_blk * BN + c0;
+            if (f0 >= args.features) break;  // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            float v[16];
+            const bool full = (f0 + 16 <= args.features);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(r[i]);
+              if (args.bias != nullptr && first_split && (full || f0 + i < args.features)) x += __ldg(args.bias + f0 + i);
+              v[i] = x * args.scale;
+            }
+            if (mode == PG_EPI_BF16) {
+              if (args.act_gelu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_tanh(v[i]);
+              }
+              __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
+              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                d4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                d4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              } else {
+                for (int i = 0; i < 16; ++i)
+                  if (f0 + i < args.features) dst[i] = __float2bfloat16(v[i]);
+              }
+            } else if (mode == PG_EPI_F32) {
+              float* dst = out_f + static_cast<long long>(tok) * args.ldo + f0;
+              const float* res = args.resid ? args.resid + static_cast<long long>(tok) * args.ldr + f0 : nullptr;
+              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                  (res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+                if (res) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float4 rr = *reinterpret_cast<const float4*>(res + 4 * i);
+                    v[4 * i] += rr.x; v[4 * i + 1] += rr.y; v[4 * i + 2] += rr.z; v[4 * i + 3] += rr.w;
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else {
+                for (int i = 0; i < 16; ++i)
+                  if (f0 + i < args.features) dst[i] = v[i] + (res ? res[i] : 0.f);
+              }
+            } else {  // PG_EPI_ATOMIC_F32
+              float* dst = out_f + static_cast<long long>(tok) * args.ldo + f0;
+              for (int i = 0; i < 16; ++i)
+                if (f0 + i < args.features) atomicAdd(dst + i, v[i]);
+            }
+          }
+        }
+      } else {
+        // SWAP: this thread owns weight row (feature) fr; columns are tokens
+        const int fr = t.m_blk * BM + rl;
+        const int j_base = t.n_blk * BN;
+        if (mode == PG_EPI_GEGLU) {
+          // packed rows: [64 gate | 64 up] per 128-row tile; out feature = m_blk*64 + rl%64
+          if (q >= 2) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+              if (j_base + c0 >= args.tokens) break;
+              uint32_t r[16];
+              tmem_ld16(taddr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xch[(rl - 64) * (BN + 1) + c0 + i] = __uint_as_float(r[i]);
+            }
+          }
+          named_bar_sync(1, 128);
+          if (q < 2) {
+            const int fo = t.m_blk * 64 + rl;
+            const bool f_ok = fo < args.features / 2;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+              if (j_base + c0 >= args.tokens) break;
+              uint32_t r[16];
+              tmem_ld16(taddr + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int j = j_base + c0 + i;
+                if (f_ok && j < args.tokens) {
+                  float val = gelu_tanh(__uint_as_float(r[i])) * xch[rl * (BN + 1) + c0 + i];
+                  out_bf[static_cast<long long>(j) * args.ldo + fo] = __float2bfloat16(val);
+                }
+              }
+            }
+          }
+          named_bar_sync(1, 128);
+        } else {
+          const bool f_ok = fr < args.features;
+          const float bias = (args.bias != nullptr && f_ok && first_split) ? __ldg(args.bias + fr) : 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (j_base + c0 >= args.tokens) break;  // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (!f_ok) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int j = j_base + c0 + i;
+              if (j < args.tokens) {
+                float x = (__uint_as_float(r[i]) + bias) * args.scale;
+                const long long o = static_cast<long long>(j) * args.ldo + fr;
+                if (mode == PG_EPI_BF16) {
+                  if (args.act_gelu) x = gelu_tanh(x);
+                  out_bf[o] = __float2bfloat16(x);
+                } else if (mode == PG_EPI_F32) {
+                  if (args.resid) x += args.resid[static_cast<long long>(j) * args.ldr + fr];
+                  out_f[o] = x;
+                } else {
+                  atomicAdd(out_f + o, x);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || p == nullptr)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, K] (row pitch ld elements), box = [box_rows, 64], 128B swizzle, OOB -> zeros
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, long long rows, long long K, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return PG_ERR_DRIVER;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool SWAP>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
+  static bool configured = false;
+  constexpr int smem = smem_bytes(BN, SWAP);
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();  // do not leave a sticky error behind
+      return PG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_tcgen05_kernel<BN, SWAP><<<grid, NUM_THREADS, smem, st>>>(ta, tb, a);
+  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                            const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
+                            int mode, int act_gelu, float scale, int swap, int split_k, void* stream) {
+  if (tokens <= 0 || features <= 0 || K <= 0) return PG_ERR_ARG;
+  if ((K % 8) != 0 || (ldx % 8) != 0 || (ldw % 8) != 0) return PG_ERR_ARG;  // TMA: 16 B pitch granularity
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return PG_ERR_ARG;
+  if (mode < PG_EPI_BF16 || mode > PG_EPI_GEGLU) return PG_ERR_ARG;
+  if (mode == PG_EPI_GEGLU && (features % 128) != 0) return PG_ERR_ARG;
+  if (swap < 0) swap = tokens <= 128 ? 1 : 0;
+  if (swap && tokens > 128) return PG_ERR_ARG;
+  const int total_kb = (K + BK - 1) / BK;
+  if (split_k <= 0) split_k = 1;
+  if (mode != PG_EPI_ATOMIC_F32) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  {  // no empty splits
+    int kb_per = (total_kb + split_k - 1) / split_k;
+    split_k = (total_kb + kb_per - 1) / kb_per;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  GemmArgs a;
+  a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
+  a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (swap) {
+    int BN = tokens <= 16 ? 16 : tokens <= 32 ? 32 : tokens <= 64 ? 64 : 128;
+    if ((rc = make_tmap_2d(&ta, w, features, K, ldw, BM)) != PG_OK) return rc;
+    if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
+    const int tiles = ((features + BM - 1) / BM) * split_k;
+    switch (BN) {
+      case 16: return launch<16, true>(ta, tb, a, tiles, st);
+      case 32: return launch<32, true>(ta, tb, a, tiles, st);
+      case 64: return launch<64, true>(ta, tb, a, tiles, st);
+      default: return launch<128, true>(ta, tb, a, tiles, st);
+    }
+  } else {
+    int BN = (mode == PG_EPI_GEGLU) ? (features >= 256 ? 256 : 128) : (features > 128 ? 256 : features > 64 ? 128 : 64);
+    if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
+    if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
+    const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;
+    switch (BN) {
+      case 64: return launch<64, false>(ta, tb, a, tiles, st);
+      case 128: return launch<128, false>(ta, tb, a, tiles, st);
+      default: return launch<256, false>(ta, tb, a, tiles, st);
+    }
+  }
+}

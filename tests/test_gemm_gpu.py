@@ -1,0 +1,128 @@
+"""tcgen05 GEMM (pg_gemm_bf16) against a plain PyTorch fp32 reference of the same op, through the C ABI."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w):
+    return x.float() @ w.float().t()
+
+
+def _mk(T, F, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(T, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(F, K, device="cuda", generator=g) * 0.05).bfloat16()
+    return x, w
+
+
+def _close(a, b, tol, what):
+    err = (a.float() - b.float()).abs().max().item()
+    ref = b.float().abs().max().item()
+    assert err <= tol * max(ref, 1e-6), f"{what}: max-abs err {err:.4g} vs ref absmax {ref:.4g}"
+
+
+SHAPES = [
+    # (tokens, features, K)
+    (128, 256, 64), (128, 256, 256), (260, 2560, 2048), (300, 1281, 256), (1024, 4304, 1152), (512, 1152, 4304),
+    (256, 1152, 640), (130, 64, 128),
+]
+
+
+@pytest.mark.parametrize("T,F,K", SHAPES)
+def test_gemm_prefill_bf16_out(T, F, K):
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K)
+    bias = torch.randn(F, device="cuda")
+    out = torch.full((T, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(x, w, out, mode=_lib.EPI_BF16, bias=bias, swap=0)
+    torch.cuda.synchronize()
+    _close(out, _ref(x, w) + bias, 1e-2, "bf16 out")
+
+
+@pytest.mark.parametrize("T,F,K", SHAPES[:5])
+def test_gemm_prefill_f32_resid(T, F, K):
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K, 1)
+    bias = torch.randn(F, device="cuda")
+    resid = torch.randn(T, F, device="cuda")
+    out = torch.full((T, F), float("nan"), device="cuda")
+    _lib.gemm(x, w, out, mode=_lib.EPI_F32, bias=bias, resid=resid, scale=1.0, swap=0)
+    torch.cuda.synchronize()
+    _close(out, _ref(x, w) + bias + resid, 2e-3, "f32 resid out")
+    # in place on the residual stream
+    r2 = resid.clone()
+    _lib.gemm(x, w, r2, mode=_lib.EPI_F32, bias=bias, resid=r2, swap=0)
+    torch.cuda.synchronize()
+    _close(r2, _ref(x, w) + bias + resid, 2e-3, "f32 in-place resid")
+
+
+def test_gemm_gelu():
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(384, 4304, 1152, 2)
+    bias = torch.randn(4304, device="cuda") * 0.1
+    out = torch.empty(384, 4304, device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(x, w, out, mode=_lib.EPI_BF16, bias=bias, act_gelu=True, swap=0)
+    torch.cuda.synchronize()
+    _close(out, torch.nn.functional.gelu(_ref(x, w) + bias, approximate="tanh"), 1e-2, "gelu")
+
+
+@pytest.mark.parametrize("T", [1, 8, 16, 17, 64, 100, 128])
+@pytest.mark.parametrize("F,K", [(2560, 2048), (1281, 256), (2048, 16384)])
+def test_gemm_swap_f32(T, F, K):
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K, 3)
+    bias = torch.randn(F, device="cuda")
+    out = torch.full((T, F), float("nan"), device="cuda")
+    _lib.gemm(x, w, out, mode=_lib.EPI_F32, bias=bias, scale=0.5, swap=1)
+    torch.cuda.synchronize()
+    _close(out, (_ref(x, w) + bias) * 0.5, 2e-3, "swap f32")
+    outb = torch.empty(T, F, device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(x, w, outb, mode=_lib.EPI_BF16, swap=1)
+    torch.cuda.synchronize()
+    _close(outb, _ref(x, w), 1e-2, "swap bf16")
+
+
+@pytest.mark.parametrize("T,split", [(1, 4), (64, 8), (64, 37), (128, 3)])
+def test_gemm_swap_splitk_atomic(T, split):
+    from paligemma_multimodal_system_b200 import _lib
+    F, K = 2048, 16384
+    x, w = _mk(T, F, K, 4)
+    resid = torch.randn(T, F, device="cuda")
+    out = resid.clone()
+    _lib.gemm(x, w, out, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=split)
+    torch.cuda.synchronize()
+    _close(out, _ref(x, w) + resid, 2e-3, "split-K atomic")
+
+
+def _pack(gate, up):
+    from paligemma_multimodal_system_b200 import _lib
+    F, K = gate.shape
+    packed = torch.empty(2 * F, K, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().pg_pack_gate_up(gate.data_ptr(), up.data_ptr(), packed.data_ptr(), F, K, _lib.stream()), "pack")
+    return packed
+
+
+@pytest.mark.parametrize("T,swap", [(1, 1), (64, 1), (128, 1), (256, 0), (260, 0), (1000, 0)])
+@pytest.mark.parametrize("F,K", [(1024, 256), (16384, 2048)])
+def test_gemm_geglu(T, swap, F, K):
+    from paligemma_multimodal_system_b200 import _lib
+    x, gate = _mk(T, F, K, 5)
+    _, up = _mk(T, F, K, 6)
+    packed = _pack(gate, up)
+    # the packing itself
+    ref_packed = torch.stack([gate.view(F // 64, 64, K), up.view(F // 64, 64, K)], 1).reshape(2 * F, K)
+    assert torch.equal(packed, ref_packed)
+    out = torch.full((T, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(x, packed, out, mode=_lib.EPI_GEGLU, swap=swap)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(_ref(x, gate), approximate="tanh") * _ref(x, up)
+    _close(out, ref, 1.5e-2, "geglu")
+
+
+def test_gemm_rejects_bad_args():
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(16, 64, 60)  # K % 8 != 0
+    out = torch.empty(16, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        _lib.gemm(x, w, out, mode=_lib.EPI_BF16)
