@@ -71,13 +71,14 @@ int pg_add_pos_emb(float* x, const float* pos, int B, int N, int D, void* stream
 /*
  * Non-causal softmax(Q K^T * scale) V, flash style (modeling_siglip.py:96-136; modeling_gemma.py:307-339 prefill
  * with the all-zero mask of modeling_paligemma.py:154-156).  bf16 in/out, fp32 softmax.
- * Row r of batch b, head h:  q + b*q_bs + (r / group)*q_ts + (r % group)*q_hs + h*q_head_off ; K/V rows: k + b*kv_bs + n*kv_ts + h*kv_head_off.
- * out: o + b*o_bs + r*o_rs + h*o_head_off.   dh in {64, 72, 256}.
+ * Row r of batch b, head h:  q + b*q_bs + (r / group)*q_ts + (r % group)*q_hs + h*q_head_off  (same for o);
+ * K/V rows: k + b*kv_bs + n*kv_ts + h*kv_head_off.  `group` > 1 stacks the query heads of one KV head as consecutive
+ * rows (MQA/GQA, replaces repeat_kv modeling_gemma.py:185-196).  All strides in elements.  dh in {64, 72, 256}.
  */
 int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
                          int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off,
-                         long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_rs,
-                         long long o_head_off, float scale, void* stream);
+                         long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts,
+                         long long o_hs, long long o_head_off, float scale, void* stream);
 
 /*
  * RoPE + KV append (modeling_gemma.py:116-151,285-302 and KVCache.update :18-57): reads qkv [T, (Hq+2Hkv)*dh]

@@ -29,7 +29,7 @@ SIGNATURES = {
     "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_add_pos_emb": [p, p, i32, i32, i32, p],
-    "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
+    "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
     "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],

@@ -22,7 +22,7 @@ struct AttnPrefillParams {
   const bf16* v;
   bf16* o;
   int rows, keys, group;
-  long long q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts, kv_head_off, o_bs, o_rs, o_head_off;
+  long long q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts, kv_head_off, o_bs, o_ts, o_hs, o_head_off;
   float sl2;  // softmax scale * log2(e)
 };
 
@@ -189,14 +189,16 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_prefill_kernel(const AttnPre
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
   const int row0 = m0 + warp * 16 + (lane >> 2);
   bf16* ob = p.o + b * p.o_bs + h * p.o_head_off;
+  const long long off0 = (row0 / p.group) * p.o_ts + (row0 % p.group) * p.o_hs;
+  const long long off1 = ((row0 + 8) / p.group) * p.o_ts + ((row0 + 8) % p.group) * p.o_hs;
 #pragma unroll
   for (int nt = 0; nt < C::DHP / 8; ++nt) {
     const int col = nt * 8 + (lane & 3) * 2;
     if (col < DH) {
       if (row0 < p.rows)
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row0) * p.o_rs + col) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
+        *reinterpret_cast<uint32_t*>(ob + off0 + col) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
       if (row0 + 8 < p.rows)
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row0 + 8) * p.o_rs + col) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+        *reinterpret_cast<uint32_t*>(ob + off1 + col) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
 }
@@ -435,11 +437,11 @@ using namespace pg;
 
 extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys,
                                     int dh, int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off,
-                                    long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_rs,
-                                    long long o_head_off, float scale, void* stream) {
+                                    long long kv_bs, long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts,
+                                    long long o_hs, long long o_head_off, float scale, void* stream) {
   if (B <= 0 || H <= 0 || rows <= 0 || keys <= 0 || group <= 0) return PG_ERR_ARG;
   if ((q_bs | q_ts | q_hs | q_head_off | kv_bs | kv_ts | kv_head_off) & 7) return PG_ERR_ARG;  // 16 B cp.async granularity
-  if ((o_bs | o_rs | o_head_off) & 1) return PG_ERR_ARG;
+  if ((o_bs | o_ts | o_hs | o_head_off) & 1) return PG_ERR_ARG;
   if (B > 65535 || H > 65535) return PG_ERR_ARG;
   AttnPrefillParams p;
   p.q = static_cast<const bf16*>(q); p.k = static_cast<const bf16*>(k); p.v = static_cast<const bf16*>(v);
@@ -447,7 +449,7 @@ extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v,
   p.rows = rows; p.keys = keys; p.group = group;
   p.q_bs = q_bs; p.q_ts = q_ts; p.q_hs = q_hs; p.q_head_off = q_head_off;
   p.kv_bs = kv_bs; p.kv_ts = kv_ts; p.kv_head_off = kv_head_off;
-  p.o_bs = o_bs; p.o_rs = o_rs; p.o_head_off = o_head_off;
+  p.o_bs = o_bs; p.o_ts = o_ts; p.o_hs = o_hs; p.o_head_off = o_head_off;
   p.sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {

@@ -1,0 +1,284 @@
+"""PaliGemmaForConditionalGeneration with the reference's API (modeling_paligemma.py:14-307) on sm_100a kernels.
+
+forward(input_ids, pixel_values, attention_mask, kv_cache) -> {"logits": fp32 [B,S,V], "kv_cache": KVCache}
+
+Prefill (kv_cache is None or empty): SigLIP tower -> projector GEMM -> fused embedding-gather/image-merge/position-id
+kernel -> Gemma prefill.  Decode (q_len == 1): the vision tower is NOT re-run (the reference re-runs it and throws the
+result away, modeling_paligemma.py:281-282; skipping it is output-identical) -> token embedding -> Gemma decode step.
+`generate()` is the batched, device-side version of the inference.py loop (CUDA-graph replay of one decode step).
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modeling_gemma import GemmaConfig, GemmaForCausalLM, KVCache
+from .modeling_siglip import SiglipVisionConfig, SiglipVisionModel, _ParamsOnly, _bf16
+
+
+class PaliGemmaConfig:
+    """Same keyword arguments, defaults and derived fields as modeling_paligemma.py:14-44."""
+
+    def __init__(self, vision_config=None, text_config=None, projection_dim=2048, ignore_index=-100,
+                 image_token_index=256000, pad_token_id=None, vocab_size=257152, hidden_size=2048, **kwargs):
+        self.projection_dim = projection_dim
+        self.ignore_index = ignore_index
+        self.image_token_index = image_token_index
+        self.pad_token_id = pad_token_id
+        self.hidden_size = hidden_size
+        self.vision_config = SiglipVisionConfig(**vision_config)
+        self.text_config = GemmaConfig(**text_config, pad_token_id=self.pad_token_id)
+        self.vocab_size = self.text_config.vocab_size
+        self.text_config.num_image_tokens = (self.vision_config.image_size // self.vision_config.patch_size) ** 2
+        self.vision_config.projection_dim = projection_dim
+        # the reference's loop reads this (inference.py:134); its own config leaves it None unless given
+        if self.vision_config.num_image_tokens is None:
+            self.vision_config.num_image_tokens = self.text_config.num_image_tokens
+
+
+class PaliGemmaMultiModalProjector(_ParamsOnly):
+    def __init__(self, config: PaliGemmaConfig, **fk):
+        super().__init__()
+        self.linear = nn.Linear(config.vision_config.hidden_size, config.projection_dim, bias=False, **fk)
+
+
+class PaliGemmaForConditionalGeneration(nn.Module):
+    def __init__(self, config: PaliGemmaConfig, device=None, dtype=None):
+        super().__init__()
+        fk = {k: v for k, v in dict(device=device, dtype=dtype).items() if v is not None}
+        self.config = config
+        self.vision_config = config.vision_config
+        self.text_config = config.text_config
+        if config.projection_dim != config.text_config.hidden_size:
+            raise ValueError("projection_dim must equal the text hidden_size (image features are merged into text embeddings)")
+        self.vision_tower = SiglipVisionModel(self.vision_config, device=device, dtype=dtype)
+        self.language_model = GemmaForCausalLM(self.text_config, device=device, dtype=dtype)
+        self.multi_modal_projector = PaliGemmaMultiModalProjector(config, **fk)
+        self.pad_token_id = config.pad_token_id if config.pad_token_id is not None else -1
+        self.dummy_image_token_id = config.image_token_index
+        self._proj_w = None
+        self._graphs = {}
+
+    def tie_weights(self):
+        return self.language_model.tie_weights()
+
+    def _apply(self, fn, *a, **k):
+        self._proj_w = None
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._proj_w = None
+        self._graphs = {}
+        self.vision_tower._packed = None
+        self.language_model._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def pack(self):
+        """Packs every weight for the kernels (bf16, fused layouts).  Called lazily by forward/generate."""
+        self.vision_tower.pack()
+        self.language_model.pack()
+        self._proj_w = _bf16(self.multi_modal_projector.linear.weight)
+        return self
+
+    # -- pieces ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def image_features(self, pixel_values):
+        """vision tower + bias-free projector (modeling_paligemma.py:60-65,281-282) -> fp32 [B, N, D] (unscaled)."""
+        if self._proj_w is None:
+            self._proj_w = _bf16(self.multi_modal_projector.linear.weight)
+        B = pixel_values.shape[0]
+        feats = self.vision_tower.forward_features(pixel_values, out_bf16=True)
+        out = torch.empty(feats.shape[0], self.config.projection_dim, device=feats.device, dtype=torch.float32)
+        _lib.gemm(feats, self._proj_w, out, mode=_lib.EPI_F32, swap=0 if feats.shape[0] > 128 else 1)
+        return out.view(B, -1, self.config.projection_dim)
+
+    @torch.no_grad()
+    def _merge(self, input_ids, attention_mask, img):
+        """_merge_input_ids_with_image_features (modeling_paligemma.py:201-251) + the sqrt(D) normaliser of
+        modeling_gemma.py:510-511 in one kernel pair.  Returns h fp32 [B*S, D], pos int32 [B*S]."""
+        pk = self.language_model._packed or self.language_model.pack()
+        B, S = input_ids.shape
+        D = self.text_config.hidden_size
+        N = img.shape[1]
+        dev = img.device
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        mask = attention_mask.to(device=dev).to(torch.int64).contiguous()
+        V = self.text_config.vocab_size
+        if bool(((ids < 0) | (ids >= V)).any()):
+            raise IndexError("input_ids out of range for the embedding table")
+        h = torch.empty(B * S, D, device=dev, dtype=torch.float32)
+        pos = torch.empty(B * S, device=dev, dtype=torch.int32)
+        src = torch.empty(B * S, device=dev, dtype=torch.int32)
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        img_scale = (self.config.projection_dim ** -0.5) * (D ** 0.5)
+        _lib.check(_lib.lib().pg_merge_embeddings(
+            ids.data_ptr(), mask.data_ptr(), pk["embed"].data_ptr(), img.data_ptr(), h.data_ptr(), pos.data_ptr(),
+            src.data_ptr(), err.data_ptr(), B, S, D, N, self.dummy_image_token_id, self.pad_token_id, D ** 0.5, img_scale,
+            _lib.stream()), "pg_merge_embeddings")
+        if int(err.item()) != 0:
+            raise ValueError(f"every row of input_ids must hold exactly {N} image tokens (id {self.dummy_image_token_id})")
+        return h, pos
+
+    @torch.no_grad()
+    def _embed_step(self, tokens_i32, kv_cache, h_out):
+        pk = self.language_model._packed or self.language_model.pack()
+        D = self.text_config.hidden_size
+        img = kv_cache.image_feats
+        _lib.check(_lib.lib().pg_embed_tokens(
+            tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), h_out.data_ptr(), tokens_i32.shape[0], D,
+            0 if img is None else img.shape[1], D ** 0.5, (self.config.projection_dim ** -0.5) * (D ** 0.5), self.pad_token_id,
+            self.dummy_image_token_id, _lib.stream()), "pg_embed_tokens")
+
+    # -- reference forward ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids: torch.LongTensor = None, pixel_values: torch.FloatTensor = None,
+                attention_mask: Optional[torch.Tensor] = None, kv_cache: Optional[KVCache] = None, last_only: bool = False):
+        _lib.require_device()
+        B, S = input_ids.shape
+        lm = self.language_model
+        c = self.text_config
+        decode = kv_cache is not None and kv_cache.num_items() > 0
+        if not decode:
+            img = self.image_features(pixel_values)
+            h, pos = self._merge(input_ids, attention_mask, img)
+            if kv_cache is not None:
+                kv_cache.image_feats = img
+            logits = lm.prefill(h, pos, B, S, kv_cache, last_only=last_only)
+        else:
+            assert S == 1, "Generation Phase more than one token CAN'T be input"
+            n = kv_cache.num_items()
+            kv_cache.ensure_capacity(n + 1)
+            # position of the new token = number of ones in the grown mask (modeling_paligemma.py:189), per row
+            pos = attention_mask.to("cuda").sum(-1).to(torch.int32)
+            kv_cache.counters[0].copy_(pos)
+            kv_cache.counters[1].fill_(n)
+            kv_cache.counters[2].fill_(n + 1)
+            bufs = lm.decode_buffers(B)
+            tok = input_ids.to(device="cuda", dtype=torch.int32).reshape(B).contiguous()
+            self._embed_step(tok, kv_cache, bufs["h"])
+            logits = lm.decode_layers(bufs, kv_cache, B).clone().view(B, 1, -1)
+            kv_cache._set_len(n + 1, c.num_hidden_layers)
+        out = {"logits": logits}
+        if kv_cache is not None:
+            out["kv_cache"] = kv_cache
+        return out
+
+    # -- batched device-side generation (inference.py:45-79 for B rows) --------------------------------------------------
+    def _gen_state(self, key, B, S, T, V):
+        """Static device buffers (+ the captured decode-step graph) for one generation geometry; reused across calls so
+        that graph capture is paid once per (batch, lengths, sampling) configuration."""
+        stt = self._graphs.get(key)
+        if stt is None:
+            dev = torch.device("cuda")
+            c = self.text_config
+            kv = KVCache(reserve_tokens=T + 1)
+            kv.allocate(B, c.num_hidden_layers, c.num_key_value_heads, c.head_dim, S + T + 1)
+            stt = dict(kv=kv, nxt=torch.empty(B, device=dev, dtype=torch.int32), cur=torch.empty(B, device=dev, dtype=torch.int32),
+                       hist=torch.zeros(T, B, device=dev, dtype=torch.int32), step=torch.zeros(1, device=dev, dtype=torch.int32),
+                       img=torch.empty(B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32), graph=None)
+            if len(self._graphs) >= 4:  # bound the number of cached geometries (each owns a KV cache)
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = stt
+        return stt
+
+    @torch.no_grad()
+    def generate(self, input_ids, pixel_values, attention_mask, max_tokens_to_generate: int, do_sample: bool = False,
+                 temperature: float = 0.8, top_p: float = 0.9, eos_token_id: Optional[int] = None, seed: int = 0,
+                 use_cuda_graph: bool = True, return_logits: bool = False, forced_tokens=None, timings: dict = None):
+        """Returns int64 tokens [B, T] (T = max_tokens_to_generate, or shorter if every row has emitted EOS; rows that
+        finished early keep generating -- trim at the first EOS as the reference loop would).  The decode step
+        (embedding, all layers, lm_head, sampler, counter advance) is captured once in a CUDA graph and replayed; the host
+        only checks EOS every 16 steps.  `forced_tokens` [B, T] teacher-forces the step inputs (parity tests)."""
+        _lib.require_device()
+        L = _lib.lib()
+        lm, c = self.language_model, self.text_config
+        B, S = input_ids.shape
+        T = int(max_tokens_to_generate)
+        V = c.vocab_size
+        dev = torch.device("cuda")
+        key = (B, S, T, bool(do_sample), float(temperature), float(top_p), int(seed))
+        stt = self._gen_state(key, B, S, T, V)
+        kv, nxt, cur, hist, step = stt["kv"], stt["nxt"], stt["cur"], stt["hist"], stt["step"]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timings is not None else None
+        if ev:
+            ev[0].record()
+        img = stt["img"].copy_(self.image_features(pixel_values))  # static buffer: the decode graph reads it
+        kv.image_feats = img
+        h, pos = self._merge(input_ids, attention_mask, img)
+        logits = lm.prefill(h, pos, B, S, kv, last_only=True).view(B, V)
+        if ev:
+            ev[1].record()
+
+        bufs = lm.decode_buffers(B)
+        logit_log = torch.empty(T, B, V, device=dev, dtype=torch.float32) if return_logits else None
+        forced = None if forced_tokens is None else forced_tokens.to(device=dev, dtype=torch.int32).t().contiguous()
+        # decode counters: position id of the next token, its cache slot, kv length including it
+        kv.counters[0].copy_(attention_mask.to(dev).sum(-1).to(torch.int32) + 1)
+        kv.counters[1].fill_(S)
+        kv.counters[2].fill_(S + 1)
+        step.zero_()
+        inv_t = 1.0 / float(temperature)
+
+        def sample(lg):
+            if do_sample:
+                _lib.check(L.pg_sample_top_p(lg.data_ptr(), V, nxt.data_ptr(), 0, B, V, inv_t, float(top_p), int(seed),
+                                             step.data_ptr(), _lib.stream()), "pg_sample_top_p")
+            else:
+                _lib.check(L.pg_argmax(lg.data_ptr(), V, nxt.data_ptr(), B, V, _lib.stream()), "pg_argmax")
+
+        def advance(n_counters):
+            _lib.check(L.pg_advance_decode(nxt.data_ptr(), hist.data_ptr(), cur.data_ptr(), kv.counters.data_ptr(), n_counters,
+                                           step.data_ptr(), B, _lib.stream()), "pg_advance_decode")
+
+        def decode_step(t=None):
+            self._embed_step(cur, kv, bufs["h"])
+            lg = lm.decode_layers(bufs, kv, B)
+            if t is not None and return_logits:
+                logit_log[t].copy_(lg)
+            sample(lg)
+            advance(3)
+            if t is not None and forced is not None:
+                cur.copy_(forced[t])
+
+        # token 0 comes from the prefill logits
+        if return_logits:
+            logit_log[0].copy_(logits)
+        sample(logits)
+        advance(0)
+        if forced is not None:
+            cur.copy_(forced[0])
+
+        graphed = use_cuda_graph and not return_logits and forced is None
+        done_at = T
+        for t in range(1, T):
+            if graphed and t >= 2:
+                if stt["graph"] is None:  # step 1 ran eagerly (lazy kernel attributes / driver entry points are warm)
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            decode_step()
+                    torch.cuda.current_stream().wait_stream(side)
+                    stt["graph"] = g
+                    # the capture itself does not execute: fall through to the replay for step t
+                stt["graph"].replay()
+            else:
+                decode_step(t)
+            if eos_token_id is not None and (t % 16 == 15 or t == T - 1):
+                if bool((hist[: t + 1] == eos_token_id).any(0).all()):
+                    done_at = t + 1
+                    break
+        kv._set_len(S + done_at - 1, c.num_hidden_layers)
+        if ev:
+            ev[2].record()
+            torch.cuda.synchronize()
+            timings["prefill_ms"] = ev[0].elapsed_time(ev[1])
+            timings["decode_ms"] = ev[1].elapsed_time(ev[2])
+            timings["decode_steps"] = done_at - 1
+        toks = hist[:done_at].t().contiguous().long()
+        if return_logits:
+            return toks, logit_log[:done_at].transpose(0, 1).contiguous()
+        return toks

@@ -23,7 +23,7 @@ def test_siglip_attention(B, H, N, dh):
     scale = dh ** -0.5
     rc = _lib.lib().pg_attention_prefill(
         qkv.data_ptr(), qkv.data_ptr() + 2 * D, qkv.data_ptr() + 4 * D, out.data_ptr(), B, H, N, N, dh, 1,
-        N * 3 * D, 3 * D, 0, dh, N * 3 * D, 3 * D, dh, N * D, D, dh, scale, _lib.stream())
+        N * 3 * D, 3 * D, 0, dh, N * 3 * D, 3 * D, dh, N * D, D, 0, dh, scale, _lib.stream())
     _lib.check(rc, "attn")
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
@@ -43,7 +43,7 @@ def test_gemma_prefill_attention(B, S, Hq, dh):
     scale = 1.0 / math.sqrt(dh)
     rc = _lib.lib().pg_attention_prefill(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, 1, S * Hq, S, dh, Hq,
-        S * Hq * dh, Hq * dh, dh, 0, S * dh, dh, 0, S * Hq * dh, dh, 0, scale, _lib.stream())
+        S * Hq * dh, Hq * dh, dh, 0, S * dh, dh, 0, S * Hq * dh, Hq * dh, dh, 0, scale, _lib.stream())
     _lib.check(rc, "attn")
     torch.cuda.synchronize()
     qf = q.float().view(B, S, Hq, dh).transpose(1, 2)
