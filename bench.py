@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: PaliGemma-3B-pt-224 decode tokens/s (+ prefill ms/image) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU cores (oracle port)
+
+Workload = BASELINE.json configs[2]: 3B-224 architecture (random init, bf16-representable, regime R2), 64 requests per
+GPU (weak scaling: batch-sharded replicas, no collective on the data path), prompt `<image>*256 <bos> t1 t2 \\n`
+(S = 260), temperature 0.8 / top-p 0.9 sampling, 128 generated tokens.  One "step" = one whole generate() job
+(prefill of 64 images + 127 graph-replayed decode steps).
+
+  value       decode tokens/s over all ranks: (K * B * 127 * N) / max-over-ranks(sum of device-timed decode segments),
+              inputs resident in HBM.  `prefill_ms_per_image` is the same for the prefill segments.
+  e2e         tokens/s through the public API from pinned HOST buffers: H2D of pixels/ids/mask and D2H of the tokens
+              inside the timed region, prefill included (all 128 tokens counted).
+  roofline    dominant kernel (gate||up weight-streaming tcgen05 GEMM of the decode step) timed alone with CUDA events,
+              rotating over the 18 layers' weights (2.4 GB > L2) against the measured HBM peak; `roofline_step` is the
+              whole decode step (5.40 GB algorithmic bytes) from the graph replays of the timed region.
+  cpu_baseline  the oracle port (fp32 PyTorch CPU restatement of the reference) on a bounded sample, rank 0, N = 1.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 64
+PROMPT_LEN = 4
+NEW_TOKENS = 128
+TEMPERATURE, TOP_P = 0.8, 0.9
+
+
+def algorithmic_bytes_per_decode_step(cfg, batch, kv_len_avg):
+    """every LM weight once (bf16) + KV read + KV write; vision tower / dead logits excluded."""
+    tc = cfg["text_config"]
+    D, F, L, V = tc["hidden_size"], tc["intermediate_size"], tc["num_hidden_layers"], tc["vocab_size"]
+    Hq, Hkv, dh = tc["num_attention_heads"], tc["num_key_value_heads"], tc["head_dim"]
+    per_layer = (Hq + 2 * Hkv) * dh * D + D * D + 3 * D * F + 2 * D
+    weights = 2 * (L * per_layer + D + V * D + V)
+    kv_read = batch * L * 2 * kv_len_avg * Hkv * dh * 2
+    kv_write = batch * L * 2 * Hkv * dh * 2
+    return weights + kv_read + kv_write
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx, pw = [], set(), None, 0.0
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); pw = max(pw, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "power_w_max": pw, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_gpu_model(cfg, seed=0):
+    import copy
+    from paligemma_multimodal_system_b200.modeling_paligemma import PaliGemmaConfig, PaliGemmaForConditionalGeneration
+    from paligemma_multimodal_system_b200.random_init import make_state_dict
+    sd = make_state_dict(cfg, "R2", seed=seed, device="cuda", dtype=torch.bfloat16)
+    model = PaliGemmaForConditionalGeneration(PaliGemmaConfig(**copy.deepcopy(cfg)), device="meta").eval()
+    model.load_state_dict(sd, strict=True, assign=True)
+    model.tie_weights()
+    model.pack()
+    return model, sd
+
+
+def time_dominant_kernel(model, batch, iters=3):
+    """gate||up decode GEMM (the largest weight stream of the step) alone, CUDA events on the launch stream, cold L2
+    (consecutive launches read different layers' 134 MB weight matrices)."""
+    from paligemma_multimodal_system_b200 import _lib
+    lm = model.language_model
+    pk = lm._packed
+    c = lm.text_config
+    x = (torch.randn(batch, c.hidden_size, device="cuda") * 0.1).bfloat16()
+    out = torch.empty(batch, c.intermediate_size, device="cuda", dtype=torch.bfloat16)
+    for lw in pk["layers"]:
+        _lib.gemm(x, lw["gu_w"], out, mode=_lib.EPI_GEGLU, swap=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 0
+    for _ in range(iters):
+        for lw in pk["layers"]:
+            _lib.gemm(x, lw["gu_w"], out, mode=_lib.EPI_GEGLU, swap=1)
+            n += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    bytes_alg = 2 * c.intermediate_size * c.hidden_size * 2 + batch * c.hidden_size * 2 + batch * c.intermediate_size * 2
+    return ms, bytes_alg
+
+
+def cpu_oracle_sample(cfg, sd_cpu, rows, new_tokens, threads):
+    """Times the oracle port (CPU fp32) on `rows` requests: prefill seconds/image and decode tokens/s."""
+    from oracle import paligemma_oracle as O
+    from paligemma_multimodal_system_b200.random_init import make_inputs
+    torch.set_num_threads(threads)
+    inp = make_inputs(cfg, batch=rows, prompt_len=PROMPT_LEN, seed=1)
+    t0 = time.perf_counter()
+    kv = []
+    feats = O.image_features(sd_cpu, cfg, inp["pixel_values"])
+    logits = O.forward(sd_cpu, cfg, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], kv, last_only=True, image_feats=feats)
+    t1 = time.perf_counter()
+    ids, mask = logits[:, -1].argmax(-1, keepdim=True), inp["attention_mask"]
+    for _ in range(new_tokens):
+        mask = torch.cat([mask, torch.ones((rows, 1), dtype=mask.dtype)], -1)
+        logits = O.forward(sd_cpu, cfg, ids, inp["pixel_values"], mask, kv, last_only=True, image_feats=feats)
+        ids = logits[:, -1].argmax(-1, keepdim=True)
+    t2 = time.perf_counter()
+    return dict(prefill_s_per_image=(t1 - t0) / rows, decode_tok_s=rows * new_tokens / (t2 - t1), seconds=t2 - t0)
+
+
+def run_reference_arm(args, cfg):
+    """`--impl reference`: the reference algorithm (oracle port; the Python reference itself cannot travel to the GPU box)
+    on the host cores, same config/metric, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from paligemma_multimodal_system_b200.random_init import make_state_dict
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = make_state_dict(cfg, "R2", seed=0, device="cpu")
+    rows, toks = 2, 6
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_sample(cfg, sd, 1, 1, threads)
+    t0 = time.perf_counter()
+    res = [cpu_oracle_sample(cfg, sd, rows, toks, threads) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    dec = sum(r["decode_tok_s"] for r in res) / len(res)
+    pre = sum(r["prefill_s_per_image"] for r in res) / len(res)
+    sample = f"{rows} requests x {toks} decode tokens per step (B={rows} batched decode, vision tower not re-run), 3B-224 fp32"
+    line = {"impl": "reference", "metric": "decode_tokens_per_s", "value": dec, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "prefill_ms_per_image": 1e3 * pre,
+            "config": {"workload": "PaliGemma-3B-pt-224 random-init, CPU sample of configs[2]", "sample": sample},
+            "cpu_baseline": {"value": dec, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": dec, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="requests per GPU")
+    ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS)
+    ap.add_argument("--image-size", type=int, default=224)
+    ap.add_argument("--greedy", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from paligemma_multimodal_system_b200.random_init import make_inputs, paligemma_3b_config
+    cfg = paligemma_3b_config(args.image_size)
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from paligemma_multimodal_system_b200 import _lib
+    _lib.require_device()
+
+    B, T = args.batch, args.new_tokens
+    model, sd = build_gpu_model(cfg, seed=0)
+    # rank r serves rows [r*B, (r+1)*B) of the global batch (seeded per row): independent requests, no exchange
+    inp = make_inputs(cfg, batch=B, prompt_len=PROMPT_LEN, seed=100 + rank)
+    S = inp["input_ids"].shape[1]
+    host = {k: v.pin_memory() for k, v in inp.items()}
+    dev = {k: v.cuda() for k, v in inp.items()}
+    gen = dict(do_sample=not args.greedy, temperature=TEMPERATURE, top_p=TOP_P, seed=1234)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    for _ in range(args.warmup):
+        model.generate(dev["input_ids"], dev["pixel_values"], dev["attention_mask"], T, **gen)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.lib().pg_launch_count()
+    pre_ms = dec_ms = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tm = {}
+        model.generate(dev["input_ids"], dev["pixel_values"], dev["attention_mask"], T, timings=tm, **gen)
+        pre_ms += tm["prefill_ms"]
+        dec_ms += tm["decode_ms"]
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    eager_launches = _lib.lib().pg_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- end-to-end arm (host buffers, copies inside the timed region) ----------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    d2h = 0
+    for _ in range(args.steps):
+        ids = host["input_ids"].cuda(non_blocking=True)
+        msk = host["attention_mask"].cuda(non_blocking=True)
+        px = host["pixel_values"].cuda(non_blocking=True)
+        toks = model.generate(ids, px, msk, T, **gen).cpu()
+        d2h = toks.numel() * toks.element_size()
+    e3.record()
+    barrier()
+    e2e_ms = e2.elapsed_time(e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    times = torch.tensor([total_ms, pre_ms, dec_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, pre_ms, dec_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        K = args.steps
+        dec_steps = T - 1
+        decode_tok_s = K * B * dec_steps * world / (dec_ms / 1e3)
+        hbm_peak, peak_src = peaks()
+        step_bytes = algorithmic_bytes_per_decode_step(cfg, B, S + T / 2)
+        step_ms = dec_ms / (K * dec_steps)
+        step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
+        k_ms, k_bytes = time_dominant_kernel(model, B)
+        k_gbs = k_bytes / (k_ms * 1e-3) / 1e9
+        graph_kernels = 3 + 9 * cfg["text_config"]["num_hidden_layers"] + 1 + 2  # embed + 9/layer + norm,head + sample,advance
+        line = {
+            "metric": "decode_tokens_per_s", "value": decode_tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "prefill_ms_per_image": pre_ms / (K * B), "decode_ms_per_token_step": step_ms,
+            "config": {"workload": f"PaliGemma-3B-pt-{args.image_size} random-init (R2), {B} requests/GPU, S={S}, "
+                                   f"{'greedy' if args.greedy else 'top-p 0.9 temp 0.8'}, {T} new tokens (BASELINE configs[2])",
+                       "global_batch": B * world, "parallelism": f"dp{world} replicas, batch-sharded, no collective",
+                       "l2_policy": "inputs larger than L2 (5.0 GB of weights streamed per decode step)"},
+            "e2e": {"value": K * B * T * world / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "generated tokens / wall incl. H2D, prefill, decode, D2H"},
+            "gpu_launches": int(eager_launches + K * max(T - 2, 0) * graph_kernels),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<64,swap> gate||up decode GEMM", "achieved": k_gbs,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "us_per_launch": 1e3 * k_ms, "algorithmic_bytes": k_bytes},
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
+                              "algorithmic_bytes": step_bytes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sd_cpu = {k: v.float().cpu() for k, v in sd.items()}
+            r = cpu_oracle_sample(cfg, sd_cpu, 1, 8, threads)
+            line["cpu_baseline"] = {"value": r["decode_tok_s"], "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "prefill_ms_per_image": 1e3 * r["prefill_s_per_image"],
+                                    "sample": "1 request, prefill + 8 greedy decode tokens, fp32 oracle port, vision tower not re-run"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

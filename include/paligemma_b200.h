@@ -33,6 +33,8 @@ extern "C" {
 /* Library / device info.  Returns the ABI version (>0) or PG_ERR_ARCH when the current device is not sm_100. */
 int pg_abi_version(void);
 int pg_check_device(void);
+/* Number of kernel launches this library has issued in the calling process (host-side counter). */
+long long pg_launch_count(void);
 
 /*
  * acc[t,f] = sum_k x[t,k] * w[f,k]  (bf16 in, fp32 accumulate on tcgen05 tensor cores, accumulator in TMEM).

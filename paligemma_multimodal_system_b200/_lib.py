@@ -22,6 +22,7 @@ p, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulongl
 SIGNATURES = {
     "pg_abi_version": [],
     "pg_check_device": [],
+    "pg_launch_count": [],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
@@ -40,7 +41,7 @@ SIGNATURES = {
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
 }
-_RESTYPE = {"pg_attention_decode_workspace_floats": i64}
+_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_launch_count": i64}
 
 _lib = None
 

@@ -409,6 +409,7 @@ static int launch_prefill(const AttnPrefillParams& p, int B, int H, cudaStream_t
   }
   dim3 grid((p.rows + BLOCK_M - 1) / BLOCK_M, H, B);
   attn_prefill_kernel<DH, NWARPS><<<grid, NWARPS * 32, smem, st>>>(p);
+  pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
@@ -426,6 +427,7 @@ static int launch_decode(const AttnDecodeParams& p, bf16* out, cudaStream_t st) 
   }
   dim3 grid(p.num_splits, p.B * p.Hkv);
   attn_decode_kernel<DH><<<grid, 128, smem, st>>>(p);
+  pg_count_launch(2);
   if (cudaGetLastError() != cudaSuccess) return PG_ERR_CUDA;
   attn_decode_combine_kernel<<<p.B * p.Hq, DH >= 128 ? 128 : 64, 0, st>>>(p.ws, out, p.B, p.Hq, DH, p.num_splits);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;

@@ -9,6 +9,10 @@
 
 #define PG_DEVINL __device__ __forceinline__
 
+// host-side count of kernel launches issued by this library (bench.py reports it as gpu_launches)
+extern "C" long long pg_launch_count(void);
+void pg_count_launch(int n);
+
 namespace pg {
 
 // ---------------------------------------------------------------------------------------------

@@ -326,7 +326,13 @@ __global__ void advance_decode_kernel(const int* __restrict__ next, int* __restr
 
 using namespace pg;
 #define PG_ST(s) reinterpret_cast<cudaStream_t>(s)
-#define PG_RET() return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA
+#define PG_RET()     \
+  pg_count_launch(1); \
+  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA
+
+static long long g_launches = 0;
+void pg_count_launch(int n) { g_launches += n; }
+extern "C" long long pg_launch_count(void) { return g_launches; }
 
 extern "C" int pg_abi_version(void) { return 1; }
 
@@ -387,6 +393,7 @@ extern "C" int pg_merge_embeddings(const long long* input_ids, const long long* 
   if (B <= 0 || S <= 0 || D <= 0 || (D % 4)) return PG_ERR_ARG;
   merge_scan_kernel<<<B, 1024, 0, PG_ST(stream)>>>(input_ids, attn_mask, src_scratch, pos, err_flag, S, N, image_token, pad_token);
   if (cudaGetLastError() != cudaSuccess) return PG_ERR_CUDA;
+  pg_count_launch(1);
   merge_gather_kernel<<<B * S, 256, 0, PG_ST(stream)>>>(input_ids, src_scratch, static_cast<const bf16*>(embed), img, h, S, D, N,
                                                         text_scale, img_scale);
   PG_RET();

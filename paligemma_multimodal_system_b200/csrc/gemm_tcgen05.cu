@@ -415,6 +415,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   }
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_tcgen05_kernel<BN, SWAP><<<grid, NUM_THREADS, smem, st>>>(ta, tb, a);
+  pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 

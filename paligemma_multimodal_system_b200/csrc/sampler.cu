@@ -255,6 +255,7 @@ using namespace pg;
 extern "C" int pg_argmax(const float* logits, long long ld, int* out, int B, int V, void* stream) {
   if (B <= 0 || V <= 0) return PG_ERR_ARG;
   argmax_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, out, V);
+  pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
@@ -264,5 +265,6 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
   if (B <= 0 || V <= 0 || !(inv_temperature > 0.f) || !(top_p >= 0.f)) return PG_ERR_ARG;
   sample_top_p_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, out, kept_count, V, inv_temperature,
                                                                             top_p, seed, step_ptr);
+  pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
