@@ -35,6 +35,9 @@ int pg_abi_version(void);
 int pg_check_device(void);
 /* Number of kernel launches this library has issued in the calling process (host-side counter). */
 long long pg_launch_count(void);
+/* Programmatic dependent launch for the decode-step kernels (default on): the next kernel's prologue and weight
+ * prefetch overlap the running kernel; every such kernel executes griddepcontrol.wait before dependent accesses. */
+int pg_set_pdl(int on);
 
 /*
  * acc[t,f] = sum_k x[t,k] * w[f,k]  (bf16 in, fp32 accumulate on tcgen05 tensor cores, accumulator in TMEM).
@@ -104,6 +107,19 @@ int pg_attention_decode(const void* q, const void* k_pages, const void* v_pages,
                         const int* kv_len, void* out, float* workspace, int B, int Hq, int Hkv, int dh, int page_size,
                         int max_pages, int num_splits, float scale, void* stream);
 long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_splits);
+
+/*
+ * Decode-step attention in ONE launch (modeling_gemma.py:285-339 at q_len == 1 + KVCache.update :18-57): rotates q and
+ * the new k (fp32 qkv [B, (Hq+2Hkv)*dh] straight from the split-K QKV GEMM), appends k/v to the paged cache at slot
+ * kv_len[b]-1, attends over kv_len[b] keys with one CTA per 64-key page (grid = max_tiles x B*Hkv, excess CTAs exit),
+ * and the last CTA to arrive for a sequence merges the per-page partials (arrival counters self-reset).
+ * counters: int32 [B*Hkv], zero before the first launch.  max_tiles >= ceil(max kv_len / 64).
+ */
+int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
+                              void* v_pages, const int* page_table, float* workspace, int* counters, void* out, int B,
+                              int Hq, int Hkv, int dh, int page_size, int max_pages, int max_tiles, float scale,
+                              void* stream);
+long long pg_attention_decode_fused_workspace_floats(int B, int Hq, int dh, int max_tiles);
 
 /* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
  * views, modeling_gemma.py:8-64). */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "pg_abi_version": [],
     "pg_check_device": [],
     "pg_launch_count": [],
+    "pg_set_pdl": [i32],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
@@ -34,6 +35,8 @@ SIGNATURES = {
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
     "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],
+    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
+    "pg_attention_decode_fused_workspace_floats": [i32, i32, i32, i32],
     "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
@@ -41,7 +44,7 @@ SIGNATURES = {
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
 }
-_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_launch_count": i64}
+_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_attention_decode_fused_workspace_floats": i64, "pg_launch_count": i64}
 
 _lib = None
 
@@ -60,6 +63,8 @@ def lib():
             fn.argtypes = args
             fn.restype = _RESTYPE.get(name, i32)
         _lib = l
+        if os.environ.get("PG_PDL", "1") == "0":
+            l.pg_set_pdl(0)
     return _lib
 
 

@@ -396,6 +396,249 @@ __global__ void attn_decode_combine_kernel(const float* ws, bf16* out, int B, in
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// fused decode step attention: RoPE(q, k_new) + KV append + split-KV attention + last-CTA combine in ONE launch
+// ------------------------------------------------------------------------------------------------------------
+struct AttnDecodeFusedParams {
+  const float* qkv;       // [B, (Hq+2Hkv)*dh] fp32 raw projections of the new token (pre-RoPE)
+  const int* pos;         // [B] position id of the new token
+  const int* kv_len;      // [B] cache length INCLUDING the new token (its slot is kv_len-1)
+  const float* inv_freq;  // [dh/2]
+  bf16* k_pages;          // [pages, 64, Hkv*dh]
+  bf16* v_pages;
+  const int* page_table;  // [B, max_pages]
+  float* ws;              // partials: o [B*Hq][max_tiles][dh], ml [B*Hq][max_tiles][2]
+  int* counters;          // [B*Hkv] arrival counters (zero on entry, reset by the combining CTA)
+  bf16* out;              // [B, Hq*dh]
+  int B, Hq, Hkv, max_pages, max_tiles;
+  float sl2;
+};
+
+// grid (max_tiles, B*Hkv); one CTA = one 64-key tile of one (sequence, kv head); 4 warps x 16 keys
+template <int DH>
+__global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecodeFusedParams p) {
+  using C = AttnCfg<DH>;
+  constexpr int BLOCK_N = 64;
+  constexpr int HALF = DH / 2;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);  // [16][LDS]
+  bf16* Ks = Qs + 16 * C::LDS;                   // [64][LDS]
+  bf16* Vs = Ks + BLOCK_N * C::LDS;              // [64][LDS]
+  float* red = reinterpret_cast<float*>(Ks);     // reused after the MMAs: [4 warps][16][DH+2]
+  __shared__ int s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int b = blockIdx.y / p.Hkv, hk = blockIdx.y % p.Hkv;
+  const int group = p.Hq / p.Hkv;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  const int len = p.kv_len[b];
+  const int n_tiles = (len + BLOCK_N - 1) / BLOCK_N;
+  if (tile >= n_tiles) return;
+  const int new_slot = len - 1;
+  const bool owns_new = (tile == new_slot / BLOCK_N);
+  const long long kv_ts = static_cast<long long>(p.Hkv) * DH;
+  const int page = p.page_table[b * p.max_pages + tile];
+  bf16* kb = p.k_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+  bf16* vb = p.v_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+  const int n0 = tile * BLOCK_N;
+  // cached rows via cp.async; the new token's row (not in the cache yet) is filled from registers below
+  load_tile<DH, 128>(Ks, BLOCK_N, [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? kb + r * kv_ts : nullptr; });
+  load_tile<DH, 128>(Vs, BLOCK_N, [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? vb + r * kv_ts : nullptr; });
+  cp_async_commit();
+
+  // RoPE (rotate-half, modeling_gemma.py:138-151) on the query heads of this group (+ the new key when owned)
+  const int W = (p.Hq + 2 * p.Hkv) * DH;
+  const float* row = p.qkv + static_cast<long long>(b) * W;
+  const float posf = static_cast<float>(p.pos[b]);
+  for (int i = threadIdx.x; i < HALF; i += 128) {
+    float sn, cs;
+    sincosf(posf * p.inv_freq[i], &sn, &cs);
+    for (int g = 0; g < group; ++g) {
+      const float* qh = row + (hk * group + g) * DH;
+      const float x1 = qh[i], x2 = qh[i + HALF];
+      Qs[g * C::LDS + i] = __float2bfloat16(x1 * cs - x2 * sn);
+      Qs[g * C::LDS + i + HALF] = __float2bfloat16(x2 * cs + x1 * sn);
+    }
+    if (owns_new) {
+      const float* kh = row + (p.Hq + hk) * DH;
+      const float* vh = row + (p.Hq + p.Hkv + hk) * DH;
+      const float x1 = kh[i], x2 = kh[i + HALF];
+      const bf16 k1 = __float2bfloat16(x1 * cs - x2 * sn), k2 = __float2bfloat16(x2 * cs + x1 * sn);
+      const bf16 v1 = __float2bfloat16(vh[i]), v2 = __float2bfloat16(vh[i + HALF]);
+      const int r = new_slot - n0;
+      kb[r * kv_ts + i] = k1; kb[r * kv_ts + i + HALF] = k2;   // KVCache.update (modeling_gemma.py:18-57)
+      vb[r * kv_ts + i] = v1; vb[r * kv_ts + i + HALF] = v2;
+    }
+  }
+  // zero the padding rows / pad columns of Q
+  for (int idx = threadIdx.x; idx < 16 * C::DHP; idx += 128) {
+    const int r = idx / C::DHP, c = idx % C::DHP;
+    if (r >= group || c >= DH) Qs[r * C::LDS + c] = __float2bfloat16(0.f);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (owns_new) {  // place the new row into the staged tile (after the zero-filling cp.async has landed)
+    const int r = new_slot - n0;
+    const float* kh = row + (p.Hq + hk) * DH;
+    const float* vh = row + (p.Hq + p.Hkv + hk) * DH;
+    for (int i = threadIdx.x; i < HALF; i += 128) {
+      float sn, cs;
+      sincosf(posf * p.inv_freq[i], &sn, &cs);
+      const float x1 = kh[i], x2 = kh[i + HALF];
+      Ks[r * C::LDS + i] = __float2bfloat16(x1 * cs - x2 * sn);
+      Ks[r * C::LDS + i + HALF] = __float2bfloat16(x2 * cs + x1 * sn);
+      Vs[r * C::LDS + i] = __float2bfloat16(vh[i]);
+      Vs[r * C::LDS + i + HALF] = __float2bfloat16(vh[i + HALF]);
+    }
+    __syncthreads();
+  }
+
+  float o[C::DHP / 8][4];
+#pragma unroll
+  for (int i = 0; i < C::DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2], l_run[2];
+  {
+    const uint32_t q_addr = smem_u32(Qs + (lane & 15) * C::LDS + (lane >> 4) * 8);
+    const bf16* Kt = Ks + warp * 16 * C::LDS;
+    const bf16* Vt = Vs + warp * 16 * C::LDS;
+    float s[2][4];
+    s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+    const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int ks = 0; ks < C::DHP / 16; ++ks) {
+      uint32_t a[4], b0, b1, b2, b3;
+      ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
+      ldmatrix_x4(k_addr + ks * 32, b0, b1, b2, b3);
+      mma_bf16_16816(s[0], a, b0, b1);
+      mma_bf16_16816(s[1], a, b2, b3);
+    }
+    const int kbase = n0 + warp * 16;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int key = kbase + nt * 8 + (lane & 3) * 2;
+      if (key >= len) s[nt][0] = s[nt][2] = -INFINITY;
+      if (key + 1 >= len) s[nt][1] = s[nt][3] = -INFINITY;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float msc = (mx == -INFINITY) ? 0.f : mx * p.sl2;
+      m_run[r] = mx;
+      s[0][2 * r] = exp2f(s[0][2 * r] * p.sl2 - msc);
+      s[0][2 * r + 1] = exp2f(s[0][2 * r + 1] * p.sl2 - msc);
+      s[1][2 * r] = exp2f(s[1][2 * r] * p.sl2 - msc);
+      s[1][2 * r + 1] = exp2f(s[1][2 * r + 1] * p.sl2 - msc);
+      float rs = s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      l_run[r] = rs;
+    }
+    uint32_t a[4];
+    a[0] = pack_bf16(s[0][0], s[0][1]);
+    a[1] = pack_bf16(s[0][2], s[0][3]);
+    a[2] = pack_bf16(s[1][0], s[1][1]);
+    a[3] = pack_bf16(s[1][2], s[1][3]);
+    const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
+#pragma unroll
+    for (int dp = 0; dp < C::DHP / 16; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(v_addr + dp * 32, b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * dp], a, b0, b1);
+      mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+    }
+  }
+  __syncthreads();  // all warps are done with Ks/Vs: reuse as the reduction buffer
+
+  constexpr int RLD = DH + 2;  // [.., DH] = m (scaled, log2 domain), [.., DH+1] = l
+  {
+    const int r0 = lane >> 2;
+    float* dst0 = red + (warp * 16 + r0) * RLD;
+    float* dst1 = red + (warp * 16 + r0 + 8) * RLD;
+#pragma unroll
+    for (int nt = 0; nt < C::DHP / 8; ++nt) {
+      const int col = nt * 8 + (lane & 3) * 2;
+      if (col < DH) {
+        dst0[col] = o[nt][0]; dst0[col + 1] = o[nt][1];
+        dst1[col] = o[nt][2]; dst1[col + 1] = o[nt][3];
+      }
+    }
+    if ((lane & 3) == 0) {
+      dst0[DH] = m_run[0] * p.sl2; dst0[DH + 1] = l_run[0];
+      dst1[DH] = m_run[1] * p.sl2; dst1[DH + 1] = l_run[1];
+    }
+  }
+  __syncthreads();
+  float* ws_o = p.ws;
+  float* ws_ml = p.ws + static_cast<long long>(p.B) * p.Hq * p.max_tiles * DH;
+  for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
+    const int r = idx / DH, col = idx % DH;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 16 + r) * RLD + DH]);
+    const float Ms = (M == -INFINITY) ? 0.f : M;
+    float acc = 0.f, Lsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float wgt = exp2f(red[(w * 16 + r) * RLD + DH] - Ms);
+      acc += red[(w * 16 + r) * RLD + col] * wgt;
+      Lsum += red[(w * 16 + r) * RLD + DH + 1] * wgt;
+    }
+    const long long hrow = (static_cast<long long>(b) * p.Hq + hk * group + r) * p.max_tiles + tile;
+    __stcg(ws_o + hrow * DH + col, acc);
+    if (col == 0) {
+      __stcg(ws_ml + hrow * 2, M);
+      __stcg(ws_ml + hrow * 2 + 1, Lsum);
+    }
+  }
+  // ---- the last CTA of this (sequence, kv head) to arrive merges the tile partials ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(p.counters + blockIdx.y, 1);
+    s_last = (old == n_tiles - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
+    const int r = idx / DH, col = idx % DH;
+    const long long hbase = (static_cast<long long>(b) * p.Hq + hk * group + r) * p.max_tiles;
+    float M = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) M = fmaxf(M, __ldcg(ws_ml + (hbase + t) * 2));
+    float acc = 0.f, Lsum = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const float wgt = exp2f(__ldcg(ws_ml + (hbase + t) * 2) - M);
+      acc += __ldcg(ws_o + (hbase + t) * DH + col) * wgt;
+      Lsum += __ldcg(ws_ml + (hbase + t) * 2 + 1) * wgt;
+    }
+    p.out[(static_cast<long long>(b) * p.Hq + hk * group + r) * DH + col] = __float2bfloat16(acc / Lsum);
+  }
+  if (threadIdx.x == 0) p.counters[blockIdx.y] = 0;  // ready for the next launch (stream ordered)
+}
+
+template <int DH>
+static int launch_decode_fused(const AttnDecodeFusedParams& p, cudaStream_t st) {
+  using C = AttnCfg<DH>;
+  constexpr int smem_main = (16 + 2 * 64) * C::LDS * 2;
+  constexpr int smem_red = 16 * C::LDS * 2 + 4 * 16 * (DH + 2) * 4;
+  constexpr int smem = smem_main > smem_red ? smem_main : smem_red;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_decode_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return PG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(p.max_tiles, p.B * p.Hkv);
+  return launch_kernel(attn_decode_fused_kernel<DH>, grid, dim3(128), smem, st, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
 template <int DH, int NWARPS>
 static int launch_prefill(const AttnPrefillParams& p, int B, int H, cudaStream_t st) {
   using C = AttnCfg<DH>;
@@ -481,6 +724,31 @@ extern "C" int pg_attention_decode(const void* q, const void* k_pages, const voi
   switch (dh) {
     case 64: return launch_decode<64>(p, static_cast<bf16*>(out), st);
     case 256: return launch_decode<256>(p, static_cast<bf16*>(out), st);
+    default: return PG_ERR_ARG;
+  }
+}
+
+extern "C" long long pg_attention_decode_fused_workspace_floats(int B, int Hq, int dh, int max_tiles) {
+  return static_cast<long long>(B) * Hq * max_tiles * (dh + 2);
+}
+
+extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq,
+                                         void* k_pages, void* v_pages, const int* page_table, float* workspace,
+                                         int* counters, void* out, int B, int Hq, int Hkv, int dh, int page_size,
+                                         int max_pages, int max_tiles, float scale, void* stream) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || max_tiles <= 0 ||
+      max_tiles > max_pages || B * Hkv > 65535)
+    return PG_ERR_ARG;
+  AttnDecodeFusedParams p;
+  p.qkv = qkv; p.pos = pos; p.kv_len = kv_len; p.inv_freq = inv_freq;
+  p.k_pages = static_cast<bf16*>(k_pages); p.v_pages = static_cast<bf16*>(v_pages);
+  p.page_table = page_table; p.ws = workspace; p.counters = counters; p.out = static_cast<bf16*>(out);
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages; p.max_tiles = max_tiles;
+  p.sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dh) {
+    case 64: return launch_decode_fused<64>(p, st);
+    case 256: return launch_decode_fused<256>(p, st);
     default: return PG_ERR_ARG;
   }
 }

@@ -12,6 +12,8 @@
 // host-side count of kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern "C" long long pg_launch_count(void);
 void pg_count_launch(int n);
+// 1 = launch kernels with programmatic dependent launch (prologue / weight prefetch of kernel N+1 overlaps kernel N)
+int pg_pdl_enabled(void);
 
 namespace pg {
 
@@ -206,6 +208,25 @@ PG_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+
+// Host-side launch through cudaLaunchKernelEx, optionally as a programmatic dependent launch.  Every kernel launched
+// this way executes griddepcontrol.wait before its first dependent global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pg_pdl_enabled() ? 1 : 0;
+  pg_count_launch(1);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace pg

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   extern __shared__ float row[];
   float* red = row + D;
   const long long r = blockIdx.x;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
   if (zero_buf != nullptr) {  // zero-fill for the split-K GEMM that follows
     const long long per = (zero_count + gridDim.x - 1) / gridDim.x;
     const long long lo = r * per, hi = min(zero_count, lo + per);
@@ -221,6 +223,8 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(const int* __restrict
                                                            int N, float text_scale, float img_scale, long long pad_token,
                                                            long long image_token) {
   const int b = blockIdx.x;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
   const long long id = tokens[b];
   float4* dst = reinterpret_cast<float4*>(h + static_cast<long long>(b) * D);
   if (id == pad_token) {
@@ -312,6 +316,8 @@ __global__ void kv_gather_kernel(const bf16* __restrict__ pages, const int* __re
 __global__ void advance_decode_kernel(const int* __restrict__ next, int* __restrict__ tok_hist, int* __restrict__ cur_tok,
                                       int* __restrict__ counters, int n_counters, int* __restrict__ step, int B) {
   const int b = threadIdx.x;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
   const int st = *step;
   if (b < B) {
     if (tok_hist) tok_hist[static_cast<long long>(st) * B + b] = next[b];
@@ -331,7 +337,10 @@ using namespace pg;
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA
 
 static long long g_launches = 0;
+static int g_pdl = 1;
 void pg_count_launch(int n) { g_launches += n; }
+int pg_pdl_enabled(void) { return g_pdl; }
+extern "C" int pg_set_pdl(int on) { g_pdl = on ? 1 : 0; return PG_OK; }
 extern "C" long long pg_launch_count(void) { return g_launches; }
 
 extern "C" int pg_abi_version(void) { return 1; }
@@ -353,8 +362,8 @@ extern "C" int pg_layernorm(const float* x, const float* gamma, const float* bet
 extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
                           long long zero_count, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
-  rmsnorm_kernel<<<rows, 256, (D + 33) * sizeof(float), PG_ST(stream)>>>(x, w, static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count);
-  PG_RET();
+  return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), (D + 33) * sizeof(float), PG_ST(stream), x, w,
+                       static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream) {
@@ -402,9 +411,8 @@ extern "C" int pg_merge_embeddings(const long long* input_ids, const long long* 
 extern "C" int pg_embed_tokens(const int* tokens, const void* embed, const float* img, float* h, int B, int D, int N,
                                float text_scale, float img_scale, long long pad_token, long long image_token, void* stream) {
   if (B <= 0 || D <= 0 || (D % 4)) return PG_ERR_ARG;
-  embed_tokens_kernel<<<B, 256, 0, PG_ST(stream)>>>(tokens, static_cast<const bf16*>(embed), img, h, D, N, text_scale, img_scale,
-                                                    pad_token, image_token);
-  PG_RET();
+  return launch_kernel(embed_tokens_kernel, dim3(B), dim3(256), 0, PG_ST(stream), tokens, static_cast<const bf16*>(embed), img, h,
+                       D, N, text_scale, img_scale, pad_token, image_token) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos, void* q_out, void* k_out, void* v_out,
@@ -438,6 +446,6 @@ extern "C" int pg_kv_gather(const void* pages, const int* page_table, void* dens
 extern "C" int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counters, int n_counters, int* step, int B,
                                  void* stream) {
   if (B <= 0 || B > 1024 || n_counters < 0) return PG_ERR_ARG;
-  advance_decode_kernel<<<1, 1024, 0, PG_ST(stream)>>>(next, tok_hist, cur_tok, counters, n_counters, step, B);
-  PG_RET();
+  return launch_kernel(advance_decode_kernel, dim3(1), dim3(1024), 0, PG_ST(stream), next, tok_hist, cur_tok, counters,
+                       n_counters, step, B) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }

@@ -26,9 +26,13 @@ constexpr int ACC_STAGES = 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
 __host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
-__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * (BN + 1) * 4 : 0; }
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 : 0; }
+// decode (SWAP, BN <= 64): two CTAs per SM (115712 B each) so that, with programmatic dependent launch, the next
+// kernel's CTAs become resident and prefetch their weights while this kernel drains; otherwise one CTA with <= 200 KB
+__host__ __device__ constexpr bool two_per_sm(int BN, bool swap) { return swap && BN <= 64; }
 __host__ __device__ constexpr int num_stages(int BN, bool swap) {
-  int s = (200 * 1024 - xch_bytes(BN, swap)) / stage_bytes(BN);
+  int budget = two_per_sm(BN, swap) ? 115712 - 256 : 200 * 1024;
+  int s = (budget - xch_bytes(BN, swap)) / stage_bytes(BN);
   return s > 8 ? 8 : s;
 }
 __host__ __device__ constexpr int tmem_cols(int BN) {
@@ -36,7 +40,7 @@ __host__ __device__ constexpr int tmem_cols(int BN) {
   return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
 }
 __host__ __device__ constexpr int smem_bytes(int BN, bool swap) {
-  return num_stages(BN, swap) * stage_bytes(BN) + xch_bytes(BN, swap) + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  return num_stages(BN, swap) * stage_bytes(BN) + xch_bytes(BN, swap) + 256 /*barriers*/;
 }
 
 struct GemmArgs {
@@ -70,7 +74,7 @@ PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_k
 PG_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <int BN, bool SWAP>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
   constexpr int STAGES = num_stages(BN, SWAP);
@@ -79,10 +83,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   constexpr int TMEM_COLS = tmem_cols(BN);
   constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B swizzle atoms need 1024 B alignment
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
   float* xch = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES);
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + xch_bytes(BN, SWAP);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -133,13 +138,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const uint64_t hintB = SWAP ? kEvictLast : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
+      // The weight operand never depends on the previous kernel: with programmatic dependent launch its first
+      // pipeline stages are fetched BEFORE griddepcontrol.wait, i.e. while the previous kernel is still running.
+      int pre = 0;
+      if (SWAP && static_cast<int>(blockIdx.x) < num_tiles) {
+        const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k);
+        pre = min(STAGES, t.kb1 - t.kb0);
+        for (int s = 0; s < pre; ++s) {
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
+        }
+      }
+      griddep_wait();
+      griddep_launch_dependents();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
+          if (pre > 0) {  // weights of this stage are already in flight
+            --pre;
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
+          }
           tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -178,6 +200,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   } else {
     // =================================== epilogue warps =================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    griddep_wait();          // outputs / residual / bias may depend on the previous kernel
     int acc = 0;
     uint32_t acc_phase = 0;
     const int mode = args.mode;
@@ -290,7 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               tmem_ld16(taddr + c0, r);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) xch[(rl - 64) * (BN + 1) + c0 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 16; ++i) xch[(rl - 64) * BN + ((c0 + i) ^ ((rl - 64) & (BN - 1) & 31))] = __uint_as_float(r[i]);
             }
           }
           named_bar_sync(1, 128);
@@ -307,7 +330,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               for (int i = 0; i < 16; ++i) {
                 const int j = j_base + c0 + i;
                 if (f_ok && j < args.tokens) {
-                  float val = gelu_tanh(__uint_as_float(r[i])) * xch[rl * (BN + 1) + c0 + i];
+                  float val = gelu_tanh(__uint_as_float(r[i])) * xch[rl * BN + ((c0 + i) ^ (rl & (BN - 1) & 31))];
                   out_bf[static_cast<long long>(j) * args.ldo + fo] = __float2bfloat16(val);
                 }
               }
@@ -413,10 +436,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
     }
     configured = true;
   }
-  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, SWAP><<<grid, NUM_THREADS, smem, st>>>(ta, tb, a);
-  pg_count_launch(1);
-  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
+  const int grid = num_tiles < slots ? num_tiles : slots;
+  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP>, dim3(grid), dim3(NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess ? PG_OK
+                                                                                                                         : PG_ERR_CUDA;
 }
 
 }  // namespace pg

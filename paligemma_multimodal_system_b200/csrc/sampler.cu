@@ -15,16 +15,42 @@ PG_DEVINL uint32_t float_key(float x) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// Visits every element of a row once: f(value, index).  16-byte loads, 4 independent loads in flight per thread
+// (the row is L2 resident; one load per thread at a time is latency bound).
+template <typename F>
+PG_DEVINL void for_each_elem(const float* __restrict__ row, int V, F f) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = V >> 2;
+    int i = tid;
+    for (; i + 3 * nt < n4; i += 4 * nt) {
+      const float4 a = __ldg(r4 + i), b = __ldg(r4 + i + nt), c = __ldg(r4 + i + 2 * nt), d = __ldg(r4 + i + 3 * nt);
+      f(a.x, 4 * i); f(a.y, 4 * i + 1); f(a.z, 4 * i + 2); f(a.w, 4 * i + 3);
+      f(b.x, 4 * (i + nt)); f(b.y, 4 * (i + nt) + 1); f(b.z, 4 * (i + nt) + 2); f(b.w, 4 * (i + nt) + 3);
+      f(c.x, 4 * (i + 2 * nt)); f(c.y, 4 * (i + 2 * nt) + 1); f(c.z, 4 * (i + 2 * nt) + 2); f(c.w, 4 * (i + 2 * nt) + 3);
+      f(d.x, 4 * (i + 3 * nt)); f(d.y, 4 * (i + 3 * nt) + 1); f(d.z, 4 * (i + 3 * nt) + 2); f(d.w, 4 * (i + 3 * nt) + 3);
+    }
+    for (; i < n4; i += nt) {
+      const float4 a = __ldg(r4 + i);
+      f(a.x, 4 * i); f(a.y, 4 * i + 1); f(a.z, 4 * i + 2); f(a.w, 4 * i + 3);
+    }
+  } else {
+    for (int i = tid; i < V; i += nt) f(row[i], i);
+  }
+}
+
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ out, int V) {
   __shared__ float sv[32];
   __shared__ int si[32];
   const float* row = logits + blockIdx.x * ld;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float v = row[i];
+  for_each_elem(row, V, [&](float v, int i) {
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-  }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -110,10 +136,12 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = logits + blockIdx.x * ld;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
 
   // pass 0: max
   float mx = -INFINITY;
-  for (int i = tid; i < V; i += 1024) mx = fmaxf(mx, row[i]);
+  for_each_elem(row, V, [&](float v, int) { mx = fmaxf(mx, v); });
   mx = block_reduce_max(mx, red);
   const float c = inv_temp * 1.4426950408889634f;  // exp((x - mx) * inv_temp) = exp2((x - mx) * c)
 
@@ -130,17 +158,20 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     __syncthreads();
     float zloc = 0.f;
     const uint32_t hi_mask = (level == 0) ? 0u : (0xFFFFFFFFu << (shift + widths[level]));
-    for (int i = tid; i < V; i += 1024) {
-      const float x = row[i];
-      const float w = exp2f((x - mx) * c);
-      if (level == 0) zloc += w;
+    for_each_elem(row, V, [&](float x, int) {
       const uint32_t key = float_key(x);
-      if ((key & hi_mask) == prefix) {
-        const int bin = (key >> shift) & (nb - 1);
+      if (level == 0) {
+        const float w = exp2f((x - mx) * c);
+        zloc += w;
+        const int bin = key >> shift;
         atomicAdd(&h_mass[bin], w);
         atomicAdd(&h_cnt[bin], 1);
+      } else if ((key & hi_mask) == prefix) {
+        const int bin = (key >> shift) & (nb - 1);
+        atomicAdd(&h_mass[bin], exp2f((x - mx) * c));
+        atomicAdd(&h_cnt[bin], 1);
       }
-    }
+    });
     if (level == 0) Z = block_reduce_sum(zloc, red);
     __syncthreads();
     const float thresh = top_p * Z;
@@ -191,12 +222,29 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   const float u = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
   const float target = u * kept_mass;
 
-  const int per_warp = ((V + 31) / 32 + 31) / 32 * 32;  // contiguous range per warp, multiple of 32
+  // each warp owns a contiguous range (multiple of 128 elements: one float4 per lane per iteration)
+  const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int per_warp = ((V + 31) / 32 + 127) / 128 * 128;
   const int lo = warp * per_warp, hi = min(V, lo + per_warp);
+  auto load4 = [&](int i, float (&x)[4]) {  // elements i..i+3 (out of range -> -inf: never kept, zero weight)
+    if (vec && i + 3 < hi) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (i + j < hi) ? row[i + j] : -INFINITY;
+    }
+  };
   float wsum = 0.f;
-  for (int i = lo + lane; i < hi; i += 32) {
-    const float x = row[i];
-    if (float_key(x) >= prefix) wsum += exp2f((x - mx) * c);
+  for (int base = lo; base < hi; base += 512) {  // 4 float4 loads in flight per lane
+    float x[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load4(base + u * 128 + lane * 4, x[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (float_key(x[u][j]) >= prefix && x[u][j] != -INFINITY) wsum += exp2f((x[u][j] - mx) * c);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
@@ -221,26 +269,55 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   if (warp == s_target_warp) {
     float acc = s_target_off;
     int found = -1, last_kept = -1;
-    for (int base = lo; base < hi && found < 0; base += 32) {
-      const int i = base + lane;
-      float w = 0.f;
-      bool kept = false;
-      if (i < hi) {
-        const float x = row[i];
-        kept = float_key(x) >= prefix;
-        if (kept) w = exp2f((x - mx) * c);
+    for (int base = lo; base < hi && found < 0; base += 128) {
+      const int i0 = base + lane * 4;
+      float x[4], w[4];
+      load4(i0, x);
+      float lsum = 0.f;
+      bool any_kept = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool kept = float_key(x[j]) >= prefix && x[j] != -INFINITY;
+        w[j] = kept ? exp2f((x[j] - mx) * c) : 0.f;
+        any_kept |= kept;
+        lsum += w[j];
       }
-      float inc = w;
+      float inc = lsum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const float t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      const bool hit = kept && (target < acc + inc);
+      const bool hit = any_kept && (target < acc + inc);
       const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-      const uint32_t keeps = __ballot_sync(0xffffffffu, kept);
-      if (keeps) last_kept = base + 31 - __clz(keeps);
-      if (hits) found = base + __ffs(hits) - 1;
+      const uint32_t keeps = __ballot_sync(0xffffffffu, any_kept);
+      if (keeps) {  // remember the last kept element seen so far (fallback for rounding at the very end)
+        const int kl = 31 - __clz(keeps);
+        int lk = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (w[j] > 0.f || (float_key(x[j]) >= prefix && x[j] != -INFINITY)) lk = i0 + j;
+        last_kept = __shfl_sync(0xffffffffu, lk, kl);
+      }
+      if (hits) {
+        const int hl = __ffs(hits) - 1;
+        // inside the hitting lane: walk its 4 elements
+        float a = acc + inc - lsum;
+        int f = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (f < 0 && w[j] > 0.f) {
+            a += w[j];
+            if (target < a) f = i0 + j;
+          }
+        }
+        if (f < 0) {  // rounding inside the lane: take its last kept element
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (w[j] > 0.f) f = i0 + j;
+        }
+        found = __shfl_sync(0xffffffffu, f, hl);
+      }
       acc += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (found < 0) found = last_kept;
@@ -254,17 +331,14 @@ using namespace pg;
 
 extern "C" int pg_argmax(const float* logits, long long ld, int* out, int B, int V, void* stream) {
   if (B <= 0 || V <= 0) return PG_ERR_ARG;
-  argmax_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, out, V);
-  pg_count_launch(1);
-  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  return launch_kernel(argmax_kernel, dim3(B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), logits, ld, out, V) == cudaSuccess
+             ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count, int B, int V,
                                float inv_temperature, float top_p, unsigned long long seed, const int* step_ptr,
                                void* stream) {
   if (B <= 0 || V <= 0 || !(inv_temperature > 0.f) || !(top_p >= 0.f)) return PG_ERR_ARG;
-  sample_top_p_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, ld, out, kept_count, V, inv_temperature,
-                                                                            top_p, seed, step_ptr);
-  pg_count_launch(1);
-  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  return launch_kernel(sample_top_p_kernel, dim3(B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), logits, ld, out,
+                       kept_count, V, inv_temperature, top_p, seed, step_ptr) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }

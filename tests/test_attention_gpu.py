@@ -93,3 +93,60 @@ def test_decode_attention_paged(B, Hq, dh, lens, splits):
     torch.cuda.synchronize()
     for b in range(B):
         assert torch.equal(dense[b, 0], k_pages[perm[b].long()].reshape(-1, dh)[: min(lens)])
+
+
+@pytest.mark.parametrize("B,Hq,dh,lens", [(4, 8, 256, [261, 300, 64, 1]), (2, 4, 64, [17, 130]), (64, 8, 256, None), (3, 8, 256, [128, 129, 65])])
+def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
+    """pg_attention_decode_fused == RoPE(q,k_new) + cache append + softmax(QK^T/sqrt(dh))V over the whole cache."""
+    from paligemma_multimodal_system_b200 import _lib
+    if lens is None:
+        lens = [260 + (i % 70) for i in range(B)]
+    page = 64
+    max_pages = (max(lens) + page - 1) // page + 1
+    num_pages = B * max_pages + 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    k_pages = (torch.randn(num_pages, page, dh, device="cuda", generator=g) * 0.5).bfloat16()
+    v_pages = (torch.randn(num_pages, page, dh, device="cuda", generator=g) * 0.5).bfloat16()
+    table = torch.randperm(num_pages, device="cuda", generator=g)[: B * max_pages].int().view(B, max_pages).contiguous()
+    qkv = torch.randn(B, (Hq + 2) * dh, device="cuda", generator=g) * 0.5
+    kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    pos = torch.tensor([l + 3 for l in lens], device="cuda", dtype=torch.int32)
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).cuda()
+    out = torch.full((B, Hq * dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ws = torch.empty(_lib.lib().pg_attention_decode_fused_workspace_floats(B, Hq, dh, max_pages), device="cuda")
+    cnt = torch.zeros(B, device="cuda", dtype=torch.int32)
+    k_before, v_before = k_pages.clone(), v_pages.clone()
+    scale = 1.0 / math.sqrt(dh)
+    for rep in range(2):  # second launch checks that the arrival counters reset themselves
+        k_pages.copy_(k_before); v_pages.copy_(v_before)
+        rc = _lib.lib().pg_attention_decode_fused(qkv.data_ptr(), pos.data_ptr(), kv_len.data_ptr(), inv_freq.data_ptr(),
+                                                  k_pages.data_ptr(), v_pages.data_ptr(), table.data_ptr(), ws.data_ptr(),
+                                                  cnt.data_ptr(), out.data_ptr(), B, Hq, 1, dh, page, max_pages, max_pages, scale,
+                                                  _lib.stream())
+        _lib.check(rc, "fused decode attn")
+        torch.cuda.synchronize()
+        assert torch.count_nonzero(cnt) == 0
+    half = dh // 2
+    rot = lambda t: torch.cat([-t[..., half:], t[..., :half]], -1)
+    for b in range(B):
+        L = lens[b]
+        ang = pos[b].float() * inv_freq
+        emb = torch.cat([ang, ang])
+        cos, sin = emb.cos(), emb.sin()
+        q = qkv[b, : Hq * dh].view(Hq, dh)
+        kn = qkv[b, Hq * dh: (Hq + 1) * dh]
+        vn = qkv[b, (Hq + 1) * dh:]
+        qr = (q * cos + rot(q) * sin).bfloat16().float()
+        kr = (kn * cos + rot(kn) * sin).bfloat16()
+        idx = table[b].long()
+        K = k_before[idx].reshape(-1, dh)[:L].clone()
+        V = v_before[idx].reshape(-1, dh)[:L].clone()
+        K[L - 1], V[L - 1] = kr, vn.bfloat16()
+        ref = torch.softmax(qr @ K.float().t() * scale, -1) @ V.float()
+        _close(out[b].view(Hq, dh), ref, 1.5e-2, f"fused decode attention row {b}")
+        # the append landed in the right page slot, nothing else in the cache changed
+        pg_, off = table[b, (L - 1) // page].item(), (L - 1) % page
+        assert (k_pages[pg_, off].float() - kr.float()).abs().max() <= 2 ** -7 * kr.float().abs().max()
+        assert torch.equal(v_pages[pg_, off], vn.bfloat16())
+    changed = (k_pages != k_before).any(-1).sum().item()
+    assert changed <= B
