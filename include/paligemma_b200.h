@@ -62,9 +62,10 @@ int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_
                  float eps, void* stream);
 
 /* GemmaRMSNorm (modeling_gemma.py:157-182): y = x * rsqrt(mean(x^2) + eps) * (1 + w); x fp32 -> y bf16.
- * Optionally zero-fills `zero_buf` (zero_count floats) for a following split-K atomic GEMM. */
+ * Optionally zero-fills `zero_buf` (zero_count floats) for a following split-K atomic GEMM, and optionally issues an L2
+ * prefetch (cp.async.bulk.prefetch.L2) of `prefetch_bytes` at `prefetch_ptr` (upcoming weights), spread over the CTAs. */
 int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
-               long long zero_count, void* stream);
+               long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream);
 
 /* SiglipVisionEmbeddings im2col (modeling_siglip.py:258-263,285-297): pixel fp32 [B,C,H,W] -> patches bf16
  * [B*(H/P)*(W/P), Kpad], column order (c, py, px) = Conv2d weight order, zero padded to Kpad. */

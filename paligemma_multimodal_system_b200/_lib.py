@@ -28,7 +28,7 @@ SIGNATURES = {
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
     "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],
-    "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p],
+    "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p, i64, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_add_pos_emb": [p, p, i32, i32, i32, p],
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
@@ -114,8 +114,9 @@ def layernorm(x, gamma, beta, eps, out_bf16=None, out_f32=None):
                              stream()), "pg_layernorm")
 
 
-def rmsnorm(x, w, out_bf16, eps=1e-6, zero_buf=None):
+def rmsnorm(x, w, out_bf16, eps=1e-6, zero_buf=None, prefetch=None, prefetch_bytes=None):
     rows, D = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
+    pf_bytes = 0 if prefetch is None else (prefetch.numel() * prefetch.element_size() if prefetch_bytes is None else prefetch_bytes)
     check(lib().pg_rmsnorm(x.data_ptr(), w.data_ptr(), out_bf16.data_ptr(), rows, D, float(eps), ptr(zero_buf),
-                           0 if zero_buf is None else zero_buf.numel(), stream()), "pg_rmsnorm")
+                           0 if zero_buf is None else zero_buf.numel(), ptr(prefetch), pf_bytes, stream()), "pg_rmsnorm")

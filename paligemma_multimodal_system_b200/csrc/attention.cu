@@ -411,11 +411,14 @@ struct AttnDecodeFusedParams {
   float* ws;              // partials: o [B*Hq][max_tiles][dh], ml [B*Hq][max_tiles][2]
   int* counters;          // [B*Hkv] arrival counters (zero on entry, reset by the combining CTA)
   bf16* out;              // [B, Hq*dh]
-  int B, Hq, Hkv, max_pages, max_tiles;
+  int B, Hq, Hkv, max_pages, max_tiles, num_splits;
   float sl2;
 };
 
-// grid (max_tiles, B*Hkv); one CTA = one 64-key tile of one (sequence, kv head); 4 warps x 16 keys
+// grid (num_splits, B*Hkv); one CTA = a contiguous range of 64-key pages of one (sequence, kv head); 4 warps x 16 keys
+// per page, K/V pages double buffered through shared memory with cp.async, online softmax across pages.
+// num_splits == 1 (enough sequences to fill the GPU): the CTA writes the output directly -- no workspace, no fences.
+// num_splits  > 1 (few sequences): per-split partials + the last CTA to arrive merges them.
 template <int DH>
 __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecodeFusedParams p) {
   using C = AttnCfg<DH>;
@@ -423,87 +426,121 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
   constexpr int HALF = DH / 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);  // [16][LDS]
-  bf16* Ks = Qs + 16 * C::LDS;                   // [64][LDS]
-  bf16* Vs = Ks + BLOCK_N * C::LDS;              // [64][LDS]
-  float* red = reinterpret_cast<float*>(Ks);     // reused after the MMAs: [4 warps][16][DH+2]
+  bf16* Ks = Qs + 16 * C::LDS;                   // [2][64][LDS]
+  bf16* Vs = Ks + 2 * BLOCK_N * C::LDS;          // [2][64][LDS]
+  float* red = reinterpret_cast<float*>(Ks);     // reused after the main loop: [4 warps][16][DH+2]
   __shared__ int s_last;
+  __shared__ bf16 new_k[DH], new_v[DH];
+  __shared__ float s_M[16], s_L[16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int split = blockIdx.x, num_splits = gridDim.x;
   const int b = blockIdx.y / p.Hkv, hk = blockIdx.y % p.Hkv;
   const int group = p.Hq / p.Hkv;
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
   const int len = p.kv_len[b];
   const int n_tiles = (len + BLOCK_N - 1) / BLOCK_N;
-  if (tile >= n_tiles) return;
+  const int tps = (n_tiles + num_splits - 1) / num_splits;
+  const int n_active = (n_tiles + tps - 1) / tps;  // splits that own at least one page
+  const int t_begin = split * tps, t_end = min(n_tiles, t_begin + tps);
+  if (t_begin >= t_end) return;
   const int new_slot = len - 1;
-  const bool owns_new = (tile == new_slot / BLOCK_N);
+  const int new_tile = new_slot / BLOCK_N;
+  const bool owns_new = (new_tile >= t_begin && new_tile < t_end);
   const long long kv_ts = static_cast<long long>(p.Hkv) * DH;
-  const int page = p.page_table[b * p.max_pages + tile];
-  bf16* kb = p.k_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
-  bf16* vb = p.v_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
-  const int n0 = tile * BLOCK_N;
-  // cached rows via cp.async; the new token's row (not in the cache yet) is filled from registers below
-  load_tile<DH, 128>(Ks, BLOCK_N, [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? kb + r * kv_ts : nullptr; });
-  load_tile<DH, 128>(Vs, BLOCK_N, [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? vb + r * kv_ts : nullptr; });
+  const int* ptab = p.page_table + b * p.max_pages;
+
+  auto load_kv = [&](int tile, int buf) {
+    const int page = ptab[tile];
+    const bf16* kb = p.k_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+    const bf16* vb = p.v_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
+    const int n0 = tile * BLOCK_N;
+    // cached rows via cp.async; the new token's row (not in the cache yet) is zero-filled here and patched below
+    load_tile<DH, 128>(Ks + buf * BLOCK_N * C::LDS, BLOCK_N,
+                       [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? kb + r * kv_ts : nullptr; });
+    load_tile<DH, 128>(Vs + buf * BLOCK_N * C::LDS, BLOCK_N,
+                       [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? vb + r * kv_ts : nullptr; });
+  };
+  load_kv(t_begin, 0);
   cp_async_commit();
 
-  // RoPE (rotate-half, modeling_gemma.py:138-151) on the query heads of this group (+ the new key when owned)
+  // RoPE (rotate-half, modeling_gemma.py:138-151) on the query heads of this group (+ the new key when owned).
+  // All global loads of a thread are issued back to back (independent), then rotated: one L2 round trip, not 20.
   const int W = (p.Hq + 2 * p.Hkv) * DH;
-  const float* row = p.qkv + static_cast<long long>(b) * W;
+  const float* __restrict__ row = p.qkv + static_cast<long long>(b) * W;
   const float posf = static_cast<float>(p.pos[b]);
   for (int i = threadIdx.x; i < HALF; i += 128) {
-    float sn, cs;
-    sincosf(posf * p.inv_freq[i], &sn, &cs);
-    for (int g = 0; g < group; ++g) {
-      const float* qh = row + (hk * group + g) * DH;
-      const float x1 = qh[i], x2 = qh[i + HALF];
-      Qs[g * C::LDS + i] = __float2bfloat16(x1 * cs - x2 * sn);
-      Qs[g * C::LDS + i + HALF] = __float2bfloat16(x2 * cs + x1 * sn);
+    float x1[16], x2[16], kx1 = 0.f, kx2 = 0.f, vx1 = 0.f, vx2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      if (g < group) {
+        const float* qh = row + (hk * group + g) * DH;
+        x1[g] = __ldcg(qh + i);
+        x2[g] = __ldcg(qh + i + HALF);
+      }
     }
     if (owns_new) {
       const float* kh = row + (p.Hq + hk) * DH;
       const float* vh = row + (p.Hq + p.Hkv + hk) * DH;
-      const float x1 = kh[i], x2 = kh[i + HALF];
-      const bf16 k1 = __float2bfloat16(x1 * cs - x2 * sn), k2 = __float2bfloat16(x2 * cs + x1 * sn);
-      const bf16 v1 = __float2bfloat16(vh[i]), v2 = __float2bfloat16(vh[i + HALF]);
-      const int r = new_slot - n0;
-      kb[r * kv_ts + i] = k1; kb[r * kv_ts + i + HALF] = k2;   // KVCache.update (modeling_gemma.py:18-57)
-      vb[r * kv_ts + i] = v1; vb[r * kv_ts + i + HALF] = v2;
+      kx1 = __ldcg(kh + i); kx2 = __ldcg(kh + i + HALF);
+      vx1 = __ldcg(vh + i); vx2 = __ldcg(vh + i + HALF);
+    }
+    float sn, cs;
+    sincosf(posf * p.inv_freq[i], &sn, &cs);
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      if (g < group) {
+        Qs[g * C::LDS + i] = __float2bfloat16(x1[g] * cs - x2[g] * sn);
+        Qs[g * C::LDS + i + HALF] = __float2bfloat16(x2[g] * cs + x1[g] * sn);
+      }
+    }
+    if (owns_new) {
+      const bf16 k1 = __float2bfloat16(kx1 * cs - kx2 * sn), k2 = __float2bfloat16(kx2 * cs + kx1 * sn);
+      const bf16 v1 = __float2bfloat16(vx1), v2 = __float2bfloat16(vx2);
+      const int page = ptab[new_tile];
+      bf16* kb = p.k_pages + (static_cast<long long>(page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
+      bf16* vb = p.v_pages + (static_cast<long long>(page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
+      kb[i] = k1; kb[i + HALF] = k2;   // KVCache.update (modeling_gemma.py:18-57)
+      vb[i] = v1; vb[i + HALF] = v2;
+      new_k[i] = k1; new_k[i + HALF] = k2;  // staged copy, patched into the shared-memory page below
+      new_v[i] = v1; new_v[i + HALF] = v2;
     }
   }
   // zero the padding rows / pad columns of Q
   for (int idx = threadIdx.x; idx < 16 * C::DHP; idx += 128) {
-    const int r = idx / C::DHP, c = idx % C::DHP;
-    if (r >= group || c >= DH) Qs[r * C::LDS + c] = __float2bfloat16(0.f);
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-  if (owns_new) {  // place the new row into the staged tile (after the zero-filling cp.async has landed)
-    const int r = new_slot - n0;
-    const float* kh = row + (p.Hq + hk) * DH;
-    const float* vh = row + (p.Hq + p.Hkv + hk) * DH;
-    for (int i = threadIdx.x; i < HALF; i += 128) {
-      float sn, cs;
-      sincosf(posf * p.inv_freq[i], &sn, &cs);
-      const float x1 = kh[i], x2 = kh[i + HALF];
-      Ks[r * C::LDS + i] = __float2bfloat16(x1 * cs - x2 * sn);
-      Ks[r * C::LDS + i + HALF] = __float2bfloat16(x2 * cs + x1 * sn);
-      Vs[r * C::LDS + i] = __float2bfloat16(vh[i]);
-      Vs[r * C::LDS + i + HALF] = __float2bfloat16(vh[i + HALF]);
-    }
-    __syncthreads();
+    const int r = idx / C::DHP, cc = idx % C::DHP;
+    if (r >= group || cc >= DH) Qs[r * C::LDS + cc] = __float2bfloat16(0.f);
   }
 
   float o[C::DHP / 8][4];
 #pragma unroll
   for (int i = 0; i < C::DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m_run[2], l_run[2];
-  {
-    const uint32_t q_addr = smem_u32(Qs + (lane & 15) * C::LDS + (lane >> 4) * 8);
-    const bf16* Kt = Ks + warp * 16 * C::LDS;
-    const bf16* Vt = Vs + warp * 16 * C::LDS;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const uint32_t q_addr = smem_u32(Qs + (lane & 15) * C::LDS + (lane >> 4) * 8);
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) {
+      load_kv(t + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (t == new_tile) {  // patch the new token's row into the staged page
+      const int r = new_slot - new_tile * BLOCK_N;
+      for (int i = threadIdx.x; i < DH; i += 128) {
+        Ks[(buf * BLOCK_N + r) * C::LDS + i] = new_k[i];
+        Vs[(buf * BLOCK_N + r) * C::LDS + i] = new_v[i];
+      }
+      __syncthreads();
+    }
+    // this warp owns keys [16*warp, 16*warp+16) of the page
+    const bf16* Kt = Ks + (buf * BLOCK_N + warp * 16) * C::LDS;
+    const bf16* Vt = Vs + (buf * BLOCK_N + warp * 16) * C::LDS;
     float s[2][4];
     s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
     const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
@@ -515,28 +552,34 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
       mma_bf16_16816(s[0], a, b0, b1);
       mma_bf16_16816(s[1], a, b2, b3);
     }
-    const int kbase = n0 + warp * 16;
+    const int kbase = t * BLOCK_N + warp * 16;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int key = kbase + nt * 8 + (lane & 3) * 2;
       if (key >= len) s[nt][0] = s[nt][2] = -INFINITY;
       if (key + 1 >= len) s[nt][1] = s[nt][3] = -INFINITY;
     }
+    float alpha[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       float mx = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float msc = (mx == -INFINITY) ? 0.f : mx * p.sl2;
-      m_run[r] = mx;
+      const float m_new = fmaxf(m_run[r], mx);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      alpha[r] = exp2f((m_run[r] - m_safe) * p.sl2);
+      const float msc = m_safe * p.sl2;
+      m_run[r] = m_new;
       s[0][2 * r] = exp2f(s[0][2 * r] * p.sl2 - msc);
       s[0][2 * r + 1] = exp2f(s[0][2 * r + 1] * p.sl2 - msc);
       s[1][2 * r] = exp2f(s[1][2 * r] * p.sl2 - msc);
       s[1][2 * r + 1] = exp2f(s[1][2 * r + 1] * p.sl2 - msc);
-      float rs = s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
-      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-      l_run[r] = rs;
+      l_run[r] = l_run[r] * alpha[r] + s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < C::DHP / 8; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
     }
     uint32_t a[4];
     a[0] = pack_bf16(s[0][0], s[0][1]);
@@ -551,10 +594,16 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
       mma_bf16_16816(o[2 * dp], a, b0, b1);
       mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
     }
+    __syncthreads();  // the buffer is overwritten by the load issued in the next iteration
   }
-  __syncthreads();  // all warps are done with Ks/Vs: reuse as the reduction buffer
 
+  // ---- merge the 4 warps (disjoint key subsets) through shared memory ----
   constexpr int RLD = DH + 2;  // [.., DH] = m (scaled, log2 domain), [.., DH+1] = l
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
   {
     const int r0 = lane >> 2;
     float* dst0 = red + (warp * 16 + r0) * RLD;
@@ -573,8 +622,9 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
     }
   }
   __syncthreads();
-  float* ws_o = p.ws;
-  float* ws_ml = p.ws + static_cast<long long>(p.B) * p.Hq * p.max_tiles * DH;
+  const long long hq0 = static_cast<long long>(b) * p.Hq + hk * group;  // first query head of this group
+  float* __restrict__ ws_o = p.ws;
+  float* __restrict__ ws_ml = p.ws + static_cast<long long>(p.B) * p.Hq * p.max_tiles * DH;
   for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
     const int r = idx / DH, col = idx % DH;
     float M = -INFINITY;
@@ -588,35 +638,59 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
       acc += red[(w * 16 + r) * RLD + col] * wgt;
       Lsum += red[(w * 16 + r) * RLD + DH + 1] * wgt;
     }
-    const long long hrow = (static_cast<long long>(b) * p.Hq + hk * group + r) * p.max_tiles + tile;
-    __stcg(ws_o + hrow * DH + col, acc);
-    if (col == 0) {
-      __stcg(ws_ml + hrow * 2, M);
-      __stcg(ws_ml + hrow * 2 + 1, Lsum);
+    if (num_splits == 1) {
+      p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc / Lsum);
+    } else {
+      const long long hrow = (hq0 + r) * p.max_tiles + split;
+      __stcg(ws_o + hrow * DH + col, acc);
+      if (col == 0) {
+        __stcg(ws_ml + hrow * 2, M);
+        __stcg(ws_ml + hrow * 2 + 1, Lsum);
+      }
     }
   }
-  // ---- the last CTA of this (sequence, kv head) to arrive merges the tile partials ----
+  if (num_splits == 1) return;
+
+  // ---- the last CTA of this (sequence, kv head) to arrive merges the split partials ----
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const int old = atomicAdd(p.counters + blockIdx.y, 1);
-    s_last = (old == n_tiles - 1);
+    s_last = (old == n_active - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (threadIdx.x < group) {
+    const int r = threadIdx.x;
+    const long long hbase = (hq0 + r) * p.max_tiles;
+    float M = -INFINITY;
+    for (int t = 0; t < n_active; ++t) M = fmaxf(M, __ldcg(ws_ml + (hbase + t) * 2));
+    float Lsum = 0.f;
+    for (int t = 0; t < n_active; ++t) Lsum += __ldcg(ws_ml + (hbase + t) * 2 + 1) * exp2f(__ldcg(ws_ml + (hbase + t) * 2) - M);
+    s_M[r] = M;
+    s_L[r] = Lsum;
+  }
+  __syncthreads();
+  float* wgt = red;  // [group][n_active]  (the staging area is free by now)
+  for (int idx = threadIdx.x; idx < group * n_active; idx += 128) {
+    const int r = idx / n_active, t = idx % n_active;
+    wgt[idx] = exp2f(__ldcg(ws_ml + ((hq0 + r) * p.max_tiles + t) * 2) - s_M[r]) / s_L[r];
+  }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
     const int r = idx / DH, col = idx % DH;
-    const long long hbase = (static_cast<long long>(b) * p.Hq + hk * group + r) * p.max_tiles;
-    float M = -INFINITY;
-    for (int t = 0; t < n_tiles; ++t) M = fmaxf(M, __ldcg(ws_ml + (hbase + t) * 2));
-    float acc = 0.f, Lsum = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const float wgt = exp2f(__ldcg(ws_ml + (hbase + t) * 2) - M);
-      acc += __ldcg(ws_o + (hbase + t) * DH + col) * wgt;
-      Lsum += __ldcg(ws_ml + (hbase + t) * 2 + 1) * wgt;
+    const long long hbase = (hq0 + r) * p.max_tiles;
+    float acc = 0.f;
+    for (int t0 = 0; t0 < n_active; t0 += 8) {  // 8 independent loads in flight
+      float v[8];
+#pragma unroll
+      for (int tt = 0; tt < 8; ++tt) v[tt] = (t0 + tt < n_active) ? __ldcg(ws_o + (hbase + t0 + tt) * DH + col) : 0.f;
+#pragma unroll
+      for (int tt = 0; tt < 8; ++tt)
+        if (t0 + tt < n_active) acc += v[tt] * wgt[r * n_active + t0 + tt];
     }
-    p.out[(static_cast<long long>(b) * p.Hq + hk * group + r) * DH + col] = __float2bfloat16(acc / Lsum);
+    p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc);
   }
   if (threadIdx.x == 0) p.counters[blockIdx.y] = 0;  // ready for the next launch (stream ordered)
 }
@@ -624,7 +698,7 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
 template <int DH>
 static int launch_decode_fused(const AttnDecodeFusedParams& p, cudaStream_t st) {
   using C = AttnCfg<DH>;
-  constexpr int smem_main = (16 + 2 * 64) * C::LDS * 2;
+  constexpr int smem_main = (16 + 4 * 64) * C::LDS * 2;
   constexpr int smem_red = 16 * C::LDS * 2 + 4 * 16 * (DH + 2) * 4;
   constexpr int smem = smem_main > smem_red ? smem_main : smem_red;
   static bool configured = false;
@@ -635,7 +709,7 @@ static int launch_decode_fused(const AttnDecodeFusedParams& p, cudaStream_t st) 
     }
     configured = true;
   }
-  dim3 grid(p.max_tiles, p.B * p.Hkv);
+  dim3 grid(p.num_splits, p.B * p.Hkv);
   return launch_kernel(attn_decode_fused_kernel<DH>, grid, dim3(128), smem, st, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
@@ -744,6 +818,14 @@ extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const
   p.k_pages = static_cast<bf16*>(k_pages); p.v_pages = static_cast<bf16*>(v_pages);
   p.page_table = page_table; p.ws = workspace; p.counters = counters; p.out = static_cast<bf16*>(out);
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages; p.max_tiles = max_tiles;
+  // enough (sequence, kv head) pairs to occupy the GPU -> one CTA streams the whole sequence; otherwise split the KV
+  // length so that ~2 CTAs per SM are in flight (partials + last-arriver merge)
+  int splits = 1;
+  if (B * Hkv < 64) {
+    splits = (2 * 148 + B * Hkv - 1) / (B * Hkv);
+    if (splits > max_tiles) splits = max_tiles;
+  }
+  p.num_splits = splits;
   p.sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {

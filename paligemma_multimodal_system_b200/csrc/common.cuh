@@ -112,6 +112,11 @@ PG_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int
 }
 PG_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// L2 prefetch of a contiguous global range (bytes: multiple of 16), executed by the bulk-copy engine
+PG_DEVINL void prefetch_l2_bulk(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+
 // PDL (programmatic dependent launch)
 PG_DEVINL void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 PG_DEVINL void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

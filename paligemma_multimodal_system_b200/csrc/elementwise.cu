@@ -65,10 +65,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       bf16* __restrict__ y, int D, float eps, float* __restrict__ zero_buf,
-                                                      long long zero_count) {
+                                                      long long zero_count, const uint8_t* __restrict__ pf_ptr,
+                                                      long long pf_bytes) {
   extern __shared__ float row[];
   float* red = row + D;
   const long long r = blockIdx.x;
+  if (pf_ptr != nullptr) {
+    // Pull upcoming weights (immutable, independent of the previous kernel) into L2 while the latency-bound part of
+    // the layer runs; issued before the dependency wait.
+    constexpr long long CH = 16384;
+    const long long per = ((pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
+    const long long lo = r * per, hi = min(pf_bytes, lo + per);
+    for (long long off = lo + threadIdx.x * CH; off < hi; off += blockDim.x * CH)
+      prefetch_l2_bulk(pf_ptr + off, static_cast<uint32_t>(min(CH, hi - off) & ~15ll));
+  }
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
   if (zero_buf != nullptr) {  // zero-fill for the split-K GEMM that follows
@@ -360,10 +370,12 @@ extern "C" int pg_layernorm(const float* x, const float* gamma, const float* bet
 }
 
 extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
-                          long long zero_count, void* stream) {
+                          long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
+  if (prefetch_ptr != nullptr && ((reinterpret_cast<uintptr_t>(prefetch_ptr) & 15) || prefetch_bytes < 0)) return PG_ERR_ARG;
   return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), (D + 33) * sizeof(float), PG_ST(stream), x, w,
-                       static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+                       static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count, static_cast<const uint8_t*>(prefetch_ptr),
+                       prefetch_bytes) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream) {

@@ -1,10 +1,9 @@
 // Sampling kernels: greedy argmax (inference.py:67-68) and temperature + top-p (inference.py:63-66,90-106).
 //
 // Top-p without a sort: the kept set of _sample_top_p is {i : sum of probs strictly greater than p_i <= top_p}, i.e. a
-// threshold on the logit.  The threshold is found by a 3-level radix select (11+11+10 bits of the order-preserving
-// integer image of the fp32 logit) whose histogram bins accumulate probability MASS; the token is then drawn by inverse
-// CDF over the kept set in vocabulary order with a counter-based RNG.  One CTA per row; the row (1 MB at V = 257 216)
-// stays L2 resident across the passes.
+// threshold on the logit.  The threshold is found by a 2-level histogram select (2048 x 2048 linear bins in logit space
+// whose bins accumulate probability MASS); the token is then drawn by inverse CDF over the kept set in vocabulary order
+// with a counter-based RNG.  One CTA per row; the row (1 MB at V = 257 216) stays L2 resident across the passes.
 #include "common.cuh"
 #include "paligemma_b200.h"
 
@@ -117,7 +116,14 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
   return r.f[32];
 }
 
-// One CTA (1024 threads) per row.
+// One CTA (1024 threads) per row.  Four vectorised passes over the (L2-resident) row:
+//   0. online max / sum-exp  ->  mx, Z
+//   1. histogram of t = (mx - x) * inv_temp over [0, t_cut) in 2048 LINEAR bins carrying probability mass.  Elements with
+//      t >= t_cut are provably outside the kept set (their total mass is < (1 - top_p) * Z / 128) and are skipped, which
+//      also keeps shared-memory atomic contention low: the bins that matter are spread linearly in logit space.
+//   2. the same inside the selected bin (2048 sub-bins): threshold resolved to t_cut / 2^22 (~5e-6 in logit units);
+//      values closer than that are treated as ties and kept together.
+//   3. inverse-CDF walk over the kept set {t < t*} in vocabulary order.
 __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ out,
                                                             int* __restrict__ kept_count, int V, float inv_temp, float top_p,
                                                             unsigned long long seed, const int* __restrict__ step_ptr) {
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   __shared__ float s_above_mass;
   __shared__ int s_above_cnt;
   __shared__ float s_bin_mass;
+  __shared__ float s_tot_mass;
   __shared__ int s_bin_cnt;
   __shared__ int s_target_warp;
   __shared__ float s_target_off;
@@ -139,49 +146,58 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
 
-  // pass 0: max
-  float mx = -INFINITY;
-  for_each_elem(row, V, [&](float v, int) { mx = fmaxf(mx, v); });
-  mx = block_reduce_max(mx, red);
+  // pass 0: online softmax statistics
   const float c = inv_temp * 1.4426950408889634f;  // exp((x - mx) * inv_temp) = exp2((x - mx) * c)
+  float m_loc = -INFINITY, z_loc = 0.f;
+  for_each_elem(row, V, [&](float v, int) {
+    if (v > m_loc) {
+      z_loc = z_loc * exp2f((m_loc - v) * c) + 1.f;
+      m_loc = v;
+    } else {
+      z_loc += exp2f((v - m_loc) * c);
+    }
+  });
+  const float mx = block_reduce_max(m_loc, red);
+  const float Z = block_reduce_sum(m_loc == -INFINITY ? 0.f : z_loc * exp2f((m_loc - mx) * c), red);
+  const float thresh = top_p * Z;
 
-  // radix select on the logit key, bins carry probability mass (unnormalised, relative to the row max)
-  uint32_t prefix = 0;        // key bits decided so far
-  float above_mass = 0.f;     // mass of keys strictly above the current prefix range
+  // elements with t >= t_cut cannot be kept: V * exp(-t_cut) <= (1 - top_p) * Z / 128
+  float t_cut = 100.f;
+  if (top_p < 1.f) t_cut = fminf(100.f, logf(static_cast<float>(V) * 128.f / ((1.f - top_p) * Z)));
+  t_cut = fmaxf(t_cut, 1e-3f);
+
+  // Every element gets a (coarse, fine) bin pair from FIXED float expressions, so the histogram passes and the final
+  // kept test classify it identically:  b0 = floor(t * NB / t_cut),  b1 = clamp(floor((t - lo1) * NB / bw0)).
+  const float inv_w0 = static_cast<float>(NB) / t_cut;
+  const float bw0 = t_cut / static_cast<float>(NB);
+  auto coarse_bin = [&](float x, float& t) -> int {  // -1: outside [0, t_cut) -> never kept
+    t = (mx - x) * inv_temp;
+    const float u = t * inv_w0;
+    if (!(t < t_cut) || !(u < static_cast<float>(NB))) return -1;
+    return min(NB - 1, static_cast<int>(u));
+  };
+  float lo1 = 0.f, inv_w1 = 0.f;
+  auto fine_bin = [&](float t) -> int {
+    const float u = (t - lo1) * inv_w1;
+    return u < 0.f ? 0 : min(NB - 1, static_cast<int>(u));
+  };
+  int sel0 = 0, sel1 = 0;
+  float above_mass = 0.f;  // mass of the bins before the selected one (all kept)
   int above_cnt = 0;
-  float Z = 0.f;
-  const int shifts[3] = {21, 10, 0};
-  const int widths[3] = {11, 11, 10};
-  for (int level = 0; level < 3; ++level) {
-    const int shift = shifts[level], nb = 1 << widths[level];
-    for (int i = tid; i < NB; i += 1024) { h_mass[i] = 0.f; h_cnt[i] = 0; }
-    __syncthreads();
-    float zloc = 0.f;
-    const uint32_t hi_mask = (level == 0) ? 0u : (0xFFFFFFFFu << (shift + widths[level]));
-    for_each_elem(row, V, [&](float x, int) {
-      const uint32_t key = float_key(x);
-      if (level == 0) {
-        const float w = exp2f((x - mx) * c);
-        zloc += w;
-        const int bin = key >> shift;
-        atomicAdd(&h_mass[bin], w);
-        atomicAdd(&h_cnt[bin], 1);
-      } else if ((key & hi_mask) == prefix) {
-        const int bin = (key >> shift) & (nb - 1);
-        atomicAdd(&h_mass[bin], exp2f((x - mx) * c));
-        atomicAdd(&h_cnt[bin], 1);
-      }
-    });
-    if (level == 0) Z = block_reduce_sum(zloc, red);
-    __syncthreads();
-    const float thresh = top_p * Z;
-    // descending scan: thread t owns bins (nb-1-2t, nb-2-2t); "before" = mass of all higher bins (+ above_mass)
-    const int b0 = nb - 1 - 2 * tid, b1 = nb - 2 - 2 * tid;
-    const float m0 = (b0 >= 0) ? h_mass[b0] : 0.f, m1 = (b1 >= 0) ? h_mass[b1] : 0.f;
-    const int c0 = (b0 >= 0) ? h_cnt[b0] : 0, c1 = (b1 >= 0) ? h_cnt[b1] : 0;
-    float ms = m0 + m1;
-    int cs = c0 + c1;
-    float ims = ms;  // inclusive scans across threads
+  const bool want_cnt = kept_count != nullptr;
+
+  // Shared-memory atomics are the cost of a histogram pass (~1-2 cycles per element per SM), so the coarse level is
+  // bracketed first: a 1/16 subsample locates the threshold bin to within +-D bins; the full pass then only bins
+  // the elements inside the bracket (everything below it is summed in registers, everything above is ignored) and
+  // VERIFIES that the bracket really contains the threshold -- otherwise it is redone over the whole range.
+  auto scan_select = [&](float base_mass, int base_cnt, int& sel_out) {
+    // ascending-t scan: thread owns bins (2 tid, 2 tid + 1); "before" = kept mass of all smaller t
+    const int b0 = 2 * tid, b1 = 2 * tid + 1;
+    const float m0 = h_mass[b0], m1 = h_mass[b1];
+    const int c0 = h_cnt[b0], c1 = h_cnt[b1];
+    const float ms = m0 + m1;
+    const int cs = c0 + c1;
+    float ims = ms;
     int ics = cs;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -191,60 +207,142 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     }
     __syncthreads();
     if (lane == 31) { red.f[warp] = ims; red.i[warp] = ics; }
-    if (tid == 0) s_bin = 0x7fffffff;
+    if (tid == 0) s_bin = -1;
     __syncthreads();
-    float offm = above_mass;
-    int offc = above_cnt;
+    float offm = base_mass;
+    int offc = base_cnt;
     for (int w = 0; w < warp; ++w) { offm += red.f[w]; offc += red.i[w]; }
     const float before0 = offm + ims - ms, before1 = before0 + m0;
     const int cbefore0 = offc + ics - cs, cbefore1 = cbefore0 + c0;
-    // lowest non-empty bin whose "before" mass is still <= thresh
-    if (b1 >= 0 && c1 > 0 && before1 <= thresh) atomicMin(&s_bin, b1);
-    else if (b0 >= 0 && c0 > 0 && before0 <= thresh) atomicMin(&s_bin, b0);
+    // the LAST non-empty bin (largest t) whose preceding mass is still <= thresh holds the threshold
+    if (m1 > 0.f && before1 <= thresh) atomicMax(&s_bin, b1);
+    else if (m0 > 0.f && before0 <= thresh) atomicMax(&s_bin, b0);
     __syncthreads();
-    int sel = s_bin;
-    if (sel == 0x7fffffff) sel = nb - 1;  // cannot happen for level 0 (the max element always qualifies); defensive
+    const int sel = s_bin;
     if (b0 == sel) { s_above_mass = before0; s_above_cnt = cbefore0; s_bin_mass = m0; s_bin_cnt = c0; }
     if (b1 == sel) { s_above_mass = before1; s_above_cnt = cbefore1; s_bin_mass = m1; s_bin_cnt = c1; }
+    if (tid == 1023) { s_tot_mass = before1 + m1; }  // mass of everything binned (+ base)
     __syncthreads();
-    above_mass = s_above_mass;
-    above_cnt = s_above_cnt;
-    prefix |= static_cast<uint32_t>(sel) << shift;
+    sel_out = sel;
+  };
+  auto clear_hist = [&]() {
+    for (int i = tid; i < NB; i += 1024) { h_mass[i] = 0.f; h_cnt[i] = 0; }
     __syncthreads();
+  };
+
+  // ---- subsample (every 16th group of 4 elements) -> estimated threshold bin ----
+  int bl = 0, bh = NB - 1;
+  if (V >= 16384) {
+    clear_hist();
+    for (int i = tid * 64; i < V; i += 1024 * 64) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (i + j < V) {
+          float t;
+          const float x = row[i + j];
+          const int b0 = coarse_bin(x, t);
+          if (b0 >= 0) atomicAdd(&h_mass[b0], 16.f * exp2f((x - mx) * c));
+        }
+      }
+    }
+    __syncthreads();
+    int est;
+    scan_select(0.f, 0, est);
+    if (est >= 0) {
+      const int D = max(8, static_cast<int>(0.25f * inv_w0) + 1);
+      bl = max(0, est - D);
+      bh = min(NB - 1, est + D);
+    }
   }
-  // kept set = keys >= prefix ; kept mass = above_mass + mass of the threshold value's ties
+  // ---- full coarse pass over the bracket (retry over the whole range if the bracket missed) ----
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    clear_hist();
+    float m_below = 0.f;
+    int c_below = 0;
+    for_each_elem(row, V, [&](float x, int) {
+      float t;
+      const int b0 = coarse_bin(x, t);
+      if (b0 < 0 || b0 > bh) return;
+      const float w = exp2f((x - mx) * c);
+      if (b0 < bl) {
+        m_below += w;
+        ++c_below;
+      } else {
+        atomicAdd(&h_mass[b0], w);
+        if (want_cnt) atomicAdd(&h_cnt[b0], 1);
+      }
+    });
+    const float base_m = block_reduce_sum(m_below, red);
+    const int base_c = static_cast<int>(block_reduce_sum(static_cast<float>(c_below), red) + 0.5f);
+    __syncthreads();
+    scan_select(base_m, base_c, sel0);
+    const bool ok = (sel0 >= 0) && (bh == NB - 1 || s_tot_mass > thresh) && (bl == 0 || base_m <= thresh);
+    __syncthreads();
+    if (ok) break;
+    bl = 0;
+    bh = NB - 1;
+    sel0 = 0;
+  }
+  if (sel0 < 0) sel0 = 0;
+  above_mass = s_above_mass;
+  above_cnt = s_above_cnt;
+  lo1 = static_cast<float>(sel0) * bw0;
+  inv_w1 = static_cast<float>(NB) / bw0;
+  __syncthreads();
+  // ---- fine level inside the selected coarse bin ----
+  clear_hist();
+  for_each_elem(row, V, [&](float x, int) {
+    float t;
+    if (coarse_bin(x, t) != sel0) return;
+    const int bin = fine_bin(t);
+    atomicAdd(&h_mass[bin], exp2f((x - mx) * c));
+    if (want_cnt) atomicAdd(&h_cnt[bin], 1);
+  });
+  __syncthreads();
+  scan_select(above_mass, above_cnt, sel1);
+  if (sel1 < 0) sel1 = 0;
+  above_mass = s_above_mass;
+  above_cnt = s_above_cnt;
+  // kept set: coarse bin < sel0, or coarse bin == sel0 and fine bin <= sel1 (the selected finest bin is kept whole)
   const float kept_mass = above_mass + s_bin_mass;
   if (tid == 0 && kept_count) kept_count[blockIdx.x] = above_cnt + s_bin_cnt;
+  auto is_kept = [&](float x) -> bool {
+    float t;
+    const int b0 = coarse_bin(x, t);
+    if (b0 < 0 || b0 > sel0) return false;
+    if (b0 < sel0) return true;
+    return fine_bin(t) <= sel1;
+  };
 
   // draw u in (0,1) and walk the kept set in vocabulary order
   const int step = step_ptr ? *step_ptr : 0;
   const uint64_t rnd = splitmix64(seed ^ splitmix64((static_cast<uint64_t>(step) << 32) | blockIdx.x));
-  const float u = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
-  const float target = u * kept_mass;
+  const float u01 = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
+  const float target = u01 * kept_mass;
 
   // each warp owns a contiguous range (multiple of 128 elements: one float4 per lane per iteration)
   const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
   const int per_warp = ((V + 31) / 32 + 127) / 128 * 128;
-  const int lo = warp * per_warp, hi = min(V, lo + per_warp);
-  auto load4 = [&](int i, float (&x)[4]) {  // elements i..i+3 (out of range -> -inf: never kept, zero weight)
-    if (vec && i + 3 < hi) {
+  const int lo_i = warp * per_warp, hi_i = min(V, lo_i + per_warp);
+  auto load4 = [&](int i, float (&x)[4]) {  // elements i..i+3 (out of range -> -inf: never kept)
+    if (vec && i + 3 < hi_i) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
       x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = (i + j < hi) ? row[i + j] : -INFINITY;
+      for (int j = 0; j < 4; ++j) x[j] = (i + j < hi_i) ? row[i + j] : -INFINITY;
     }
   };
   float wsum = 0.f;
-  for (int base = lo; base < hi; base += 512) {  // 4 float4 loads in flight per lane
+  for (int base = lo_i; base < hi_i; base += 512) {  // 4 float4 loads in flight per lane
     float x[4][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load4(base + u * 128 + lane * 4, x[u]);
+    for (int q = 0; q < 4; ++q) load4(base + q * 128 + lane * 4, x[q]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (float_key(x[u][j]) >= prefix && x[u][j] != -INFINITY) wsum += exp2f((x[u][j] - mx) * c);
+        if (is_kept(x[q][j])) wsum += exp2f((x[q][j] - mx) * c);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
@@ -269,18 +367,17 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   if (warp == s_target_warp) {
     float acc = s_target_off;
     int found = -1, last_kept = -1;
-    for (int base = lo; base < hi && found < 0; base += 128) {
+    for (int base = lo_i; base < hi_i && found < 0; base += 128) {
       const int i0 = base + lane * 4;
       float x[4], w[4];
       load4(i0, x);
       float lsum = 0.f;
-      bool any_kept = false;
+      int lk = -1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool kept = float_key(x[j]) >= prefix && x[j] != -INFINITY;
-        w[j] = kept ? exp2f((x[j] - mx) * c) : 0.f;
-        any_kept |= kept;
-        lsum += w[j];
+        const bool kept = is_kept(x[j]);
+        w[j] = kept ? exp2f((x[j] - mx) * c) : -1.f;  // -1 marks "not kept" (a kept weight may underflow to 0)
+        if (kept) { lk = i0 + j; lsum += w[j]; }
       }
       float inc = lsum;
 #pragma unroll
@@ -288,34 +385,22 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
         const float t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      const bool hit = any_kept && (target < acc + inc);
+      const bool hit = (lk >= 0) && (target < acc + inc);
       const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-      const uint32_t keeps = __ballot_sync(0xffffffffu, any_kept);
-      if (keeps) {  // remember the last kept element seen so far (fallback for rounding at the very end)
-        const int kl = 31 - __clz(keeps);
-        int lk = -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (w[j] > 0.f || (float_key(x[j]) >= prefix && x[j] != -INFINITY)) lk = i0 + j;
-        last_kept = __shfl_sync(0xffffffffu, lk, kl);
-      }
+      const uint32_t keeps = __ballot_sync(0xffffffffu, lk >= 0);
+      if (keeps) last_kept = __shfl_sync(0xffffffffu, lk, 31 - __clz(keeps));
       if (hits) {
         const int hl = __ffs(hits) - 1;
-        // inside the hitting lane: walk its 4 elements
-        float a = acc + inc - lsum;
+        float a = acc + inc - lsum;  // mass before this lane's elements
         int f = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (f < 0 && w[j] > 0.f) {
+          if (f < 0 && w[j] >= 0.f) {
             a += w[j];
             if (target < a) f = i0 + j;
           }
         }
-        if (f < 0) {  // rounding inside the lane: take its last kept element
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (w[j] > 0.f) f = i0 + j;
-        }
+        if (f < 0) f = lk;  // rounding inside the lane
         found = __shfl_sync(0xffffffffu, f, hl);
       }
       acc += __shfl_sync(0xffffffffu, inc, 31);

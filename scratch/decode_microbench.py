@@ -1,0 +1,82 @@
+"""Steady-state timing of each decode-step kernel (3B shapes, B=64), rotating over 18 layers' weights (cold L2)."""
+import math, os, sys, torch
+sys.path.insert(0, '.')
+from paligemma_multimodal_system_b200 import _lib
+L = _lib.lib()
+B, D, F, Hq, Hkv, dh, V, NL = int(os.environ.get("MB_B", 64)), 2048, 16384, 8, 1, 256, 257216, 18
+W = (Hq + 2 * Hkv) * dh
+dev = "cuda"
+def rnd(*s): return (torch.randn(*s, device=dev) * 0.02).bfloat16()
+qkv_w = [rnd(W, D) for _ in range(NL)]
+o_w = [rnd(D, D) for _ in range(NL)]
+gu_w = [rnd(2 * F, D) for _ in range(NL)]
+down_w = [rnd(D, F) for _ in range(NL)]
+head_w = rnd(V, D); head_b = torch.randn(V, device=dev)
+hn = rnd(B, D); att = rnd(B, Hq * dh); mid = rnd(B, F)
+h = torch.randn(B, D, device=dev); qkv = torch.zeros(B, W, device=dev)
+midout = torch.empty(B, F, device=dev, dtype=torch.bfloat16)
+logits = torch.empty(B, V, device=dev)
+ln_w = torch.zeros(D, device=dev)
+hn_out = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+
+def timeit(name, fn, bytes_per_launch, reps=3):
+    for i in range(NL): fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for i in range(NL): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * NL)
+    print(f"{name:34s} {us:8.2f} us   {bytes_per_launch / us / 1e3:8.1f} GB/s  ideal {bytes_per_launch / 6550.7e3:6.2f} us")
+
+def graph_time(name, fn, bytes_per_launch, reps=5):
+    """same, but the 18 launches captured in one CUDA graph (no host launch overhead)"""
+    for i in range(NL): fn(i)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for i in range(NL): fn(i)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * NL)
+    print(f"{name:34s} {us:8.2f} us   {bytes_per_launch / us / 1e3:8.1f} GB/s  ideal {bytes_per_launch / 6550.7e3:6.2f} us   [graph]")
+
+for pdl in (1,):
+    L.pg_set_pdl(pdl)
+    print(f"==== PDL={pdl}  B={B}")
+    for sp in (7, 14):
+        graph_time(f"qkv split{sp}", lambda i: _lib.gemm(hn, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), W * D * 2)
+    for sp in (9, 18):
+        graph_time(f"o split{sp}", lambda i: _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), D * D * 2)
+    graph_time("gate-up geglu", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
+    for sp in (9, 18):
+        graph_time(f"down split{sp}", lambda i: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), D * F * 2)
+    graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
+    graph_time("rmsnorm", lambda i: _lib.rmsnorm(h, ln_w, hn_out), B * D * 6)
+    def layer(i):
+        _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv)
+        _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
+        _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
+        _lib.rmsnorm(h, ln_w, hn_out)
+        _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+        _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
+    graph_time("layer (no attention)", layer, (W * D + D * D + 3 * F * D) * 2)
+    for gu_mb, dn_mb in ((0, 67), (32, 67), (64, 67), (100, 0), (134, 0), (134, 67), (64, 32)):
+        def layer_pf(i, gu_mb=gu_mb, dn_mb=dn_mb):
+            # spin a little like the attention would (latency-bound part): qkv + o gemm + 2 rmsnorm already there
+            _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv, prefetch=down_w[i] if dn_mb else None, prefetch_bytes=dn_mb << 20)
+            _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
+            _lib.rmsnorm(h, ln_w, hn_out, prefetch=gu_w[i] if gu_mb else None, prefetch_bytes=gu_mb << 20)   # stands in for attention
+            _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
+            _lib.rmsnorm(h, ln_w, hn_out)
+            _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+            _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=18)
+        graph_time(f"layer + L2 prefetch gu {gu_mb} MB, down {dn_mb} MB", layer_pf, (W * D + D * D + 3 * F * D) * 2)
+    timeit("layer (no attention) eager", layer, (W * D + D * D + 3 * F * D) * 2)
