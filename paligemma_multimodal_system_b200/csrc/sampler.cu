@@ -4,6 +4,8 @@
 // threshold on the logit.  The threshold is found by a 2-level histogram select (2048 x 2048 linear bins in logit space
 // whose bins accumulate probability MASS); the token is then drawn by inverse CDF over the kept set in vocabulary order
 // with a counter-based RNG.  One CTA per row; the row (1 MB at V = 257 216) stays L2 resident across the passes.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "paligemma_b200.h"
 
@@ -116,87 +118,148 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
   return r.f[32];
 }
 
-// One CTA (1024 threads) per row.  Four vectorised passes over the (L2-resident) row:
-//   0. online max / sum-exp  ->  mx, Z
-//   1. histogram of t = (mx - x) * inv_temp over [0, t_cut) in 2048 LINEAR bins carrying probability mass.  Elements with
-//      t >= t_cut are provably outside the kept set (their total mass is < (1 - top_p) * Z / 128) and are skipped, which
-//      also keeps shared-memory atomic contention low: the bins that matter are spread linearly in logit space.
-//   2. the same inside the selected bin (2048 sub-bins): threshold resolved to t_cut / 2^22 (~5e-6 in logit units);
-//      values closer than that are treated as ties and kept together.
-//   3. inverse-CDF walk over the kept set {t < t*} in vocabulary order.
+// -------------------------------------------------------------------------------------------------------------------
+// top-p sampler: one thread-block CLUSTER of R CTAs (1024 threads each) per row; each warp owns a contiguous segment of
+// the row; cross-CTA reductions and histogram merges go through distributed shared memory.
+//
+//   P0  row max                                                       (no transcendental)
+//   PS  1/16 subsample -> histogram of u = (mx - x) * inv_temp * NB / t_cut -> estimated threshold bin -> bracket [bl, bh]
+//   P1  full pass: w = exp2(..) for every element; mass below / inside (shared-memory atomics, only the bracket) / above
+//       the bracket -> exact Z, exact coarse bin sel0; the bracket is VERIFIED and the pass redone over all bins if the
+//       estimate missed (shared-memory atomics cost ~1-2 cycles per element, hence the bracket)
+//   P2  elements of the bracket: bins below sel0 are kept (segment sums), bin sel0 goes into a 2048-bin fine histogram and
+//       a small candidate list -> fine bin sel1.  The threshold is thereby resolved to t_cut / 2^22 (~5e-6 in logit
+//       units); values closer than that are ties and are kept together.
+//   P3  inverse-CDF walk in vocabulary order: segment sums pick the segment, its warp re-reads ~V/(32R) elements.
+// Every element is classified by ONE fixed float expression (u, and (u - sel0) * NB for the fine bin) in all passes.
+// -------------------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+struct TopPShared {
+  float h_mass[2048];
+  int h_cnt[2048];
+  float m_sum[2048];      // merged (cluster-wide) histogram
+  int c_sum[2048];
+  float seg_kept[32];     // kept mass of each warp's segment
+  int seg_cnt[32];
+  float cta_val[4];       // per-CTA scalars published to the cluster: [0] max, [1] below, [2] inside+above (mass), [3] spare
+  int cta_cnt[2];         // [0] below count
+  float cand_w[1024];     // elements of coarse bin sel0: weight, fine bin, owning warp
+  short cand_fine[1024];
+  short cand_warp[1024];
+  int n_cand;
+  BlockRed red;
+  int s_bin;
+  float s_before_mass, s_bin_mass, s_tot_mass;
+  int s_before_cnt, s_bin_cnt;
+};
+
+// visits the float4 groups of [lo, hi) (lo multiple of 4 elements) owned by one warp: f(value, index); 4 loads in flight
+template <typename F>
+PG_DEVINL void for_each_in_segment(const float* __restrict__ row, int lo, int hi, bool vec, int lane, F f) {
+  if (vec) {
+    int i = lo + lane * 4;
+    for (; i + 3 * 128 + 3 < hi; i += 4 * 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(row + i + 128));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(row + i + 256));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(row + i + 384));
+      f(a.x, i); f(a.y, i + 1); f(a.z, i + 2); f(a.w, i + 3);
+      f(b.x, i + 128); f(b.y, i + 129); f(b.z, i + 130); f(b.w, i + 131);
+      f(c.x, i + 256); f(c.y, i + 257); f(c.z, i + 258); f(c.w, i + 259);
+      f(d.x, i + 384); f(d.y, i + 385); f(d.z, i + 386); f(d.w, i + 387);
+    }
+    for (; i + 3 < hi; i += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
+      f(a.x, i); f(a.y, i + 1); f(a.z, i + 2); f(a.w, i + 3);
+    }
+    for (int j = i; j < hi && j < i + 4; ++j) f(row[j], j);  // (hi is a multiple of 4 when vec: never taken)
+  } else {
+    for (int i = lo + lane; i < hi; i += 32) f(row[i], i);
+  }
+}
+
 __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ out,
                                                             int* __restrict__ kept_count, int V, float inv_temp, float top_p,
                                                             unsigned long long seed, const int* __restrict__ step_ptr) {
   constexpr int NB = 2048;
-  __shared__ float h_mass[NB];
-  __shared__ int h_cnt[NB];
-  __shared__ BlockRed red;
-  __shared__ float w_tot[32];
-  __shared__ int s_bin;
-  __shared__ float s_above_mass;
-  __shared__ int s_above_cnt;
-  __shared__ float s_bin_mass;
-  __shared__ float s_tot_mass;
-  __shared__ int s_bin_cnt;
-  __shared__ int s_target_warp;
-  __shared__ float s_target_off;
-
+  __shared__ TopPShared S;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int R = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int row_idx = blockIdx.x / R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* row = logits + blockIdx.x * ld;
+  const float* __restrict__ row = logits + row_idx * ld;
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
 
-  // pass 0: online softmax statistics
-  const float c = inv_temp * 1.4426950408889634f;  // exp((x - mx) * inv_temp) = exp2((x - mx) * c)
-  float m_loc = -INFINITY, z_loc = 0.f;
-  for_each_elem(row, V, [&](float v, int) {
-    if (v > m_loc) {
-      z_loc = z_loc * exp2f((m_loc - v) * c) + 1.f;
-      m_loc = v;
-    } else {
-      z_loc += exp2f((v - m_loc) * c);
-    }
-  });
-  const float mx = block_reduce_max(m_loc, red);
-  const float Z = block_reduce_sum(m_loc == -INFINITY ? 0.f : z_loc * exp2f((m_loc - mx) * c), red);
-  const float thresh = top_p * Z;
-
-  // elements with t >= t_cut cannot be kept: V * exp(-t_cut) <= (1 - top_p) * Z / 128
-  float t_cut = 100.f;
-  if (top_p < 1.f) t_cut = fminf(100.f, logf(static_cast<float>(V) * 128.f / ((1.f - top_p) * Z)));
-  t_cut = fmaxf(t_cut, 1e-3f);
-
-  // Every element gets a (coarse, fine) bin pair from FIXED float expressions, so the histogram passes and the final
-  // kept test classify it identically:  b0 = floor(t * NB / t_cut),  b1 = clamp(floor((t - lo1) * NB / bw0)).
-  const float inv_w0 = static_cast<float>(NB) / t_cut;
-  const float bw0 = t_cut / static_cast<float>(NB);
-  auto coarse_bin = [&](float x, float& t) -> int {  // -1: outside [0, t_cut) -> never kept
-    t = (mx - x) * inv_temp;
-    const float u = t * inv_w0;
-    if (!(t < t_cut) || !(u < static_cast<float>(NB))) return -1;
-    return min(NB - 1, static_cast<int>(u));
-  };
-  float lo1 = 0.f, inv_w1 = 0.f;
-  auto fine_bin = [&](float t) -> int {
-    const float u = (t - lo1) * inv_w1;
-    return u < 0.f ? 0 : min(NB - 1, static_cast<int>(u));
-  };
-  int sel0 = 0, sel1 = 0;
-  float above_mass = 0.f;  // mass of the bins before the selected one (all kept)
-  int above_cnt = 0;
+  const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int nseg = R * 32;
+  const int seg_len = ((V + nseg - 1) / nseg + 127) / 128 * 128;
+  const int seg = rank * 32 + warp;
+  const int seg_lo = min(V, seg * seg_len), seg_hi = min(V, seg_lo + seg_len);
   const bool want_cnt = kept_count != nullptr;
 
-  // Shared-memory atomics are the cost of a histogram pass (~1-2 cycles per element per SM), so the coarse level is
-  // bracketed first: a 1/16 subsample locates the threshold bin to within +-D bins; the full pass then only bins
-  // the elements inside the bracket (everything below it is summed in registers, everything above is ignored) and
-  // VERIFIES that the bracket really contains the threshold -- otherwise it is redone over the whole range.
-  auto scan_select = [&](float base_mass, int base_cnt, int& sel_out) {
-    // ascending-t scan: thread owns bins (2 tid, 2 tid + 1); "before" = kept mass of all smaller t
+  auto remote = [&](auto* ptr, int r) { return cluster.map_shared_rank(ptr, r); };
+  auto cluster_sum_f = [&](float v, int slot) -> float {  // block reduce, publish, sum over the cluster in rank order
+    const float t = block_reduce_sum(v, S.red);
+    if (tid == 0) S.cta_val[slot] = t;
+    cluster.sync();
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) acc += *remote(&S.cta_val[slot], r);
+    cluster.sync();
+    return acc;
+  };
+
+  // ---- P0: row max ----
+  float m_loc = -INFINITY;
+  for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float v, int) { m_loc = fmaxf(m_loc, v); });
+  {
+    const float t = block_reduce_max(m_loc, S.red);
+    if (tid == 0) S.cta_val[0] = t;
+    cluster.sync();
+    float acc = -INFINITY;
+    for (int r = 0; r < R; ++r) acc = fmaxf(acc, *remote(&S.cta_val[0], r));
+    cluster.sync();
+    m_loc = acc;
+  }
+  const float mx = m_loc;
+  const float c = inv_temp * 1.4426950408889634f;  // w = exp((x - mx) * inv_temp) = exp2(x * c - mx * c)
+  const float cm = mx * c;
+  // elements with t = (mx - x) * inv_temp >= t_cut cannot be kept: V * exp(-t_cut) <= (1 - top_p) / 128 <= (1 - top_p) Z / 128
+  float t_cut = 80.f;
+  if (top_p < 1.f) t_cut = fminf(80.f, logf(static_cast<float>(V) * 128.f / (1.f - top_p)));
+  t_cut = fmaxf(t_cut, 1e-3f);
+  const float k0 = inv_temp * static_cast<float>(NB) / t_cut;  // u = (mx - x) * k0  in [0, NB) <=> t in [0, t_cut)
+  const float c0 = mx * k0;
+  auto u_of = [&](float x) { return fmaf(-x, k0, c0); };
+  auto w_of = [&](float x) { return exp2f(fmaf(x, c, -cm)); };
+
+  auto clear_hist = [&]() {
+    for (int i = tid; i < NB; i += 1024) { S.h_mass[i] = 0.f; S.h_cnt[i] = 0; }
+    if (tid < 32) { S.seg_kept[tid] = 0.f; S.seg_cnt[tid] = 0; }
+    if (tid == 0) S.n_cand = 0;
+    __syncthreads();
+  };
+  // merged histogram of the cluster (fixed rank order => bitwise identical in every CTA)
+  auto merge_hist = [&]() {
+    cluster.sync();
+    for (int i = tid; i < NB; i += 1024) {
+      float m = 0.f;
+      int n = 0;
+      for (int r = 0; r < R; ++r) { m += remote(S.h_mass, r)[i]; n += remote(S.h_cnt, r)[i]; }
+      S.m_sum[i] = m;
+      S.c_sum[i] = n;
+    }
+    cluster.sync();
+  };
+  // ascending-t scan of the merged histogram: the LAST non-empty bin whose preceding mass is <= thresh
+  auto scan_select = [&](float base_mass, int base_cnt, float thresh) -> int {
     const int b0 = 2 * tid, b1 = 2 * tid + 1;
-    const float m0 = h_mass[b0], m1 = h_mass[b1];
-    const int c0 = h_cnt[b0], c1 = h_cnt[b1];
+    const float m0 = S.m_sum[b0], m1 = S.m_sum[b1];
+    const int n0 = S.c_sum[b0], n1 = S.c_sum[b1];
     const float ms = m0 + m1;
-    const int cs = c0 + c1;
+    const int cs = n0 + n1;
     float ims = ms;
     int ics = cs;
 #pragma unroll
@@ -206,208 +269,243 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
       if (lane >= o) { ims += tf; ics += ti; }
     }
     __syncthreads();
-    if (lane == 31) { red.f[warp] = ims; red.i[warp] = ics; }
-    if (tid == 0) s_bin = -1;
+    if (lane == 31) { S.red.f[warp] = ims; S.red.i[warp] = ics; }
+    if (tid == 0) S.s_bin = -1;
     __syncthreads();
     float offm = base_mass;
     int offc = base_cnt;
-    for (int w = 0; w < warp; ++w) { offm += red.f[w]; offc += red.i[w]; }
+    for (int w = 0; w < warp; ++w) { offm += S.red.f[w]; offc += S.red.i[w]; }
     const float before0 = offm + ims - ms, before1 = before0 + m0;
-    const int cbefore0 = offc + ics - cs, cbefore1 = cbefore0 + c0;
-    // the LAST non-empty bin (largest t) whose preceding mass is still <= thresh holds the threshold
-    if (m1 > 0.f && before1 <= thresh) atomicMax(&s_bin, b1);
-    else if (m0 > 0.f && before0 <= thresh) atomicMax(&s_bin, b0);
+    const int cb0 = offc + ics - cs, cb1 = cb0 + n0;
+    if (m1 > 0.f && before1 <= thresh) atomicMax(&S.s_bin, b1);
+    else if (m0 > 0.f && before0 <= thresh) atomicMax(&S.s_bin, b0);
     __syncthreads();
-    const int sel = s_bin;
-    if (b0 == sel) { s_above_mass = before0; s_above_cnt = cbefore0; s_bin_mass = m0; s_bin_cnt = c0; }
-    if (b1 == sel) { s_above_mass = before1; s_above_cnt = cbefore1; s_bin_mass = m1; s_bin_cnt = c1; }
-    if (tid == 1023) { s_tot_mass = before1 + m1; }  // mass of everything binned (+ base)
+    const int sel = S.s_bin;
+    if (b0 == sel) { S.s_before_mass = before0; S.s_before_cnt = cb0; S.s_bin_mass = m0; S.s_bin_cnt = n0; }
+    if (b1 == sel) { S.s_before_mass = before1; S.s_before_cnt = cb1; S.s_bin_mass = m1; S.s_bin_cnt = n1; }
+    if (tid == 1023) S.s_tot_mass = before1 + m1;
     __syncthreads();
-    sel_out = sel;
-  };
-  auto clear_hist = [&]() {
-    for (int i = tid; i < NB; i += 1024) { h_mass[i] = 0.f; h_cnt[i] = 0; }
-    __syncthreads();
+    return sel;
   };
 
-  // ---- subsample (every 16th group of 4 elements) -> estimated threshold bin ----
+  // ---- PS: subsample -> bracket ----
   int bl = 0, bh = NB - 1;
   if (V >= 16384) {
     clear_hist();
-    for (int i = tid * 64; i < V; i += 1024 * 64) {
+    float zs = 0.f;
+    for (int i = seg_lo + lane * 64; i < seg_hi; i += 32 * 64) {  // 4 consecutive elements out of every 64
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (i + j < V) {
-          float t;
+        if (i + j < seg_hi) {
           const float x = row[i + j];
-          const int b0 = coarse_bin(x, t);
-          if (b0 >= 0) atomicAdd(&h_mass[b0], 16.f * exp2f((x - mx) * c));
+          const float u = u_of(x), w = 16.f * w_of(x);
+          zs += w;
+          if (u < static_cast<float>(NB)) atomicAdd(&S.h_mass[static_cast<int>(u)], w);
         }
       }
     }
-    __syncthreads();
-    int est;
-    scan_select(0.f, 0, est);
+    const float z_est = cluster_sum_f(zs, 3);
+    merge_hist();
+    const int est = scan_select(0.f, 0, top_p * z_est);
     if (est >= 0) {
-      const int D = max(8, static_cast<int>(0.25f * inv_w0) + 1);
+      const int D = max(8, static_cast<int>(0.25f * static_cast<float>(NB) / t_cut) + 1);
       bl = max(0, est - D);
       bh = min(NB - 1, est + D);
     }
   }
-  // ---- full coarse pass over the bracket (retry over the whole range if the bracket missed) ----
+
+  // ---- P1: exact Z, exact coarse bin (bracket verified, else redone over every bin) ----
+  int sel0 = 0;
+  float Z = 0.f, thresh = 0.f, base_mass = 0.f;
+  int base_cnt = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     clear_hist();
-    float m_below = 0.f;
-    int c_below = 0;
-    for_each_elem(row, V, [&](float x, int) {
-      float t;
-      const int b0 = coarse_bin(x, t);
-      if (b0 < 0 || b0 > bh) return;
-      const float w = exp2f((x - mx) * c);
-      if (b0 < bl) {
+    const float blf = static_cast<float>(bl), bhf = static_cast<float>(bh + 1);
+    float m_below = 0.f, m_rest = 0.f;
+    int n_below = 0;
+    for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int) {
+      const float u = u_of(x), w = w_of(x);
+      if (u < blf) {
         m_below += w;
-        ++c_below;
+        ++n_below;
       } else {
-        atomicAdd(&h_mass[b0], w);
-        if (want_cnt) atomicAdd(&h_cnt[b0], 1);
+        m_rest += w;
+        if (u < bhf) {
+          const int bin = static_cast<int>(u);
+          atomicAdd(&S.h_mass[bin], w);
+          if (want_cnt) atomicAdd(&S.h_cnt[bin], 1);
+        }
       }
     });
-    const float base_m = block_reduce_sum(m_below, red);
-    const int base_c = static_cast<int>(block_reduce_sum(static_cast<float>(c_below), red) + 0.5f);
-    __syncthreads();
-    scan_select(base_m, base_c, sel0);
-    const bool ok = (sel0 >= 0) && (bh == NB - 1 || s_tot_mass > thresh) && (bl == 0 || base_m <= thresh);
+    // per-warp kept mass so far (everything below the bracket is kept if the bracket verifies)
+    float wm = m_below;
+    int wn = n_below;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wm += __shfl_xor_sync(0xffffffffu, wm, o);
+      wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    }
+    if (lane == 0) { S.seg_kept[warp] = wm; S.seg_cnt[warp] = wn; }
+    base_mass = cluster_sum_f(m_below, 1);
+    const float rest = cluster_sum_f(m_rest, 2);
+    base_cnt = static_cast<int>(cluster_sum_f(static_cast<float>(n_below), 3) + 0.5f);
+    Z = base_mass + rest;
+    thresh = top_p * Z;
+    merge_hist();
+    sel0 = scan_select(base_mass, base_cnt, thresh);
+    const bool ok = (sel0 >= 0) && (bh == NB - 1 || S.s_tot_mass > thresh) && (bl == 0 || base_mass <= thresh);
     __syncthreads();
     if (ok) break;
     bl = 0;
     bh = NB - 1;
-    sel0 = 0;
   }
-  if (sel0 < 0) sel0 = 0;
-  above_mass = s_above_mass;
-  above_cnt = s_above_cnt;
-  lo1 = static_cast<float>(sel0) * bw0;
-  inv_w1 = static_cast<float>(NB) / bw0;
+  if (sel0 < 0) sel0 = 0;  // unreachable: the row maximum sits in bin 0 with nothing before it
+  const float sel0f = static_cast<float>(sel0);
+  float above_mass = S.s_before_mass;  // kept mass of every bin before sel0
+  int above_cnt = S.s_before_cnt;
   __syncthreads();
-  // ---- fine level inside the selected coarse bin ----
-  clear_hist();
-  for_each_elem(row, V, [&](float x, int) {
-    float t;
-    if (coarse_bin(x, t) != sel0) return;
-    const int bin = fine_bin(t);
-    atomicAdd(&h_mass[bin], exp2f((x - mx) * c));
-    if (want_cnt) atomicAdd(&h_cnt[bin], 1);
-  });
-  __syncthreads();
-  scan_select(above_mass, above_cnt, sel1);
+
+  // ---- P2: bins [bl, sel0) of the bracket are kept; bin sel0 -> fine histogram + candidate list ----
+  {
+    const float blf = static_cast<float>(bl);
+    for (int i = tid; i < NB; i += 1024) { S.h_mass[i] = 0.f; S.h_cnt[i] = 0; }
+    __syncthreads();
+    float m_in = 0.f;
+    int n_in = 0;
+    for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int) {
+      const float u = u_of(x);
+      if (u < blf || !(u < sel0f + 1.f)) return;
+      const float w = w_of(x);
+      if (u < sel0f) {
+        m_in += w;
+        ++n_in;
+      } else {
+        const float u1 = (u - sel0f) * static_cast<float>(NB);
+        const int fine = min(NB - 1, static_cast<int>(u1));
+        atomicAdd(&S.h_mass[fine], w);
+        if (want_cnt) atomicAdd(&S.h_cnt[fine], 1);
+        const int slot = atomicAdd(&S.n_cand, 1);
+        if (slot < 1024) { S.cand_w[slot] = w; S.cand_fine[slot] = static_cast<short>(fine); S.cand_warp[slot] = static_cast<short>(warp); }
+      }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m_in += __shfl_xor_sync(0xffffffffu, m_in, o);
+      n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+    }
+    if (lane == 0) { S.seg_kept[warp] += m_in; S.seg_cnt[warp] += n_in; }
+  }
+  merge_hist();
+  int sel1 = scan_select(above_mass, above_cnt, thresh);
   if (sel1 < 0) sel1 = 0;
-  above_mass = s_above_mass;
-  above_cnt = s_above_cnt;
-  // kept set: coarse bin < sel0, or coarse bin == sel0 and fine bin <= sel1 (the selected finest bin is kept whole)
-  const float kept_mass = above_mass + s_bin_mass;
-  if (tid == 0 && kept_count) kept_count[blockIdx.x] = above_cnt + s_bin_cnt;
-  auto is_kept = [&](float x) -> bool {
-    float t;
-    const int b0 = coarse_bin(x, t);
-    if (b0 < 0 || b0 > sel0) return false;
-    if (b0 < sel0) return true;
-    return fine_bin(t) <= sel1;
+  const int kept_total_cnt = S.s_before_cnt + S.s_bin_cnt;
+  __syncthreads();
+  auto is_kept = [&](float x, float& w) -> bool {
+    const float u = u_of(x);
+    if (!(u < sel0f + 1.f)) return false;
+    w = w_of(x);
+    if (u < sel0f) return true;
+    return min(NB - 1, static_cast<int>((u - sel0f) * static_cast<float>(NB))) <= sel1;
   };
+  // candidates of bin sel0 that made it (fine bin <= sel1) join their segment's kept mass
+  if (S.n_cand <= 1024) {
+    for (int i = tid; i < S.n_cand; i += 1024)
+      if (S.cand_fine[i] <= sel1) atomicAdd(&S.seg_kept[S.cand_warp[i]], S.cand_w[i]);
+  } else {  // pathological (thousands of near-identical logits at the threshold): recount bin sel0 from the row
+    float m_c = 0.f;
+    for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int) {
+      const float u = u_of(x);
+      float w;
+      if (!(u < sel0f) && is_kept(x, w)) m_c += w;
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m_c += __shfl_xor_sync(0xffffffffu, m_c, o);
+    if (lane == 0) S.seg_kept[warp] += m_c;
+  }
+  if (tid == 0 && rank == 0 && want_cnt) kept_count[row_idx] = kept_total_cnt;
 
-  // draw u in (0,1) and walk the kept set in vocabulary order
+  // ---- P3: pick the segment, walk it ----
+  cluster.sync();  // seg_kept of every CTA is final
   const int step = step_ptr ? *step_ptr : 0;
-  const uint64_t rnd = splitmix64(seed ^ splitmix64((static_cast<uint64_t>(step) << 32) | blockIdx.x));
+  const uint64_t rnd = splitmix64(seed ^ splitmix64((static_cast<uint64_t>(step) << 32) | static_cast<uint32_t>(row_idx)));
   const float u01 = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
-  const float target = u01 * kept_mass;
-
-  // each warp owns a contiguous range (multiple of 128 elements: one float4 per lane per iteration)
-  const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-  const int per_warp = ((V + 31) / 32 + 127) / 128 * 128;
-  const int lo_i = warp * per_warp, hi_i = min(V, lo_i + per_warp);
-  auto load4 = [&](int i, float (&x)[4]) {  // elements i..i+3 (out of range -> -inf: never kept)
-    if (vec && i + 3 < hi_i) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
-      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = (i + j < hi_i) ? row[i + j] : -INFINITY;
-    }
-  };
-  float wsum = 0.f;
-  for (int base = lo_i; base < hi_i; base += 512) {  // 4 float4 loads in flight per lane
-    float x[4][4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) load4(base + q * 128 + lane * 4, x[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (is_kept(x[q][j])) wsum += exp2f((x[q][j] - mx) * c);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-  if (lane == 0) w_tot[warp] = wsum;
-  __syncthreads();
-  if (tid == 0) {
-    float acc = 0.f;
-    int tw = -1;
-    float off = 0.f;
-    int last_nonempty = 0;
-    float last_off = 0.f;
-    for (int w = 0; w < 32; ++w) {
-      if (w_tot[w] > 0.f) { last_nonempty = w; last_off = acc; }
-      if (tw < 0 && w_tot[w] > 0.f && target < acc + w_tot[w]) { tw = w; off = acc; }
-      acc += w_tot[w];
-    }
-    if (tw < 0) { tw = last_nonempty; off = last_off; }  // rounding: target fell past the end
-    s_target_warp = tw;
-    s_target_off = off;
-  }
-  __syncthreads();
-  if (warp == s_target_warp) {
-    float acc = s_target_off;
-    int found = -1, last_kept = -1;
-    for (int base = lo_i; base < hi_i && found < 0; base += 128) {
-      const int i0 = base + lane * 4;
-      float x[4], w[4];
-      load4(i0, x);
-      float lsum = 0.f;
-      int lk = -1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool kept = is_kept(x[j]);
-        w[j] = kept ? exp2f((x[j] - mx) * c) : -1.f;  // -1 marks "not kept" (a kept weight may underflow to 0)
-        if (kept) { lk = i0 + j; lsum += w[j]; }
+  {
+    // gather the (<= 128) segment sums into local shared memory, one thread scans them
+    if (tid < nseg) S.m_sum[tid] = remote(S.seg_kept, tid >> 5)[tid & 31];
+    __syncthreads();
+    if (tid == 0) {
+      float total = 0.f;
+      for (int sg = 0; sg < nseg; ++sg) total += S.m_sum[sg];
+      const float target = u01 * total;
+      int tseg = -1, last_nonempty = -1;
+      float toff = 0.f, last_off = 0.f, acc = 0.f;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const float v = S.m_sum[sg];
+        if (v > 0.f) { last_nonempty = sg; last_off = acc; }
+        if (tseg < 0 && v > 0.f && target < acc + v) { tseg = sg; toff = acc; }
+        acc += v;
       }
-      float inc = lsum;
+      if (tseg < 0) { tseg = last_nonempty; toff = last_off; }  // rounding: target fell past the end
+      S.s_bin = tseg;
+      S.s_before_mass = toff;
+      S.s_tot_mass = target;
+    }
+    __syncthreads();
+    const int tseg = S.s_bin;
+    const float toff = S.s_before_mass, target = S.s_tot_mass;
+    if (tseg == seg) {  // this warp owns the target segment
+      float acc2 = toff;
+      int found = -1, last_kept = -1;
+      for (int base = seg_lo; base < seg_hi && found < 0; base += 128) {
+        const int i0 = base + lane * 4;
+        float x[4], w[4];
+        if (vec && i0 + 3 < seg_hi) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(row + i0));
+          x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+        } else {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const bool hit = (lk >= 0) && (target < acc + inc);
-      const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-      const uint32_t keeps = __ballot_sync(0xffffffffu, lk >= 0);
-      if (keeps) last_kept = __shfl_sync(0xffffffffu, lk, 31 - __clz(keeps));
-      if (hits) {
-        const int hl = __ffs(hits) - 1;
-        float a = acc + inc - lsum;  // mass before this lane's elements
-        int f = -1;
+          for (int j = 0; j < 4; ++j) x[j] = (i0 + j < seg_hi) ? row[i0 + j] : -INFINITY;
+        }
+        float lsum = 0.f;
+        int lk = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (f < 0 && w[j] >= 0.f) {
-            a += w[j];
-            if (target < a) f = i0 + j;
-          }
+          float wj = 0.f;
+          const bool kept = (x[j] != -INFINITY) && is_kept(x[j], wj);
+          w[j] = kept ? wj : -1.f;  // -1 marks "not kept"
+          if (kept) { lk = i0 + j; lsum += wj; }
         }
-        if (f < 0) f = lk;  // rounding inside the lane
-        found = __shfl_sync(0xffffffffu, f, hl);
+        float inc = lsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const bool hit = (lk >= 0) && (target < acc2 + inc);
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        const uint32_t keeps = __ballot_sync(0xffffffffu, lk >= 0);
+        if (keeps) last_kept = __shfl_sync(0xffffffffu, lk, 31 - __clz(keeps));
+        if (hits) {
+          const int hl = __ffs(hits) - 1;
+          float a = acc2 + inc - lsum;  // mass before this lane's elements
+          int f = -1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (f < 0 && w[j] >= 0.f) {
+              a += w[j];
+              if (target < a) f = i0 + j;
+            }
+          }
+          if (f < 0) f = lk;  // rounding inside the lane
+          found = __shfl_sync(0xffffffffu, f, hl);
+        }
+        acc2 += __shfl_sync(0xffffffffu, inc, 31);
       }
-      acc += __shfl_sync(0xffffffffu, inc, 31);
+      if (found < 0) found = last_kept;
+      if (lane == 0) out[row_idx] = found;
     }
-    if (found < 0) found = last_kept;
-    if (lane == 0) out[blockIdx.x] = found;
   }
+  cluster.sync();  // keep shared memory alive until every CTA has read the segment sums
 }
 
 }  // namespace pg
@@ -424,6 +522,26 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
                                float inv_temperature, float top_p, unsigned long long seed, const int* step_ptr,
                                void* stream) {
   if (B <= 0 || V <= 0 || !(inv_temperature > 0.f) || !(top_p >= 0.f)) return PG_ERR_ARG;
-  return launch_kernel(sample_top_p_kernel, dim3(B), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), logits, ld, out,
-                       kept_count, V, inv_temperature, top_p, seed, step_ptr) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  // cluster of R CTAs per row: enough CTAs to cover the GPU when the batch alone cannot
+  int R = 1;
+  if (V >= 65536) R = 2;  // (64 regs x 1024 threads = one CTA per SM: 2 x 64 rows covers 128 of the 148 SMs)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * R);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pg_pdl_enabled() ? 2 : 1;
+  pg_count_launch(1);
+  return cudaLaunchKernelEx(&cfg, sample_top_p_kernel, logits, ld, out, kept_count, V, inv_temperature, top_p, seed, step_ptr) ==
+                 cudaSuccess
+             ? PG_OK
+             : PG_ERR_CUDA;
 }

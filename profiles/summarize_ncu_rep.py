@@ -1,0 +1,26 @@
+"""Extracts the roofline-relevant metrics of every profiled launch in an .ncu-rep (ncu --set full) as CSV."""
+import csv
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+        "smsp__cycles_active.avg"]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
+    w = csv.writer(sys.stdout)
+    w.writerow([f"{name} [{units[i]}]" if units[i] else name for name, i in idx])
+    for r in rows[2:]:
+        w.writerow([r[i] for _, i in idx])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
