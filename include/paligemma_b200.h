@@ -112,15 +112,12 @@ long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_sp
 /*
  * Decode-step attention in ONE launch (modeling_gemma.py:285-339 at q_len == 1 + KVCache.update :18-57): rotates q and
  * the new k (fp32 qkv [B, (Hq+2Hkv)*dh] straight from the split-K QKV GEMM), appends k/v to the paged cache at slot
- * kv_len[b]-1, attends over kv_len[b] keys with one CTA per 64-key page (grid = max_tiles x B*Hkv, excess CTAs exit),
- * and the last CTA to arrive for a sequence merges the per-page partials (arrival counters self-reset).
- * counters: int32 [B*Hkv], zero before the first launch.  max_tiles >= ceil(max kv_len / 64).
+ * kv_len[b]-1 and attends over kv_len[b] keys.  One thread-block cluster per (sequence, kv head): each rank streams a
+ * contiguous range of 64-key pages through shared memory, the ranks merge through distributed shared memory.
  */
 int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
-                              void* v_pages, const int* page_table, float* workspace, int* counters, void* out, int B,
-                              int Hq, int Hkv, int dh, int page_size, int max_pages, int max_tiles, float scale,
-                              void* stream);
-long long pg_attention_decode_fused_workspace_floats(int B, int Hq, int dh, int max_tiles);
+                              void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh,
+                              int page_size, int max_pages, float scale, void* stream);
 
 /* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
  * views, modeling_gemma.py:8-64). */

@@ -35,8 +35,7 @@ SIGNATURES = {
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
     "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],
-    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
-    "pg_attention_decode_fused_workspace_floats": [i32, i32, i32, i32],
+    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
@@ -44,7 +43,7 @@ SIGNATURES = {
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
 }
-_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_attention_decode_fused_workspace_floats": i64, "pg_launch_count": i64}
+_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_launch_count": i64}
 
 _lib = None
 

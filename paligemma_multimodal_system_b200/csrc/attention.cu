@@ -9,6 +9,8 @@
 //
 // Round-1 implementation: mma.sync m16n8k16 tensor-core tiles (attention is 1.4 % of the 224-px prefill FLOPs); the
 // tcgen05/TMEM version for the 448/896-px configs is the next step for this file.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "paligemma_b200.h"
 
@@ -398,7 +400,10 @@ __global__ void attn_decode_combine_kernel(const float* ws, bf16* out, int B, in
 
 
 // ------------------------------------------------------------------------------------------------------------
-// fused decode step attention: RoPE(q, k_new) + KV append + split-KV attention + last-CTA combine in ONE launch
+// fused decode-step attention: RoPE(q, k_new) + KV append + attention over the paged cache in ONE launch.
+// One thread-block CLUSTER per (sequence, kv head): rank r streams a contiguous range of 64-key pages through a
+// 3-deep cp.async ring in shared memory (4 warps x 16 keys per page, mma.sync tiles, online softmax), then the ranks
+// merge their partial (max, sum, O) through distributed shared memory -- no global workspace, atomics or fences.
 // ------------------------------------------------------------------------------------------------------------
 struct AttnDecodeFusedParams {
   const float* qkv;       // [B, (Hq+2Hkv)*dh] fp32 raw projections of the new token (pre-RoPE)
@@ -408,69 +413,84 @@ struct AttnDecodeFusedParams {
   bf16* k_pages;          // [pages, 64, Hkv*dh]
   bf16* v_pages;
   const int* page_table;  // [B, max_pages]
-  float* ws;              // partials: o [B*Hq][max_tiles][dh], ml [B*Hq][max_tiles][2]
-  int* counters;          // [B*Hkv] arrival counters (zero on entry, reset by the combining CTA)
   bf16* out;              // [B, Hq*dh]
-  int B, Hq, Hkv, max_pages, max_tiles, num_splits;
+  int B, Hq, Hkv, max_pages;
   float sl2;
 };
 
-// grid (num_splits, B*Hkv); one CTA = a contiguous range of 64-key pages of one (sequence, kv head); 4 warps x 16 keys
-// per page, K/V pages double buffered through shared memory with cp.async, online softmax across pages.
-// num_splits == 1 (enough sequences to fill the GPU): the CTA writes the output directly -- no workspace, no fences.
-// num_splits  > 1 (few sequences): per-split partials + the last CTA to arrive merges them.
 template <int DH>
-__global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecodeFusedParams p) {
+__global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecodeFusedParams p) {
   using C = AttnCfg<DH>;
+  namespace cg = cooperative_groups;
   constexpr int BLOCK_N = 64;
   constexpr int HALF = DH / 2;
+  constexpr int NBUF = 3;
+  constexpr int NT = 256;                          // 8 warps: two groups of 4, each group works on its own page
+  constexpr int BUF_ELEMS = 2 * BLOCK_N * C::LDS;  // one ring slot: K page then V page
+  constexpr int RLD = DH + 2;                      // partial row: DH accumulators, m (log2 domain), l
+  constexpr uint32_t ROW_BYTES = DH * 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);  // [16][LDS]
-  bf16* Ks = Qs + 16 * C::LDS;                   // [2][64][LDS]
-  bf16* Vs = Ks + 2 * BLOCK_N * C::LDS;          // [2][64][LDS]
-  float* red = reinterpret_cast<float*>(Ks);     // reused after the main loop: [4 warps][16][DH+2]
-  __shared__ int s_last;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);    // [16][LDS]
+  bf16* ring = Qs + 16 * C::LDS;                   // [NBUF][K 64 x LDS | V 64 x LDS]
+  float* red = reinterpret_cast<float*>(ring);                      // after the loop: [8 warps][16][RLD]  (slots 0-1)
+  float* part = reinterpret_cast<float*>(ring + 2 * BUF_ELEMS);     // this CTA's merged partial [16][RLD] (slot 2)
   __shared__ bf16 new_k[DH], new_v[DH];
-  __shared__ float s_M[16], s_L[16];
+  __shared__ __align__(8) uint64_t bars[NBUF];
 
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, num_splits = gridDim.x;
-  const int b = blockIdx.y / p.Hkv, hk = blockIdx.y % p.Hkv;
+  const int wg = warp >> 2, wq = warp & 3;  // warp group (which page of a pair), warp within the group (which 16 keys)
+  const int seq = blockIdx.x / CS;
+  const int b = seq / p.Hkv, hk = seq % p.Hkv;
   const int group = p.Hq / p.Hkv;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NBUF; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_fence_init();
+  }
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
+  __syncthreads();
   const int len = p.kv_len[b];
   const int n_tiles = (len + BLOCK_N - 1) / BLOCK_N;
-  const int tps = (n_tiles + num_splits - 1) / num_splits;
-  const int n_active = (n_tiles + tps - 1) / tps;  // splits that own at least one page
-  const int t_begin = split * tps, t_end = min(n_tiles, t_begin + tps);
-  if (t_begin >= t_end) return;
+  const int tps = (n_tiles + CS - 1) / CS;
+  const int t_begin = min(n_tiles, rank * tps), t_end = min(n_tiles, t_begin + tps);
+  const int n_my = t_end - t_begin;
   const int new_slot = len - 1;
   const int new_tile = new_slot / BLOCK_N;
   const bool owns_new = (new_tile >= t_begin && new_tile < t_end);
   const long long kv_ts = static_cast<long long>(p.Hkv) * DH;
   const int* ptab = p.page_table + b * p.max_pages;
 
-  auto load_kv = [&](int tile, int buf) {
+  // One 512 B bulk copy (TMA engine) per cached K / V row, completion counted on the slot's mbarrier.  Rows that are
+  // not in the cache (beyond kv_len, or the new token's slot) are zero-filled with plain stores.
+  auto load_kv = [&](int tile, int slot) {
     const int page = ptab[tile];
-    const bf16* kb = p.k_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
-    const bf16* vb = p.v_pages + static_cast<long long>(page) * BLOCK_N * kv_ts + hk * DH;
     const int n0 = tile * BLOCK_N;
-    // cached rows via cp.async; the new token's row (not in the cache yet) is zero-filled here and patched below
-    load_tile<DH, 128>(Ks + buf * BLOCK_N * C::LDS, BLOCK_N,
-                       [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? kb + r * kv_ts : nullptr; });
-    load_tile<DH, 128>(Vs + buf * BLOCK_N * C::LDS, BLOCK_N,
-                       [&](int r) -> const bf16* { return ((n0 + r) < len && (n0 + r) != new_slot) ? vb + r * kv_ts : nullptr; });
+    const uint32_t bar = smem_u32(&bars[slot]);
+    int rows = min(BLOCK_N, len - n0);
+    if (tile == new_tile) rows -= 1;  // the new token's row is patched in from registers
+    if (threadIdx.x == 0) mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROW_BYTES * 2);
+    if (threadIdx.x < 2 * BLOCK_N) {
+      const int kv = threadIdx.x >> 6, r = threadIdx.x & 63;
+      bf16* dst = ring + slot * BUF_ELEMS + kv * BLOCK_N * C::LDS + r * C::LDS;
+      if ((n0 + r) < len && (n0 + r) != new_slot) {
+        const bf16* src = (kv ? p.v_pages : p.k_pages) + (static_cast<long long>(page) * BLOCK_N + r) * kv_ts + hk * DH;
+        bulk_copy_g2s(smem_u32(dst), src, ROW_BYTES, bar);
+      } else {
+        for (int c = 0; c < C::DHP / 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   };
-  load_kv(t_begin, 0);
-  cp_async_commit();
+  for (int i = 0; i < NBUF && i < n_my; ++i) load_kv(t_begin + i, i);  // everything this rank can hold is in flight now
 
   // RoPE (rotate-half, modeling_gemma.py:138-151) on the query heads of this group (+ the new key when owned).
   // All global loads of a thread are issued back to back (independent), then rotated: one L2 round trip, not 20.
   const int W = (p.Hq + 2 * p.Hkv) * DH;
   const float* __restrict__ row = p.qkv + static_cast<long long>(b) * W;
   const float posf = static_cast<float>(p.pos[b]);
-  for (int i = threadIdx.x; i < HALF; i += 128) {
+  for (int i = threadIdx.x; i < HALF; i += NT) {
     float x1[16], x2[16], kx1 = 0.f, kx2 = 0.f, vx1 = 0.f, vx2 = 0.f;
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
@@ -508,10 +528,23 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
     }
   }
   // zero the padding rows / pad columns of Q
-  for (int idx = threadIdx.x; idx < 16 * C::DHP; idx += 128) {
+  for (int idx = threadIdx.x; idx < 16 * C::DHP; idx += NT) {
     const int r = idx / C::DHP, cc = idx % C::DHP;
     if (r >= group || cc >= DH) Qs[r * C::LDS + cc] = __float2bfloat16(0.f);
   }
+  __syncthreads();  // Q, new_k / new_v staged
+  if (owns_new) {   // patch the new token's row into its ring slot (if that page is among the first NBUF)
+    const int i_new = new_tile - t_begin;
+    if (i_new < NBUF) {
+      bf16* Kb = ring + (i_new % NBUF) * BUF_ELEMS;
+      const int r = new_slot - new_tile * BLOCK_N;
+      for (int k = threadIdx.x; k < DH; k += NT) {
+        Kb[r * C::LDS + k] = new_k[k];
+        Kb[(BLOCK_N + r) * C::LDS + k] = new_v[k];
+      }
+    }
+  }
+  __syncthreads();
 
   float o[C::DHP / 8][4];
 #pragma unroll
@@ -520,85 +553,112 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
   float l_run[2] = {0.f, 0.f};
   const uint32_t q_addr = smem_u32(Qs + (lane & 15) * C::LDS + (lane >> 4) * 8);
 
-  for (int t = t_begin; t < t_end; ++t) {
-    const int buf = (t - t_begin) & 1;
-    if (t + 1 < t_end) {
-      load_kv(t + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+  // pages are consumed in pairs: warp group 0 takes page 2j, group 1 takes page 2j+1 (both groups stay in lock step
+  // through the CTA barriers so that ring slots can be recycled)
+  for (int i0 = 0; i0 < n_my; i0 += 2) {
+    const int i = i0 + wg;
+    const bool active = i < n_my;
+    if (active) {
+      const int t = t_begin + i;
+      const int slot = i % NBUF;
+      mbar_wait(smem_u32(&bars[slot]), (i / NBUF) & 1);
+      const bf16* Kt = ring + slot * BUF_ELEMS + wq * 16 * C::LDS;
+      const bf16* Vt = Kt + BLOCK_N * C::LDS;
+      float s[2][4], s2[2][4];  // two independent accumulator sets (even / odd k-steps): 4 MMA chains in flight
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[a][e] = s2[a][e] = 0.f;
+      const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int ks = 0; ks < C::DHP / 16; ks += 2) {
+        uint32_t a[4], b0, b1, b2, b3;
+        ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
+        ldmatrix_x4(k_addr + ks * 32, b0, b1, b2, b3);
+        mma_bf16_16816(s[0], a, b0, b1);
+        mma_bf16_16816(s[1], a, b2, b3);
+        if (ks + 1 < C::DHP / 16) {
+          uint32_t c4[4], d0, d1, d2, d3;
+          ldmatrix_x4(q_addr + (ks + 1) * 32, c4[0], c4[1], c4[2], c4[3]);
+          ldmatrix_x4(k_addr + (ks + 1) * 32, d0, d1, d2, d3);
+          mma_bf16_16816(s2[0], c4, d0, d1);
+          mma_bf16_16816(s2[1], c4, d2, d3);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[a][e] += s2[a][e];
+      const int kbase = t * BLOCK_N + wq * 16;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int key = kbase + nt * 8 + (lane & 3) * 2;
+        if (key >= len) s[nt][0] = s[nt][2] = -INFINITY;
+        if (key + 1 >= len) s[nt][1] = s[nt][3] = -INFINITY;
+      }
+      float alpha[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float mx = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[r], mx);
+        const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+        alpha[r] = exp2f((m_run[r] - m_safe) * p.sl2);
+        const float msc = m_safe * p.sl2;
+        m_run[r] = m_new;
+        s[0][2 * r] = exp2f(s[0][2 * r] * p.sl2 - msc);
+        s[0][2 * r + 1] = exp2f(s[0][2 * r + 1] * p.sl2 - msc);
+        s[1][2 * r] = exp2f(s[1][2 * r] * p.sl2 - msc);
+        s[1][2 * r + 1] = exp2f(s[1][2 * r + 1] * p.sl2 - msc);
+        l_run[r] = l_run[r] * alpha[r] + s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
+      }
+      if (i0 > 0) {  // (first pair: the accumulators are still zero)
+#pragma unroll
+        for (int k = 0; k < C::DHP / 8; ++k) {
+          o[k][0] *= alpha[0]; o[k][1] *= alpha[0];
+          o[k][2] *= alpha[1]; o[k][3] *= alpha[1];
+        }
+      }
+      uint32_t a[4];
+      a[0] = pack_bf16(s[0][0], s[0][1]);
+      a[1] = pack_bf16(s[0][2], s[0][3]);
+      a[2] = pack_bf16(s[1][0], s[1][1]);
+      a[3] = pack_bf16(s[1][2], s[1][3]);
+      const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
+#pragma unroll
+      for (int dp = 0; dp < C::DHP / 16; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(v_addr + dp * 32, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], a, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+      }
     }
-    __syncthreads();
-    if (t == new_tile) {  // patch the new token's row into the staged page
-      const int r = new_slot - new_tile * BLOCK_N;
-      for (int i = threadIdx.x; i < DH; i += 128) {
-        Ks[(buf * BLOCK_N + r) * C::LDS + i] = new_k[i];
-        Vs[(buf * BLOCK_N + r) * C::LDS + i] = new_v[i];
+    __syncthreads();  // both pages of the pair are consumed
+    // refill the two slots just freed (long contexts): pages i0 + NBUF, i0 + 1 + NBUF
+    if (i0 + NBUF < n_my) {
+      fence_proxy_async_smem();
+      for (int k = 0; k < 2; ++k) {
+        const int inext = i0 + k + NBUF;
+        if (i0 + k < n_my && inext < n_my) {
+          load_kv(t_begin + inext, inext % NBUF);
+          if (t_begin + inext == new_tile) {  // (only when the new token's page is not among the first NBUF)
+            __syncthreads();
+            bf16* Kb = ring + (inext % NBUF) * BUF_ELEMS;
+            const int r = new_slot - new_tile * BLOCK_N;
+            for (int q = threadIdx.x; q < DH; q += NT) {
+              Kb[r * C::LDS + q] = new_k[q];
+              Kb[(BLOCK_N + r) * C::LDS + q] = new_v[q];
+            }
+          }
+        }
       }
       __syncthreads();
     }
-    // this warp owns keys [16*warp, 16*warp+16) of the page
-    const bf16* Kt = Ks + (buf * BLOCK_N + warp * 16) * C::LDS;
-    const bf16* Vt = Vs + (buf * BLOCK_N + warp * 16) * C::LDS;
-    float s[2][4];
-    s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
-    const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
-#pragma unroll
-    for (int ks = 0; ks < C::DHP / 16; ++ks) {
-      uint32_t a[4], b0, b1, b2, b3;
-      ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
-      ldmatrix_x4(k_addr + ks * 32, b0, b1, b2, b3);
-      mma_bf16_16816(s[0], a, b0, b1);
-      mma_bf16_16816(s[1], a, b2, b3);
-    }
-    const int kbase = t * BLOCK_N + warp * 16;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int key = kbase + nt * 8 + (lane & 3) * 2;
-      if (key >= len) s[nt][0] = s[nt][2] = -INFINITY;
-      if (key + 1 >= len) s[nt][1] = s[nt][3] = -INFINITY;
-    }
-    float alpha[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float mx = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m_run[r], mx);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      alpha[r] = exp2f((m_run[r] - m_safe) * p.sl2);
-      const float msc = m_safe * p.sl2;
-      m_run[r] = m_new;
-      s[0][2 * r] = exp2f(s[0][2 * r] * p.sl2 - msc);
-      s[0][2 * r + 1] = exp2f(s[0][2 * r + 1] * p.sl2 - msc);
-      s[1][2 * r] = exp2f(s[1][2 * r] * p.sl2 - msc);
-      s[1][2 * r + 1] = exp2f(s[1][2 * r + 1] * p.sl2 - msc);
-      l_run[r] = l_run[r] * alpha[r] + s[0][2 * r] + s[0][2 * r + 1] + s[1][2 * r] + s[1][2 * r + 1];
-    }
-#pragma unroll
-    for (int i = 0; i < C::DHP / 8; ++i) {
-      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
-      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
-    }
-    uint32_t a[4];
-    a[0] = pack_bf16(s[0][0], s[0][1]);
-    a[1] = pack_bf16(s[0][2], s[0][3]);
-    a[2] = pack_bf16(s[1][0], s[1][1]);
-    a[3] = pack_bf16(s[1][2], s[1][3]);
-    const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
-#pragma unroll
-    for (int dp = 0; dp < C::DHP / 16; ++dp) {
-      uint32_t b0, b1, b2, b3;
-      ldmatrix_x4_trans(v_addr + dp * 32, b0, b1, b2, b3);
-      mma_bf16_16816(o[2 * dp], a, b0, b1);
-      mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
-    }
-    __syncthreads();  // the buffer is overwritten by the load issued in the next iteration
   }
+  __syncthreads();
 
-  // ---- merge the 4 warps (disjoint key subsets) through shared memory ----
-  constexpr int RLD = DH + 2;  // [.., DH] = m (scaled, log2 domain), [.., DH+1] = l
+  // ---- merge the 8 warps (disjoint key subsets) through shared memory ----
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
@@ -608,99 +668,85 @@ __global__ void __launch_bounds__(128) attn_decode_fused_kernel(const AttnDecode
     const int r0 = lane >> 2;
     float* dst0 = red + (warp * 16 + r0) * RLD;
     float* dst1 = red + (warp * 16 + r0 + 8) * RLD;
+    const bool hi_rows = group > 8;  // rows 8..15 are padding unless the GQA group is larger than 8
 #pragma unroll
     for (int nt = 0; nt < C::DHP / 8; ++nt) {
       const int col = nt * 8 + (lane & 3) * 2;
       if (col < DH) {
         dst0[col] = o[nt][0]; dst0[col + 1] = o[nt][1];
-        dst1[col] = o[nt][2]; dst1[col + 1] = o[nt][3];
+        if (hi_rows) { dst1[col] = o[nt][2]; dst1[col + 1] = o[nt][3]; }
       }
     }
     if ((lane & 3) == 0) {
       dst0[DH] = m_run[0] * p.sl2; dst0[DH + 1] = l_run[0];
-      dst1[DH] = m_run[1] * p.sl2; dst1[DH + 1] = l_run[1];
+      if (hi_rows) { dst1[DH] = m_run[1] * p.sl2; dst1[DH + 1] = l_run[1]; }
     }
   }
   __syncthreads();
   const long long hq0 = static_cast<long long>(b) * p.Hq + hk * group;  // first query head of this group
-  float* __restrict__ ws_o = p.ws;
-  float* __restrict__ ws_ml = p.ws + static_cast<long long>(p.B) * p.Hq * p.max_tiles * DH;
-  for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
+  for (int idx = threadIdx.x; idx < group * DH; idx += NT) {
     const int r = idx / DH, col = idx % DH;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 16 + r) * RLD + DH]);
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, red[(w * 16 + r) * RLD + DH]);
     const float Ms = (M == -INFINITY) ? 0.f : M;
     float acc = 0.f, Lsum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < 8; ++w) {
       const float wgt = exp2f(red[(w * 16 + r) * RLD + DH] - Ms);
       acc += red[(w * 16 + r) * RLD + col] * wgt;
       Lsum += red[(w * 16 + r) * RLD + DH + 1] * wgt;
     }
-    if (num_splits == 1) {
+    if (CS == 1) {
       p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc / Lsum);
     } else {
-      const long long hrow = (hq0 + r) * p.max_tiles + split;
-      __stcg(ws_o + hrow * DH + col, acc);
-      if (col == 0) {
-        __stcg(ws_ml + hrow * 2, M);
-        __stcg(ws_ml + hrow * 2 + 1, Lsum);
-      }
+      part[r * RLD + col] = acc;
+      if (col == 0) { part[r * RLD + DH] = M; part[r * RLD + DH + 1] = Lsum; }
     }
   }
-  if (num_splits == 1) return;
+  if (CS == 1) return;
 
-  // ---- the last CTA of this (sequence, kv head) to arrive merges the split partials ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int old = atomicAdd(p.counters + blockIdx.y, 1);
-    s_last = (old == n_active - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < group) {
-    const int r = threadIdx.x;
-    const long long hbase = (hq0 + r) * p.max_tiles;
-    float M = -INFINITY;
-    for (int t = 0; t < n_active; ++t) M = fmaxf(M, __ldcg(ws_ml + (hbase + t) * 2));
-    float Lsum = 0.f;
-    for (int t = 0; t < n_active; ++t) Lsum += __ldcg(ws_ml + (hbase + t) * 2 + 1) * exp2f(__ldcg(ws_ml + (hbase + t) * 2) - M);
-    s_M[r] = M;
-    s_L[r] = Lsum;
-  }
-  __syncthreads();
-  float* wgt = red;  // [group][n_active]  (the staging area is free by now)
-  for (int idx = threadIdx.x; idx < group * n_active; idx += 128) {
-    const int r = idx / n_active, t = idx % n_active;
-    wgt[idx] = exp2f(__ldcg(ws_ml + ((hq0 + r) * p.max_tiles + t) * 2) - s_M[r]) / s_L[r];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < group * DH; idx += 128) {
-    const int r = idx / DH, col = idx % DH;
-    const long long hbase = (hq0 + r) * p.max_tiles;
-    float acc = 0.f;
-    for (int t0 = 0; t0 < n_active; t0 += 8) {  // 8 independent loads in flight
-      float v[8];
+  // ---- merge the ranks through distributed shared memory; rank q finalises columns [q*DH/CS, (q+1)*DH/CS) ----
+  cluster.sync();
+  {
+    const int cols_per = (DH + CS - 1) / CS;
+    const int c_lo = rank * cols_per, c_hi = min(DH, c_lo + cols_per);
+    const int ncol = max(0, c_hi - c_lo);
+    for (int idx = threadIdx.x; idx < group * ncol; idx += NT) {
+      const int r = idx / ncol, col = c_lo + idx % ncol;
+      float mv[8], lv[8], av[8];
 #pragma unroll
-      for (int tt = 0; tt < 8; ++tt) v[tt] = (t0 + tt < n_active) ? __ldcg(ws_o + (hbase + t0 + tt) * DH + col) : 0.f;
+      for (int q = 0; q < 8; ++q) {  // independent remote loads, issued back to back
+        if (q < CS) {
+          const float* rp = cluster.map_shared_rank(part, q);
+          mv[q] = rp[r * RLD + DH];
+          lv[q] = rp[r * RLD + DH + 1];
+          av[q] = rp[r * RLD + col];
+        }
+      }
+      float M = -INFINITY;
 #pragma unroll
-      for (int tt = 0; tt < 8; ++tt)
-        if (t0 + tt < n_active) acc += v[tt] * wgt[r * n_active + t0 + tt];
+      for (int q = 0; q < 8; ++q)
+        if (q < CS) M = fmaxf(M, mv[q]);
+      float acc = 0.f, Lsum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < CS) {
+          const float wgt = exp2f(mv[q] - M);  // empty ranks carry m = -inf, l = 0
+          acc += av[q] * wgt;
+          Lsum += lv[q] * wgt;
+        }
+      }
+      p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc / Lsum);
     }
-    p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc);
   }
-  if (threadIdx.x == 0) p.counters[blockIdx.y] = 0;  // ready for the next launch (stream ordered)
+  cluster.sync();  // shared memory must stay alive until every rank has read it
 }
 
 template <int DH>
-static int launch_decode_fused(const AttnDecodeFusedParams& p, cudaStream_t st) {
+static int launch_decode_fused(const AttnDecodeFusedParams& p, int cluster_size, cudaStream_t st) {
   using C = AttnCfg<DH>;
-  constexpr int smem_main = (16 + 4 * 64) * C::LDS * 2;
-  constexpr int smem_red = 16 * C::LDS * 2 + 4 * 16 * (DH + 2) * 4;
-  constexpr int smem = smem_main > smem_red ? smem_main : smem_red;
+  constexpr int smem = (16 + 3 * 2 * 64) * C::LDS * 2;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_decode_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -709,8 +755,22 @@ static int launch_decode_fused(const AttnDecodeFusedParams& p, cudaStream_t st) 
     }
     configured = true;
   }
-  dim3 grid(p.num_splits, p.B * p.Hkv);
-  return launch_kernel(attn_decode_fused_kernel<DH>, grid, dim3(128), smem, st, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.B * p.Hkv * cluster_size));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pg_pdl_enabled() ? 2 : 1;
+  pg_count_launch(1);
+  return cudaLaunchKernelEx(&cfg, attn_decode_fused_kernel<DH>, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 template <int DH, int NWARPS>
@@ -802,35 +862,25 @@ extern "C" int pg_attention_decode(const void* q, const void* k_pages, const voi
   }
 }
 
-extern "C" long long pg_attention_decode_fused_workspace_floats(int B, int Hq, int dh, int max_tiles) {
-  return static_cast<long long>(B) * Hq * max_tiles * (dh + 2);
-}
-
 extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq,
-                                         void* k_pages, void* v_pages, const int* page_table, float* workspace,
-                                         int* counters, void* out, int B, int Hq, int Hkv, int dh, int page_size,
-                                         int max_pages, int max_tiles, float scale, void* stream) {
-  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || max_tiles <= 0 ||
-      max_tiles > max_pages || B * Hkv > 65535)
-    return PG_ERR_ARG;
+                                         void* k_pages, void* v_pages, const int* page_table, void* out, int B, int Hq,
+                                         int Hkv, int dh, int page_size, int max_pages, float scale, void* stream) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || max_pages <= 0) return PG_ERR_ARG;
   AttnDecodeFusedParams p;
   p.qkv = qkv; p.pos = pos; p.kv_len = kv_len; p.inv_freq = inv_freq;
   p.k_pages = static_cast<bf16*>(k_pages); p.v_pages = static_cast<bf16*>(v_pages);
-  p.page_table = page_table; p.ws = workspace; p.counters = counters; p.out = static_cast<bf16*>(out);
-  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages; p.max_tiles = max_tiles;
-  // enough (sequence, kv head) pairs to occupy the GPU -> one CTA streams the whole sequence; otherwise split the KV
-  // length so that ~2 CTAs per SM are in flight (partials + last-arriver merge)
-  int splits = 1;
-  if (B * Hkv < 64) {
-    splits = (2 * 148 + B * Hkv - 1) / (B * Hkv);
-    if (splits > max_tiles) splits = max_tiles;
-  }
-  p.num_splits = splits;
+  p.page_table = page_table; p.out = static_cast<bf16*>(out);
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages;
   p.sl2 = scale * 1.4426950408889634f;
+  // cluster size: as many CTAs as fit in ONE wave (the 3-deep page ring allows one CTA per SM), at most one page per
+  // rank, at most 8 (portable cluster limit)
+  int cs = 148 / (B * Hkv);
+  if (cs > max_pages) cs = max_pages;
+  cs = cs >= 8 ? 8 : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {
-    case 64: return launch_decode_fused<64>(p, st);
-    case 256: return launch_decode_fused<256>(p, st);
+    case 64: return launch_decode_fused<64>(p, cs, st);
+    case 256: return launch_decode_fused<256>(p, cs, st);
     default: return PG_ERR_ARG;
   }
 }

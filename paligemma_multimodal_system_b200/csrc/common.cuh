@@ -110,6 +110,12 @@ PG_DEVINL void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
+// 1D bulk copy global -> shared (bytes multiple of 16, both addresses 16 B aligned), completion on an mbarrier
+PG_DEVINL void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 PG_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // L2 prefetch of a contiguous global range (bytes: multiple of 16), executed by the bulk-copy engine

@@ -320,14 +320,11 @@ class GemmaForCausalLM(nn.Module):
     def decode_buffers(self, B):
         c = self.text_config
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        cnt = self._ws.get("d_cnt")
-        if cnt is None or cnt.numel() != B * Hkv:
-            cnt = self._ws["d_cnt"] = torch.zeros(B * Hkv, device="cuda", dtype=torch.int32)  # attention arrival counters
         return dict(
             h=self._buf("d_h", (B, D), torch.float32), hn=self._buf("d_hn", (B, D), torch.bfloat16),
             qkv=self._buf("d_qkv", (B, (Hq + 2 * Hkv) * dh), torch.float32),
             att=self._buf("d_att", (B, Hq * dh), torch.bfloat16), mid=self._buf("d_mid", (B, F), torch.bfloat16),
-            logits=self._buf("d_logits", (B, V), torch.float32), cnt=cnt)
+            logits=self._buf("d_logits", (B, V), torch.float32))
 
     @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B):
@@ -340,7 +337,6 @@ class GemmaForCausalLM(nn.Module):
         h, hn, qkv, att, mid = bufs["h"], bufs["hn"], bufs["qkv"], bufs["att"], bufs["mid"]
         pos, kvl = kv_cache.counters[0], kv_cache.counters[2]
         max_pages = kv_cache.page_table.shape[1]
-        ws = self._buf("d_ws", (L.pg_attention_decode_fused_workspace_floats(B, Hq, dh, max_pages),), torch.float32)
         scale = 1.0 / math.sqrt(dh)
         W = (Hq + 2 * Hkv) * dh
         sp_qkv = _pick_split((W + 127) // 128, D // 64)
@@ -352,8 +348,8 @@ class GemmaForCausalLM(nn.Module):
             # RoPE + KV append + split-KV attention + combine: one launch
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
-                kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), ws.data_ptr(), bufs["cnt"].data_ptr(),
-                att.data_ptr(), B, Hq, Hkv, dh, PAGE, max_pages, max_pages, scale, st), "pg_attention_decode_fused")
+                kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
+                max_pages, scale, st), "pg_attention_decode_fused")
             _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_o)
             _lib.rmsnorm(h, lw["ln2"], hn)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
