@@ -209,7 +209,10 @@ def main():
 
     B, T = args.batch, args.new_tokens
     model, sd = build_gpu_model(cfg, seed=0)
-    # rank r serves rows [r*B, (r+1)*B) of the global batch (seeded per row): independent requests, no exchange
+    # rank r serves rows [r*B, (r+1)*B) of the global batch (B per GPU: weak scaling): independent requests, no exchange
+    from paligemma_multimodal_system_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(B * world, world, rank)
+    assert hi - lo == B
     inp = make_inputs(cfg, batch=B, prompt_len=PROMPT_LEN, seed=100 + rank)
     S = inp["input_ids"].shape[1]
     host = {k: v.pin_memory() for k, v in inp.items()}

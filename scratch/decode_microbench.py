@@ -48,6 +48,16 @@ def graph_time(name, fn, bytes_per_launch, reps=5):
     us = e0.elapsed_time(e1) * 1e3 / (reps * NL)
     print(f"{name:34s} {us:8.2f} us   {bytes_per_launch / us / 1e3:8.1f} GB/s  ideal {bytes_per_launch / 6550.7e3:6.2f} us   [graph]")
 
+# attention inputs
+PAGE=64; kvlen=324; max_pages=7
+k_pages=[rnd(B*max_pages, PAGE, dh) for _ in range(NL)]; v_pages=[rnd(B*max_pages, PAGE, dh) for _ in range(NL)]
+table=torch.arange(B*max_pages, device=dev, dtype=torch.int32).view(B,max_pages).contiguous()
+kvl=torch.full((B,), kvlen, device=dev, dtype=torch.int32); posd=torch.full((B,), kvlen, device=dev, dtype=torch.int32)
+inv_freq=(1.0/(10000.0**(torch.arange(0,dh,2,dtype=torch.int64).float()/dh))).to(dev)
+qkvf=torch.randn(B, W, device=dev)*0.5
+attout=torch.empty(B, Hq*dh, device=dev, dtype=torch.bfloat16)
+def attn(i):
+    _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), attout.data_ptr(), B, Hq, Hkv, dh, PAGE, max_pages, 1.0/16, _lib.stream()), "attn")
 for pdl in (1,):
     L.pg_set_pdl(pdl)
     print(f"==== PDL={pdl}  B={B}")
@@ -60,6 +70,16 @@ for pdl in (1,):
         graph_time(f"down split{sp}", lambda i: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), D * F * 2)
     graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
     graph_time("rmsnorm", lambda i: _lib.rmsnorm(h, ln_w, hn_out), B * D * 6)
+    graph_time("attention fused (kv 324)", attn, B * kvlen * dh * 2 * 2)
+    def full_layer(i):
+        _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv)
+        _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
+        attn(i)
+        _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
+        _lib.rmsnorm(h, ln_w, hn_out)
+        _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+        _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=18)
+    graph_time("FULL layer", full_layer, (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4)
     def layer(i):
         _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv)
         _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
@@ -68,15 +88,4 @@ for pdl in (1,):
         _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
         _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
     graph_time("layer (no attention)", layer, (W * D + D * D + 3 * F * D) * 2)
-    for gu_mb, dn_mb in ((0, 67), (32, 67), (64, 67), (100, 0), (134, 0), (134, 67), (64, 32)):
-        def layer_pf(i, gu_mb=gu_mb, dn_mb=dn_mb):
-            # spin a little like the attention would (latency-bound part): qkv + o gemm + 2 rmsnorm already there
-            _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv, prefetch=down_w[i] if dn_mb else None, prefetch_bytes=dn_mb << 20)
-            _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
-            _lib.rmsnorm(h, ln_w, hn_out, prefetch=gu_w[i] if gu_mb else None, prefetch_bytes=gu_mb << 20)   # stands in for attention
-            _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
-            _lib.rmsnorm(h, ln_w, hn_out)
-            _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
-            _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=18)
-        graph_time(f"layer + L2 prefetch gu {gu_mb} MB, down {dn_mb} MB", layer_pf, (W * D + D * D + 3 * F * D) * 2)
     timeit("layer (no attention) eager", layer, (W * D + D * D + 3 * F * D) * 2)
