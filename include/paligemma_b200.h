@@ -157,6 +157,52 @@ int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count
 int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counters, int n_counters, int* step, int B,
                       void* stream);
 
+/*
+ * A whole Gemma decode step (token embedding, L x [RMSNorm, QKV, RoPE + KV append + attention, O, RMSNorm, gate||up GEGLU,
+ * down], final RMSNorm, lm_head) in ONE persistent kernel: one CTA per SM, the ops above are phases separated by grid
+ * barriers (modeling_gemma.py:385-418,453-472,501-533 at q_len == 1; B <= 64 sequences).  Cooperative launch.
+ * Buffers are the same as for the per-op entry points; `tensor_maps` is a DEVICE array of (4*L + 4) CUtensorMap filled by
+ * pg_decode_step_encode_maps (host) and copied once; `barrier_state` is an array of 256 zero-initialised uint32 in device
+ * memory (one epoch flag per CTA, persists across launches).
+ */
+typedef struct PgDecodeStepArgs {
+  const void* tensor_maps;
+  int L, B, D, F, Hq, Hkv, dh, V;
+  int split_qkv, split_o, split_down;
+  const int* cur_tok;          /* [B] token ids to embed */
+  const void* embed;           /* bf16 [V, D] */
+  const float* img;            /* fp32 [B, n_img, D] projected image features (may be NULL) */
+  int n_img;
+  float text_scale, img_scale;
+  long long pad_token, image_token;
+  float* h;                    /* fp32 [B, D] residual stream (written) */
+  void* hn;                    /* bf16 [B, D] */
+  float* qkv;                  /* fp32 [B, (Hq+2Hkv)*dh] */
+  void* att;                   /* bf16 [B, Hq*dh] */
+  void* mid;                   /* bf16 [B, F] */
+  float* logits;               /* fp32 [B, V] (lm_head output incl. bias) */
+  const float* ln1;            /* fp32 [L, D] input_layernorm weights */
+  const float* ln2;            /* fp32 [L, D] post_attention_layernorm weights */
+  const float* norm_w;         /* fp32 [D] */
+  const float* head_b;         /* fp32 [V] */
+  float eps;
+  void* k_pages;               /* bf16 [L][pages][64][Hkv*dh] */
+  void* v_pages;
+  long long layer_stride;      /* elements between layers */
+  const int* page_table;       /* [B, max_pages] */
+  const int* pos;              /* [B] position id of the token */
+  const int* kv_len;           /* [B] cache length including the token */
+  const float* inv_freq;       /* [dh/2] */
+  int max_pages, page_size;
+  float scale;                 /* 1/sqrt(dh) */
+  unsigned int* barrier_state; /* [256] */
+  unsigned long long* trace;   /* optional [1024 + 3*(7*L+3)]: per-phase %globaltimer / clock64 of CTA trace_cta (profiling) */
+  int trace_cta;
+} PgDecodeStepArgs;
+int pg_decode_step(const PgDecodeStepArgs* args, void* stream);
+int pg_decode_step_encode_maps(void* out_maps_host, const void* const* weights, const void* hn, const void* att,
+                               const void* mid, int L, int B, int D, int F, int Hq, int Hkv, int dh, int V);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,8 +42,27 @@ SIGNATURES = {
     "pg_argmax": [p, i64, p, i32, i32, p],
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
+    "pg_decode_step": [p, p],
+    "pg_decode_step_encode_maps": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32],
 }
 _RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_launch_count": i64}
+
+
+
+class DecodeStepArgs(C.Structure):
+    """Mirror of PgDecodeStepArgs (include/paligemma_b200.h)."""
+    _fields_ = [
+        ("tensor_maps", p),
+        ("L", i32), ("B", i32), ("D", i32), ("F", i32), ("Hq", i32), ("Hkv", i32), ("dh", i32), ("V", i32),
+        ("split_qkv", i32), ("split_o", i32), ("split_down", i32),
+        ("cur_tok", p), ("embed", p), ("img", p), ("n_img", i32), ("text_scale", f32), ("img_scale", f32),
+        ("pad_token", i64), ("image_token", i64),
+        ("h", p), ("hn", p), ("qkv", p), ("att", p), ("mid", p), ("logits", p),
+        ("ln1", p), ("ln2", p), ("norm_w", p), ("head_b", p), ("eps", f32),
+        ("k_pages", p), ("v_pages", p), ("layer_stride", i64), ("page_table", p), ("pos", p), ("kv_len", p), ("inv_freq", p),
+        ("max_pages", i32), ("page_size", i32), ("scale", f32), ("barrier_state", p), ("trace", p), ("trace_cta", i32),
+    ]
+
 
 _lib = None
 

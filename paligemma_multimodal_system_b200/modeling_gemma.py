@@ -8,7 +8,9 @@ Compute path per layer (all through the C ABI of include/paligemma_b200.h):
             residual stream, and split-KV attention over the paged bf16 cache.
 The residual stream is fp32 (as in the reference); GEMM operands are bf16.
 """
+import ctypes
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -210,6 +212,8 @@ class GemmaForCausalLM(nn.Module):
         self.model = GemmaModel(config, **fk)
         self._packed = None
         self._ws = {}
+        self._step_maps = {}
+        self._barrier_state = None
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
@@ -248,8 +252,11 @@ class GemmaForCausalLM(nn.Module):
                 qkv_w=torch.cat([_bf16(a.q_proj.weight), _bf16(a.k_proj.weight), _bf16(a.v_proj.weight)], 0).contiguous(),
                 o_w=_bf16(a.o_proj.weight), gu_w=gu, down_w=_bf16(l.mlp.down_proj.weight)))
             del gate, up
+        pk["ln1_all"] = torch.stack([lw["ln1"] for lw in pk["layers"]]).contiguous()
+        pk["ln2_all"] = torch.stack([lw["ln2"] for lw in pk["layers"]]).contiguous()
         torch.cuda.synchronize()
         self._packed = pk
+        self._step_maps = {}
         return pk
 
     def _buf(self, name, shape, dtype):
@@ -356,6 +363,66 @@ class GemmaForCausalLM(nn.Module):
             _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
         _lib.rmsnorm(h, pk["norm_w"], hn)
         _lib.gemm(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], swap=1)
+        return bufs["logits"]
+
+    # -- one-kernel decode step ------------------------------------------------------------------------------------------
+    def megakernel_ok(self, B):
+        c = self.text_config
+        # opt-in: measured slower than the PDL-chained per-op kernels (2.19 vs 1.74 ms / step at 3B, 64 sequences): a grid
+        # barrier costs ~2.3 us, about the same as a programmatic-dependent-launch kernel boundary
+        return (os.environ.get("PG_MEGAKERNEL", "0") == "1" and B * c.num_key_value_heads <= 148 and B <= 64
+                and c.head_dim in (64, 256) and c.num_attention_heads // c.num_key_value_heads <= 8)
+
+    @torch.no_grad()
+    def decode_step(self, bufs, kv_cache: KVCache, B, tokens_i32, img, img_scale, pad_token, image_token):
+        """Embeds `tokens_i32` [B] and runs every layer + final norm + lm_head; fp32 logits land in bufs['logits'].
+        B <= 64: ONE persistent cooperative kernel (csrc/decode_step.cu); otherwise the per-op kernels."""
+        c = self.text_config
+        pk = self._packed or self.pack()
+        L = _lib.lib()
+        D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
+        if not self.megakernel_ok(B):
+            _lib.check(L.pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
+                                         0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
+                                         _lib.stream()), "pg_embed_tokens")
+            return self.decode_layers(bufs, kv_cache, B)
+        key = (B, bufs["hn"].data_ptr(), bufs["att"].data_ptr(), bufs["mid"].data_ptr())
+        maps = self._step_maps.get(key)
+        if maps is None:
+            n = 4 * c.num_hidden_layers + 4
+            host = ctypes.create_string_buffer(n * 128)
+            wl = []
+            for lw in pk["layers"]:
+                wl += [lw["qkv_w"].data_ptr(), lw["o_w"].data_ptr(), lw["gu_w"].data_ptr(), lw["down_w"].data_ptr()]
+            wl.append(pk["head_w"].data_ptr())
+            warr = (ctypes.c_void_p * len(wl))(*wl)
+            _lib.check(L.pg_decode_step_encode_maps(ctypes.addressof(host), ctypes.addressof(warr), bufs["hn"].data_ptr(),
+                                                    bufs["att"].data_ptr(), bufs["mid"].data_ptr(), c.num_hidden_layers, B, D, F,
+                                                    Hq, Hkv, dh, V), "pg_decode_step_encode_maps")
+            maps = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).cuda()
+            self._step_maps = {key: maps}
+        if self._barrier_state is None:
+            self._barrier_state = torch.zeros(256, device="cuda", dtype=torch.int32)
+        W = (Hq + 2 * Hkv) * dh
+        a = _lib.DecodeStepArgs()
+        a.tensor_maps = maps.data_ptr()
+        a.L, a.B, a.D, a.F, a.Hq, a.Hkv, a.dh, a.V = c.num_hidden_layers, B, D, F, Hq, Hkv, dh, V
+        a.split_qkv = _pick_split((W + 127) // 128, D // 64)
+        a.split_o = _pick_split((D + 127) // 128, D // 64)
+        a.split_down = _pick_split((D + 127) // 128, F // 64)
+        a.cur_tok, a.embed, a.img = tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img)
+        a.n_img = 0 if img is None else img.shape[1]
+        a.text_scale, a.img_scale, a.pad_token, a.image_token = D ** 0.5, img_scale, pad_token, image_token
+        a.h, a.hn, a.qkv, a.att, a.mid, a.logits = (bufs[k].data_ptr() for k in ("h", "hn", "qkv", "att", "mid", "logits"))
+        a.ln1, a.ln2, a.norm_w, a.head_b, a.eps = pk["ln1_all"].data_ptr(), pk["ln2_all"].data_ptr(), pk["norm_w"].data_ptr(), pk["head_b"].data_ptr(), 1e-6
+        a.k_pages, a.v_pages = kv_cache.k_pages.data_ptr(), kv_cache.v_pages.data_ptr()
+        a.layer_stride = kv_cache.k_pages.stride(0)
+        a.page_table, a.pos, a.kv_len = kv_cache.page_table.data_ptr(), kv_cache.counters[0].data_ptr(), kv_cache.counters[2].data_ptr()
+        a.inv_freq, a.max_pages, a.page_size, a.scale = pk["inv_freq"].data_ptr(), kv_cache.page_table.shape[1], PAGE, 1.0 / math.sqrt(dh)
+        a.barrier_state = self._barrier_state.data_ptr()
+        a.trace = _lib.ptr(getattr(self, "_trace", None))
+        a.trace_cta = getattr(self, "_trace_cta", 0)
+        _lib.check(L.pg_decode_step(ctypes.byref(a), _lib.stream()), "pg_decode_step")
         return bufs["logits"]
 
     def forward(self, input_embeds=None, position_ids=None, attention_mask=None, kv_cache=None):

@@ -122,14 +122,11 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         return h, pos
 
     @torch.no_grad()
-    def _embed_step(self, tokens_i32, kv_cache, h_out):
-        pk = self.language_model._packed or self.language_model.pack()
+    def _decode_step(self, tokens_i32, kv_cache, bufs, B):
         D = self.text_config.hidden_size
-        img = kv_cache.image_feats
-        _lib.check(_lib.lib().pg_embed_tokens(
-            tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), h_out.data_ptr(), tokens_i32.shape[0], D,
-            0 if img is None else img.shape[1], D ** 0.5, (self.config.projection_dim ** -0.5) * (D ** 0.5), self.pad_token_id,
-            self.dummy_image_token_id, _lib.stream()), "pg_embed_tokens")
+        return self.language_model.decode_step(bufs, kv_cache, B, tokens_i32, kv_cache.image_feats,
+                                               (self.config.projection_dim ** -0.5) * (D ** 0.5), self.pad_token_id,
+                                               self.dummy_image_token_id)
 
     # -- reference forward ---------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -157,8 +154,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             kv_cache.counters[2].fill_(n + 1)
             bufs = lm.decode_buffers(B)
             tok = input_ids.to(device="cuda", dtype=torch.int32).reshape(B).contiguous()
-            self._embed_step(tok, kv_cache, bufs["h"])
-            logits = lm.decode_layers(bufs, kv_cache, B).clone().view(B, 1, -1)
+            logits = self._decode_step(tok, kv_cache, bufs, B).clone().view(B, 1, -1)
             kv_cache._set_len(n + 1, c.num_hidden_layers)
         out = {"logits": logits}
         if kv_cache is not None:
@@ -233,8 +229,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
                                            step.data_ptr(), B, _lib.stream()), "pg_advance_decode")
 
         def decode_step(t=None):
-            self._embed_step(cur, kv, bufs["h"])
-            lg = lm.decode_layers(bufs, kv, B)
+            lg = self._decode_step(cur, kv, bufs, B)
             if t is not None and return_logits:
                 logit_log[t].copy_(lg)
             sample(lg)
