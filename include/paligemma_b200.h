@@ -38,6 +38,8 @@ long long pg_launch_count(void);
 /* Programmatic dependent launch for the decode-step kernels (default on): the next kernel's prologue and weight
  * prefetch overlap the running kernel; every such kernel executes griddepcontrol.wait before dependent accesses. */
 int pg_set_pdl(int on);
+/* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
+int pg_debug_set_gemm_trace(long long* device_buffer);
 
 /*
  * acc[t,f] = sum_k x[t,k] * w[f,k]  (bf16 in, fp32 accumulate on tcgen05 tensor cores, accumulator in TMEM).

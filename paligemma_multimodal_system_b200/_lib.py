@@ -24,6 +24,7 @@ SIGNATURES = {
     "pg_check_device": [],
     "pg_launch_count": [],
     "pg_set_pdl": [i32],
+    "pg_debug_set_gemm_trace": [p],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
         }
       }
     }
+    __syncwarp();  // the whole warp reaches the CTA-wide barrier below together (bar.sync counts warps, not lanes)
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
     if (lane == 0) {
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
         }
       }
     }
+    __syncwarp();
   } else {
     // =========================================== workers ================================================
     const int wtid = threadIdx.x - 64;       // 0..255

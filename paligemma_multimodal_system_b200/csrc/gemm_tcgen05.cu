@@ -53,6 +53,7 @@ struct GemmArgs {
   const float* bias;
   const float* resid;
   long long ldr;
+  long long* trace;  // optional profiling stamps (clock64) written by CTA 0
 };
 
 struct TileInfo {
@@ -108,6 +109,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   const int total_kb = (args.K + BK - 1) / BK;
   const int num_tiles = m_blocks * n_blocks * args.split_k;
 
+  const bool tr = (args.trace != nullptr) && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) args.trace[0] = clock64();  // kernel entry
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
@@ -149,7 +152,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
         }
       }
+      if (tr) args.trace[1] = clock64();  // weights prefetch issued
       griddep_wait();
+      if (tr) args.trace[2] = clock64();  // previous kernel complete
       griddep_launch_dependents();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
@@ -167,6 +172,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
       }
     }
+    __syncwarp();  // the whole warp reaches the CTA-wide barrier below together (bar.sync counts warps, not lanes)
   } else if (warp == 1) {
     // =================================== MMA issuer =====================================
     if (lane == 0) {
@@ -197,6 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // =================================== epilogue warps =================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
@@ -209,6 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (tr && threadIdx.x == 64) args.trace[3] = clock64();  // accumulator ready (first tile)
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const int rl = q * 32 + lane;  // row inside the tile
@@ -340,6 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         } else {
           const bool f_ok = fr < args.features;
           const float bias = (args.bias != nullptr && f_ok && first_split) ? __ldg(args.bias + fr) : 0.f;
+          // (measured: 16-byte REDG.F32x4 after a lane-quad transpose is ~2x SLOWER here than 4-byte coalesced reds)
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 16) {
             if (j_base + c0 >= args.tokens) break;  // warp-uniform
@@ -369,6 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
+      if (tr && threadIdx.x == 64) args.trace[4] = clock64();  // epilogue of this tile issued
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
@@ -376,6 +386,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) args.trace[5] = clock64();  // all roles done
+  if (tr && threadIdx.x == 64) args.trace[6] = clock64();
+  if (tr && threadIdx.x == 32) args.trace[7] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -415,6 +428,9 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, long long rows, long lo
   return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
 }
 
+static long long* g_gemm_trace = nullptr;
+static int g_gemm_trace_idx = 0;
+extern "C" int pg_debug_set_gemm_trace(long long* p) { g_gemm_trace = p; g_gemm_trace_idx = 0; return 0; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -468,7 +484,7 @@ extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long lo
 
   GemmArgs a;
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
-  a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
+  a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr; a.trace = g_gemm_trace ? g_gemm_trace + 8 * (g_gemm_trace_idx++ % 64) : nullptr;
 
   CUtensorMap ta, tb;
   int rc;

@@ -61,12 +61,12 @@ def attn(i):
 for pdl in (1,):
     L.pg_set_pdl(pdl)
     print(f"==== PDL={pdl}  B={B}")
-    for sp in (7, 14):
+    for sp in (2, 4, 7, 14):
         graph_time(f"qkv split{sp}", lambda i: _lib.gemm(hn, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), W * D * 2)
-    for sp in (9, 18):
+    for sp in (1, 2, 4, 9, 18):
         graph_time(f"o split{sp}", lambda i: _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), D * D * 2)
     graph_time("gate-up geglu", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
-    for sp in (9, 18):
+    for sp in (4, 9, 18, 36):
         graph_time(f"down split{sp}", lambda i: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp), D * F * 2)
     graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
     graph_time("rmsnorm", lambda i: _lib.rmsnorm(h, ln_w, hn_out), B * D * 6)
