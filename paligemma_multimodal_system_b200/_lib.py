@@ -139,3 +139,21 @@ def rmsnorm(x, w, out_bf16, eps=1e-6, zero_buf=None, prefetch=None, prefetch_byt
     pf_bytes = 0 if prefetch is None else (prefetch.numel() * prefetch.element_size() if prefetch_bytes is None else prefetch_bytes)
     check(lib().pg_rmsnorm(x.data_ptr(), w.data_ptr(), out_bf16.data_ptr(), rows, D, float(eps), ptr(zero_buf),
                            0 if zero_buf is None else zero_buf.numel(), ptr(prefetch), pf_bytes, stream()), "pg_rmsnorm")
+
+
+def gemm_residual(x, w, h, bias=None):
+    """h += x @ w.T (+ bias): the residual-stream GEMMs (out_proj / fc2 / o_proj / down_proj).  With enough output tiles
+    the epilogue adds the fp32 residual in place; with few tiles (small token counts: latency path, decode) the K
+    dimension is split over CTAs and the partials are red.add-ed into h so that the whole GPU streams the weights."""
+    T, K = x.shape
+    F = w.shape[0]
+    swap = 1 if T <= 128 else 0
+    if swap:
+        tiles = (F + 127) // 128
+    else:
+        tiles = ((T + 127) // 128) * ((F + 255) // 256)
+    kb = (K + 63) // 64
+    if tiles >= 120 or kb < 8 or T > 512:  # (large-batch prefill keeps the deterministic, atomics-free epilogue)
+        return gemm(x, w, h, mode=EPI_F32, bias=bias, resid=h, swap=swap)
+    split = max(1, min(kb // 4, (2 * 148 if swap else 148) // tiles))
+    return gemm(x, w, h, mode=EPI_ATOMIC_F32, bias=bias, swap=swap, split_k=split)

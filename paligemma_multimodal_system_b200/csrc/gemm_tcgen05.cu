@@ -500,7 +500,16 @@ extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long lo
       default: return launch<128, true>(ta, tb, a, tiles, st);
     }
   } else {
-    int BN = (mode == PG_EPI_GEGLU) ? (features >= 256 ? 256 : 128) : (features > 128 ? 256 : features > 64 ? 128 : 64);
+    // largest N tile that still gives the persistent grid ~a wave of CTAs (small token counts: latency path)
+    const int m_blocks = (tokens + BM - 1) / BM;
+    auto ntiles = [&](int bn) { return m_blocks * ((features + bn - 1) / bn) * split_k; };
+    int BN;
+    if (mode == PG_EPI_GEGLU) {
+      BN = (features >= 256 && ntiles(256) >= 120) ? 256 : 128;
+    } else {
+      BN = features > 128 ? 256 : features > 64 ? 128 : 64;
+      while (BN > 64 && ntiles(BN) < 120) BN /= 2;
+    }
     if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
     const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;

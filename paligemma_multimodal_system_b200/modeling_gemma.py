@@ -305,10 +305,10 @@ class GemmaForCausalLM(nn.Module):
                 q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), B, Hkv, S * G, S, dh, G,
                 S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
                 S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill")
-            _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_F32, resid=h, swap=0 if T > 128 else 1)
+            _lib.gemm_residual(att, lw["o_w"], h)
             _lib.rmsnorm(h, lw["ln2"], hn)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=0 if T > 128 else 1)
-            _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_F32, resid=h, swap=0 if T > 128 else 1)
+            _lib.gemm_residual(mid, lw["down_w"], h)
         if have_cache:
             kv_cache._set_len(S, c.num_hidden_layers)
         if last_only:

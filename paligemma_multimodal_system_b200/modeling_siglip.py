@@ -176,10 +176,10 @@ class SiglipVisionModel(nn.Module):
             _lib.check(L.pg_attention_prefill(
                 qkv.data_ptr(), qkv.data_ptr() + 2 * Dv, qkv.data_ptr() + 4 * Dv, att.data_ptr(), B, Hh, N, N, dh, 1,
                 N * 3 * Dv, 3 * Dv, 0, dh, N * 3 * Dv, 3 * Dv, dh, N * Dv, Dv, 0, dh, scale, st), "pg_attention_prefill")
-            _lib.gemm(att, lw["out_w"], x, mode=_lib.EPI_F32, bias=lw["out_b"], resid=x, swap=0)
+            _lib.gemm_residual(att, lw["out_w"], x, bias=lw["out_b"])
             _lib.layernorm(x, lw["ln2_w"], lw["ln2_b"], c.layer_norm_eps, out_bf16=h)
             _lib.gemm(h, lw["fc1_w"], mid, mode=_lib.EPI_BF16, bias=lw["fc1_b"], act_gelu=True, swap=0)
-            _lib.gemm(mid, lw["fc2_w"], x, mode=_lib.EPI_F32, bias=lw["fc2_b"], resid=x, swap=0)
+            _lib.gemm_residual(mid, lw["fc2_w"], x, bias=lw["fc2_b"])
         if out_bf16:
             _lib.layernorm(x, pk["post_w"], pk["post_b"], c.layer_norm_eps, out_bf16=h)
             return h
