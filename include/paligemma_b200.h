@@ -40,6 +40,7 @@ long long pg_launch_count(void);
 int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
+int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_decode_fused (8 stamps per launch) */
 
 /*
  * acc[t,f] = sum_k x[t,k] * w[f,k]  (bf16 in, fp32 accumulate on tcgen05 tensor cores, accumulator in TMEM).
@@ -115,11 +116,12 @@ long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_sp
  * Decode-step attention in ONE launch (modeling_gemma.py:285-339 at q_len == 1 + KVCache.update :18-57): rotates q and
  * the new k (fp32 qkv [B, (Hq+2Hkv)*dh] straight from the split-K QKV GEMM), appends k/v to the paged cache at slot
  * kv_len[b]-1 and attends over kv_len[b] keys.  One thread-block cluster per (sequence, kv head): each rank streams a
- * contiguous range of 64-key pages through shared memory, the ranks merge through distributed shared memory.
+ * contiguous range of 64-key pages (TMA tensor loads into 128B-swizzled shared memory) and the ranks merge through
+ * distributed shared memory.  num_pages = pages in the pool (k_pages / v_pages are [num_pages, 64, Hkv*dh] bf16).
  */
 int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
                               void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh,
-                              int page_size, int max_pages, float scale, void* stream);
+                              int page_size, int num_pages, int max_pages, float scale, void* stream);
 
 /* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
  * views, modeling_gemma.py:8-64). */

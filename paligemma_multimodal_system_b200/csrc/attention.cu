@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "paligemma_b200.h"
+#include "tmap.cuh"
 
 namespace pg {
 
@@ -416,26 +417,34 @@ struct AttnDecodeFusedParams {
   bf16* out;              // [B, Hq*dh]
   int B, Hq, Hkv, max_pages;
   float sl2;
+  long long* trace;  // optional profiling stamps (clock64) of CTA 0
 };
 
 template <int DH>
-__global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecodeFusedParams p) {
+__global__ void __launch_bounds__(256) attn_decode_fused_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                const __grid_constant__ CUtensorMap tmV,
+                                                                const AttnDecodeFusedParams p) {
   using C = AttnCfg<DH>;
   namespace cg = cooperative_groups;
   constexpr int BLOCK_N = 64;
   constexpr int HALF = DH / 2;
   constexpr int NBUF = 3;
   constexpr int NT = 256;                          // 8 warps: two groups of 4, each group works on its own page
-  constexpr int BUF_ELEMS = 2 * BLOCK_N * C::LDS;  // one ring slot: K page then V page
+  constexpr int NBOX = DH / 64;                    // 128-byte-wide TMA boxes per K / V page
+  constexpr int BOX_BYTES = BLOCK_N * 128;         // 64 rows x 128 B, 128B-swizzled (conflict-free ldmatrix)
+  constexpr int KV_BYTES = NBOX * BOX_BYTES;       // one K (or V) page in shared memory
+  constexpr int SLOT_BYTES = 2 * KV_BYTES;         // ring slot: K page then V page
   constexpr int RLD = DH + 2;                      // partial row: DH accumulators, m (log2 domain), l
-  constexpr uint32_t ROW_BYTES = DH * 2;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);    // [16][LDS]
-  bf16* ring = Qs + 16 * C::LDS;                   // [NBUF][K 64 x LDS | V 64 x LDS]
-  float* red = reinterpret_cast<float*>(ring);                      // after the loop: [8 warps][16][RLD]  (slots 0-1)
-  float* part = reinterpret_cast<float*>(ring + 2 * BUF_ELEMS);     // this CTA's merged partial [16][RLD] (slot 2)
+  extern __shared__ __align__(1024) uint8_t smem_dec[];
+  uint8_t* ring = smem_dec;                                                // [NBUF][K | V]
+  bf16* Qs = reinterpret_cast<bf16*>(smem_dec + NBUF * SLOT_BYTES);        // [16][LDS]
+  float* red = reinterpret_cast<float*>(ring);                             // after the loop: [8 warps][16][RLD]
+  float* part = red + 8 * 16 * RLD;                                        // this CTA's merged partial [16][RLD]
+  static_assert(8 * 16 * RLD * 4 + 16 * RLD * 4 <= NBUF * SLOT_BYTES, "reduction staging must fit in the page ring");
   __shared__ bf16 new_k[DH], new_v[DH];
   __shared__ __align__(8) uint64_t bars[NBUF];
+  const uint32_t ring_u32 = smem_u32(ring);
+  if ((ring_u32 & 1023u) != 0) __trap();
 
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = static_cast<int>(cluster.num_blocks());
@@ -445,11 +454,16 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
   const int seq = blockIdx.x / CS;
   const int b = seq / p.Hkv, hk = seq % p.Hkv;
   const int group = p.Hq / p.Hkv;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) p.trace[0] = clock64();
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
     for (int i = 0; i < NBUF; ++i) mbar_init(smem_u32(&bars[i]), 1);
     mbar_fence_init();
   }
   griddep_wait();
+  if (tr) p.trace[1] = clock64();
   if (threadIdx.x == 0) griddep_launch_dependents();
   __syncthreads();
   const int len = p.kv_len[b];
@@ -463,34 +477,60 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
   const long long kv_ts = static_cast<long long>(p.Hkv) * DH;
   const int* ptab = p.page_table + b * p.max_pages;
 
-  // One 512 B bulk copy (TMA engine) per cached K / V row, completion counted on the slot's mbarrier.  Rows that are
-  // not in the cache (beyond kv_len, or the new token's slot) are zero-filled with plain stores.
+  // One page = NBOX TMA boxes for K and NBOX for V (64 rows x 128 B each, hardware 128B swizzle), all on the slot's
+  // mbarrier.  Rows beyond kv_len hold zeros / stale finite values from the page pool: their scores are masked and
+  // their probabilities are exactly 0.  The new token's row is patched in from registers below.
+  // (issued by thread 128, which has no RoPE work, so that the page loads overlap the query staging)
   auto load_kv = [&](int tile, int slot) {
-    const int page = ptab[tile];
-    const int n0 = tile * BLOCK_N;
-    const uint32_t bar = smem_u32(&bars[slot]);
-    int rows = min(BLOCK_N, len - n0);
-    if (tile == new_tile) rows -= 1;  // the new token's row is patched in from registers
-    if (threadIdx.x == 0) mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROW_BYTES * 2);
-    if (threadIdx.x < 2 * BLOCK_N) {
-      const int kv = threadIdx.x >> 6, r = threadIdx.x & 63;
-      bf16* dst = ring + slot * BUF_ELEMS + kv * BLOCK_N * C::LDS + r * C::LDS;
-      if ((n0 + r) < len && (n0 + r) != new_slot) {
-        const bf16* src = (kv ? p.v_pages : p.k_pages) + (static_cast<long long>(page) * BLOCK_N + r) * kv_ts + hk * DH;
-        bulk_copy_g2s(smem_u32(dst), src, ROW_BYTES, bar);
-      } else {
-        for (int c = 0; c < C::DHP / 8; ++c) reinterpret_cast<uint4*>(dst)[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 128) {
+      const int page = __ldg(ptab + tile);
+      const uint32_t bar = smem_u32(&bars[slot]);
+      const uint32_t dst = ring_u32 + slot * SLOT_BYTES;
+      mbar_expect_tx(bar, SLOT_BYTES);
+#pragma unroll
+      for (int bx = 0; bx < NBOX; ++bx) {
+        tma_load_2d(dst + bx * BOX_BYTES, &tmK, bar, hk * DH + bx * 64, page * BLOCK_N, kEvictFirst);
+        tma_load_2d(dst + KV_BYTES + bx * BOX_BYTES, &tmV, bar, hk * DH + bx * 64, page * BLOCK_N, kEvictFirst);
       }
     }
   };
-  for (int i = 0; i < NBUF && i < n_my; ++i) load_kv(t_begin + i, i);  // everything this rank can hold is in flight now
+  // byte offset of element (row r, column c) inside a swizzled K (or V) page
+  auto swz = [&](int r, int c) -> int { return (c >> 6) * BOX_BYTES + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
+  auto patch_new_row = [&](int slot) {
+    uint8_t* Kb = ring + slot * SLOT_BYTES;
+    const int r = new_slot - new_tile * BLOCK_N;
+    for (int k = threadIdx.x; k < DH; k += NT) {
+      *reinterpret_cast<bf16*>(Kb + swz(r, k)) = new_k[k];
+      *reinterpret_cast<bf16*>(Kb + KV_BYTES + swz(r, k)) = new_v[k];
+    }
+  };
+  if (threadIdx.x == 128) {  // everything this rank can hold goes in flight now; page ids are fetched together first
+    int pages[NBUF];
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) pages[i] = (i < n_my) ? __ldg(ptab + t_begin + i) : 0;
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) {
+      if (i < n_my) {
+        const uint32_t bar = smem_u32(&bars[i]);
+        const uint32_t dst = ring_u32 + i * SLOT_BYTES;
+        mbar_expect_tx(bar, SLOT_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) {
+          tma_load_2d(dst + bx * BOX_BYTES, &tmK, bar, hk * DH + bx * 64, pages[i] * BLOCK_N, kEvictFirst);
+          tma_load_2d(dst + KV_BYTES + bx * BOX_BYTES, &tmV, bar, hk * DH + bx * 64, pages[i] * BLOCK_N, kEvictFirst);
+        }
+      }
+    }
+  }
 
   // RoPE (rotate-half, modeling_gemma.py:138-151) on the query heads of this group (+ the new key when owned).
   // All global loads of a thread are issued back to back (independent), then rotated: one L2 round trip, not 20.
   const int W = (p.Hq + 2 * p.Hkv) * DH;
   const float* __restrict__ row = p.qkv + static_cast<long long>(b) * W;
-  const float posf = static_cast<float>(p.pos[b]);
+  const float posf = static_cast<float>(__ldg(p.pos + b));
+  const int new_page = owns_new ? __ldg(ptab + new_tile) : 0;
   for (int i = threadIdx.x; i < HALF; i += NT) {
+    const float freq = __ldg(p.inv_freq + i);
     float x1[16], x2[16], kx1 = 0.f, kx2 = 0.f, vx1 = 0.f, vx2 = 0.f;
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
@@ -507,7 +547,7 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
       vx1 = __ldcg(vh + i); vx2 = __ldcg(vh + i + HALF);
     }
     float sn, cs;
-    sincosf(posf * p.inv_freq[i], &sn, &cs);
+    sincosf(posf * freq, &sn, &cs);
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
       if (g < group) {
@@ -518,7 +558,7 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
     if (owns_new) {
       const bf16 k1 = __float2bfloat16(kx1 * cs - kx2 * sn), k2 = __float2bfloat16(kx2 * cs + kx1 * sn);
       const bf16 v1 = __float2bfloat16(vx1), v2 = __float2bfloat16(vx2);
-      const int page = ptab[new_tile];
+      const int page = new_page;
       bf16* kb = p.k_pages + (static_cast<long long>(page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
       bf16* vb = p.v_pages + (static_cast<long long>(page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
       kb[i] = k1; kb[i + HALF] = k2;   // KVCache.update (modeling_gemma.py:18-57)
@@ -533,18 +573,7 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
     if (r >= group || cc >= DH) Qs[r * C::LDS + cc] = __float2bfloat16(0.f);
   }
   __syncthreads();  // Q, new_k / new_v staged
-  if (owns_new) {   // patch the new token's row into its ring slot (if that page is among the first NBUF)
-    const int i_new = new_tile - t_begin;
-    if (i_new < NBUF) {
-      bf16* Kb = ring + (i_new % NBUF) * BUF_ELEMS;
-      const int r = new_slot - new_tile * BLOCK_N;
-      for (int k = threadIdx.x; k < DH; k += NT) {
-        Kb[r * C::LDS + k] = new_k[k];
-        Kb[(BLOCK_N + r) * C::LDS + k] = new_v[k];
-      }
-    }
-  }
-  __syncthreads();
+  if (tr) p.trace[2] = clock64();
 
   float o[C::DHP / 8][4];
 #pragma unroll
@@ -562,25 +591,38 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
       const int t = t_begin + i;
       const int slot = i % NBUF;
       mbar_wait(smem_u32(&bars[slot]), (i / NBUF) & 1);
-      const bf16* Kt = ring + slot * BUF_ELEMS + wq * 16 * C::LDS;
-      const bf16* Vt = Kt + BLOCK_N * C::LDS;
+      if (tr && i0 == 0) p.trace[3] = clock64();
+      if (t == new_tile) {  // the TMA has landed: overwrite the new token's row (only this warp group reads this page)
+        const int r = new_slot - new_tile * BLOCK_N;
+        uint8_t* Kb = ring + slot * SLOT_BYTES;
+        for (int k = (warp & 3) * 32 + lane; k < DH; k += 128) {
+          *reinterpret_cast<bf16*>(Kb + swz(r, k)) = new_k[k];
+          *reinterpret_cast<bf16*>(Kb + KV_BYTES + swz(r, k)) = new_v[k];
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");  // the 4 warps of this group
+      }
+      const uint32_t k_base = ring_u32 + slot * SLOT_BYTES;
+      const uint32_t v_base = k_base + KV_BYTES;
       float s[2][4], s2[2][4];  // two independent accumulator sets (even / odd k-steps): 4 MMA chains in flight
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[a][e] = s2[a][e] = 0.f;
-      const uint32_t k_addr = smem_u32(Kt + ((lane & 7) + (lane >> 4) * 8) * C::LDS + ((lane >> 3) & 1) * 8);
+      // ldmatrix row addresses in the swizzled page: row kr, 16-byte chunk index XOR (kr & 7)
+      const int kr = wq * 16 + (lane & 7) + (lane >> 4) * 8;
+      const uint32_t k_row = k_base + kr * 128;
+      const int k_sub = (lane >> 3) & 1;  // which 8-column half of the 16-wide k-step
 #pragma unroll
       for (int ks = 0; ks < C::DHP / 16; ks += 2) {
         uint32_t a[4], b0, b1, b2, b3;
         ldmatrix_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
-        ldmatrix_x4(k_addr + ks * 32, b0, b1, b2, b3);
+        ldmatrix_x4(k_row + (ks >> 2) * BOX_BYTES + (((((ks & 3) << 1) + k_sub) ^ (kr & 7)) << 4), b0, b1, b2, b3);
         mma_bf16_16816(s[0], a, b0, b1);
         mma_bf16_16816(s[1], a, b2, b3);
         if (ks + 1 < C::DHP / 16) {
           uint32_t c4[4], d0, d1, d2, d3;
           ldmatrix_x4(q_addr + (ks + 1) * 32, c4[0], c4[1], c4[2], c4[3]);
-          ldmatrix_x4(k_addr + (ks + 1) * 32, d0, d1, d2, d3);
+          ldmatrix_x4(k_row + ((ks + 1) >> 2) * BOX_BYTES + ((((((ks + 1) & 3) << 1) + k_sub) ^ (kr & 7)) << 4), d0, d1, d2, d3);
           mma_bf16_16816(s2[0], c4, d0, d1);
           mma_bf16_16816(s2[1], c4, d2, d3);
         }
@@ -625,11 +667,13 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
       a[1] = pack_bf16(s[0][2], s[0][3]);
       a[2] = pack_bf16(s[1][0], s[1][1]);
       a[3] = pack_bf16(s[1][2], s[1][3]);
-      const uint32_t v_addr = smem_u32(Vt + ((lane & 7) + ((lane >> 3) & 1) * 8) * C::LDS + (lane >> 4) * 8);
+      const int vr = wq * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const uint32_t v_row = v_base + vr * 128;
+      const int v_sub = lane >> 4;
 #pragma unroll
       for (int dp = 0; dp < C::DHP / 16; ++dp) {
         uint32_t b0, b1, b2, b3;
-        ldmatrix_x4_trans(v_addr + dp * 32, b0, b1, b2, b3);
+        ldmatrix_x4_trans(v_row + (dp >> 2) * BOX_BYTES + (((((dp & 3) << 1) + v_sub) ^ (vr & 7)) << 4), b0, b1, b2, b3);
         mma_bf16_16816(o[2 * dp], a, b0, b1);
         mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
       }
@@ -640,24 +684,13 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
       fence_proxy_async_smem();
       for (int k = 0; k < 2; ++k) {
         const int inext = i0 + k + NBUF;
-        if (i0 + k < n_my && inext < n_my) {
-          load_kv(t_begin + inext, inext % NBUF);
-          if (t_begin + inext == new_tile) {  // (only when the new token's page is not among the first NBUF)
-            __syncthreads();
-            bf16* Kb = ring + (inext % NBUF) * BUF_ELEMS;
-            const int r = new_slot - new_tile * BLOCK_N;
-            for (int q = threadIdx.x; q < DH; q += NT) {
-              Kb[r * C::LDS + q] = new_k[q];
-              Kb[(BLOCK_N + r) * C::LDS + q] = new_v[q];
-            }
-          }
-        }
+        if (i0 + k < n_my && inext < n_my) load_kv(t_begin + inext, inext % NBUF);
       }
-      __syncthreads();
     }
   }
   __syncthreads();
 
+  if (tr) p.trace[4] = clock64();
   // ---- merge the 8 warps (disjoint key subsets) through shared memory ----
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -684,69 +717,96 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const AttnDecode
   }
   __syncthreads();
   const long long hq0 = static_cast<long long>(b) * p.Hq + hk * group;  // first query head of this group
-  for (int idx = threadIdx.x; idx < group * DH; idx += NT) {
-    const int r = idx / DH, col = idx % DH;
+  __shared__ float s_w[8][16];   // weight of warp w's partial for row r (already divided by the row sum when CS == 1)
+  __shared__ float s_ML[16][2];  // this CTA's merged (max, sum) per row
+  if (threadIdx.x < group) {
+    const int r = threadIdx.x;
     float M = -INFINITY;
 #pragma unroll
     for (int w = 0; w < 8; ++w) M = fmaxf(M, red[(w * 16 + r) * RLD + DH]);
     const float Ms = (M == -INFINITY) ? 0.f : M;
-    float acc = 0.f, Lsum = 0.f;
+    float Lsum = 0.f, wv[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const float wgt = exp2f(red[(w * 16 + r) * RLD + DH] - Ms);
-      acc += red[(w * 16 + r) * RLD + col] * wgt;
-      Lsum += red[(w * 16 + r) * RLD + DH + 1] * wgt;
+      wv[w] = exp2f(red[(w * 16 + r) * RLD + DH] - Ms);
+      Lsum += red[(w * 16 + r) * RLD + DH + 1] * wv[w];
     }
-    if (CS == 1) {
-      p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc / Lsum);
-    } else {
-      part[r * RLD + col] = acc;
-      if (col == 0) { part[r * RLD + DH] = M; part[r * RLD + DH + 1] = Lsum; }
-    }
+    const float norm = (CS == 1) ? 1.f / Lsum : 1.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_w[w][r] = wv[w] * norm;
+    s_ML[r][0] = M;
+    s_ML[r][1] = Lsum;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < group * DH; idx += NT) {
+    const int r = idx / DH, col = idx % DH;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += red[(w * 16 + r) * RLD + col] * s_w[w][r];
+    if (CS == 1) p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc);
+    else part[r * RLD + col] = acc;
+  }
+  if (CS > 1 && threadIdx.x < group) {
+    part[threadIdx.x * RLD + DH] = s_ML[threadIdx.x][0];
+    part[threadIdx.x * RLD + DH + 1] = s_ML[threadIdx.x][1];
   }
   if (CS == 1) return;
 
+  if (tr) p.trace[5] = clock64();
   // ---- merge the ranks through distributed shared memory; rank q finalises columns [q*DH/CS, (q+1)*DH/CS) ----
   cluster.sync();
+  if (tr) p.trace[6] = clock64();
   {
-    const int cols_per = (DH + CS - 1) / CS;
-    const int c_lo = rank * cols_per, c_hi = min(DH, c_lo + cols_per);
-    const int ncol = max(0, c_hi - c_lo);
-    for (int idx = threadIdx.x; idx < group * ncol; idx += NT) {
-      const int r = idx / ncol, col = c_lo + idx % ncol;
-      float mv[8], lv[8], av[8];
+    __shared__ float s_rw[16][8];  // weight (incl. 1 / row sum) of rank q's partial for row r
+    if (threadIdx.x < group) {
+      const int r = threadIdx.x;
+      float mv[8], lv[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {  // independent remote loads, issued back to back
         if (q < CS) {
           const float* rp = cluster.map_shared_rank(part, q);
           mv[q] = rp[r * RLD + DH];
           lv[q] = rp[r * RLD + DH + 1];
-          av[q] = rp[r * RLD + col];
         }
       }
       float M = -INFINITY;
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (q < CS) M = fmaxf(M, mv[q]);
-      float acc = 0.f, Lsum = 0.f;
+      float Lsum = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q < CS) {
-          const float wgt = exp2f(mv[q] - M);  // empty ranks carry m = -inf, l = 0
-          acc += av[q] * wgt;
-          Lsum += lv[q] * wgt;
-        }
-      }
-      p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc / Lsum);
+      for (int q = 0; q < 8; ++q)
+        if (q < CS) Lsum += lv[q] * exp2f(mv[q] - M);  // empty ranks carry m = -inf, l = 0
+      const float inv = 1.f / Lsum;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < CS) s_rw[r][q] = exp2f(mv[q] - M) * inv;
+    }
+    __syncthreads();
+    const int cols_per = (DH + CS - 1) / CS;
+    const int c_lo = rank * cols_per, c_hi = min(DH, c_lo + cols_per);
+    const int ncol = max(0, c_hi - c_lo);
+    for (int idx = threadIdx.x; idx < group * ncol; idx += NT) {
+      const int r = idx / ncol, col = c_lo + idx % ncol;
+      float av[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < CS) av[q] = cluster.map_shared_rank(part, q)[r * RLD + col];
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < CS) acc += av[q] * s_rw[r][q];
+      p.out[(hq0 + r) * DH + col] = __float2bfloat16(acc);
     }
   }
   cluster.sync();  // shared memory must stay alive until every rank has read it
+  if (tr) p.trace[7] = clock64();
 }
 
 template <int DH>
-static int launch_decode_fused(const AttnDecodeFusedParams& p, int cluster_size, cudaStream_t st) {
+static int launch_decode_fused(const AttnDecodeFusedParams& p, int num_pages, int cluster_size, cudaStream_t st) {
   using C = AttnCfg<DH>;
-  constexpr int smem = (16 + 3 * 2 * 64) * C::LDS * 2;
+  constexpr int smem = 3 * 2 * (DH / 64) * 64 * 128 + 16 * C::LDS * 2;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_decode_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -755,6 +815,12 @@ static int launch_decode_fused(const AttnDecodeFusedParams& p, int cluster_size,
     }
     configured = true;
   }
+  // the page pools viewed as 2D [num_pages * 64 rows, Hkv * dh columns]; one box = 64 rows x 64 columns (128 B)
+  CUtensorMap tmK, tmV;
+  int rc;
+  const long long cols = static_cast<long long>(p.Hkv) * DH;
+  if ((rc = make_tmap_2d(&tmK, p.k_pages, static_cast<long long>(num_pages) * 64, cols, cols, 64)) != PG_OK) return rc;
+  if ((rc = make_tmap_2d(&tmV, p.v_pages, static_cast<long long>(num_pages) * 64, cols, cols, 64)) != PG_OK) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(p.B * p.Hkv * cluster_size));
   cfg.blockDim = dim3(256);
@@ -770,7 +836,7 @@ static int launch_decode_fused(const AttnDecodeFusedParams& p, int cluster_size,
   cfg.attrs = attr;
   cfg.numAttrs = pg_pdl_enabled() ? 2 : 1;
   pg_count_launch(1);
-  return cudaLaunchKernelEx(&cfg, attn_decode_fused_kernel<DH>, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+  return cudaLaunchKernelEx(&cfg, attn_decode_fused_kernel<DH>, tmK, tmV, p) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 template <int DH, int NWARPS>
@@ -862,16 +928,24 @@ extern "C" int pg_attention_decode(const void* q, const void* k_pages, const voi
   }
 }
 
+static long long* g_attn_trace = nullptr;
+static int g_attn_trace_idx = 0;
+extern "C" int pg_debug_set_attn_trace(long long* p) { g_attn_trace = p; g_attn_trace_idx = 0; return 0; }
+
 extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq,
                                          void* k_pages, void* v_pages, const int* page_table, void* out, int B, int Hq,
-                                         int Hkv, int dh, int page_size, int max_pages, float scale, void* stream) {
-  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || max_pages <= 0) return PG_ERR_ARG;
+                                         int Hkv, int dh, int page_size, int num_pages, int max_pages, float scale,
+                                         void* stream) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 16 || page_size != 64 || max_pages <= 0 || num_pages <= 0)
+    return PG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(k_pages) & 15) || (reinterpret_cast<uintptr_t>(v_pages) & 15)) return PG_ERR_ARG;
   AttnDecodeFusedParams p;
   p.qkv = qkv; p.pos = pos; p.kv_len = kv_len; p.inv_freq = inv_freq;
   p.k_pages = static_cast<bf16*>(k_pages); p.v_pages = static_cast<bf16*>(v_pages);
   p.page_table = page_table; p.out = static_cast<bf16*>(out);
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages;
   p.sl2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace ? g_attn_trace + 8 * (g_attn_trace_idx++ % 64) : nullptr;
   // cluster size: as many CTAs as fit in ONE wave (the 3-deep page ring allows one CTA per SM), at most one page per
   // rank, at most 8 (portable cluster limit)
   int cs = 148 / (B * Hkv);
@@ -879,8 +953,8 @@ extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const
   cs = cs >= 8 ? 8 : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {
-    case 64: return launch_decode_fused<64>(p, cs, st);
-    case 256: return launch_decode_fused<256>(p, cs, st);
+    case 64: return launch_decode_fused<64>(p, num_pages, cs, st);
+    case 256: return launch_decode_fused<256>(p, num_pages, cs, st);
     default: return PG_ERR_ARG;
   }
 }

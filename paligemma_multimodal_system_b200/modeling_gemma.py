@@ -356,7 +356,7 @@ class GemmaForCausalLM(nn.Module):
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
-                max_pages, scale, st), "pg_attention_decode_fused")
+                kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
             _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_o)
             _lib.rmsnorm(h, lw["ln2"], hn)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)

@@ -57,7 +57,7 @@ inv_freq=(1.0/(10000.0**(torch.arange(0,dh,2,dtype=torch.int64).float()/dh))).to
 qkvf=torch.randn(B, W, device=dev)*0.5
 attout=torch.empty(B, Hq*dh, device=dev, dtype=torch.bfloat16)
 def attn(i):
-    _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), attout.data_ptr(), B, Hq, Hkv, dh, PAGE, max_pages, 1.0/16, _lib.stream()), "attn")
+    _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), attout.data_ptr(), B, Hq, Hkv, dh, PAGE, B*max_pages, max_pages, 1.0/16, _lib.stream()), "attn")
 for pdl in (1,):
     L.pg_set_pdl(pdl)
     print(f"==== PDL={pdl}  B={B}")

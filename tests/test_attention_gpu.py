@@ -120,7 +120,7 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
         k_pages.copy_(k_before); v_pages.copy_(v_before)
         rc = _lib.lib().pg_attention_decode_fused(qkv.data_ptr(), pos.data_ptr(), kv_len.data_ptr(), inv_freq.data_ptr(),
                                                   k_pages.data_ptr(), v_pages.data_ptr(), table.data_ptr(), out.data_ptr(),
-                                                  B, Hq, 1, dh, page, max_pages, scale, _lib.stream())
+                                                  B, Hq, 1, dh, page, num_pages, max_pages, scale, _lib.stream())
         _lib.check(rc, "fused decode attn")
         torch.cuda.synchronize()
     half = dh // 2
