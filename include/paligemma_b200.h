@@ -40,6 +40,8 @@ long long pg_launch_count(void);
 int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
+int pg_debug_set_decode_gemm_trace(long long* device_buffer); /* pg_gemm_decode: 8 stamps per launch */
+int pg_debug_decode_gemm_max_clusters(int cluster_k); /* cudaOccupancyMaxActiveClusters of the 64-token decode GEMM */
 int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_decode_fused (8 stamps per launch) */
 
 /*
@@ -52,6 +54,36 @@ int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_
 int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
                  const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
                  int act_gelu, float scale, int swap, int split_k, void* stream);
+
+/* Same, with the RMSNorm factor of the PRODUCER of x applied in the epilogue (swap kernels only): acc[t,f] is multiplied
+ * by rsqrt(ss_in[t] / norm_dim + eps) before bias / activation / GEGLU.  x then holds bf16(h * (1 + w)) and ss_in[t] the
+ * sum of squares of the fp32 h row (GemmaRMSNorm, modeling_gemma.py:172-181, folded into the consumer GEMM). */
+int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                         const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
+                         int act_gelu, float scale, int swap, int split_k, const float* ss_in, int norm_dim, float eps,
+                         void* stream);
+
+/*
+ * Decode-step GEMM (tokens <= 128) with the split-K reduction done inside a thread-block cluster through distributed
+ * shared memory (no global atomics): cluster_k in {1,2,4,8,16} CTAs share one 128-row output tile.  Replaces q/k/v_proj,
+ * o_proj and down_proj at q_len == 1 (modeling_gemma.py:274-278,356,210-218) and the GemmaRMSNorm that follows the
+ * residual add (modeling_gemma.py:172-181,393-417).
+ *   PG_DEC_F32:        out[t,f] = acc * rsqrt(ss_in[t]/norm_dim + eps) + bias[f]     (ss_in, bias optional)
+ *   PG_DEC_RESID_NORM: out[t,f] += acc  (fp32 residual stream, in place);  hb[t,f] = bf16(out[t,f] * (1 + norm_w[f]));
+ *                      ss_out[t] += sum_f out[t,f]^2  (ss_out must be zero before the launch)
+ */
+#define PG_DEC_F32 0
+#define PG_DEC_RESID_NORM 1
+int pg_gemm_decode(const void* x, long long ldx, const void* w, long long ldw, int tokens, int features, int K, int mode,
+                   int cluster_k, float* out, long long ldo, const float* bias, const float* ss_in, int norm_dim,
+                   float eps, void* hb, long long ldh, const float* norm_w, float* ss_out, void* stream);
+
+/* Head of a decode step: optionally gathers the token embeddings (same rules as pg_embed_tokens; tokens == NULL keeps the
+ * fp32 rows already in h), then hb[b,:] = bf16(h[b,:] * (1 + norm_w)), ss[b] = sum h[b,:]^2 and zero-fills
+ * zero_buf[0 .. zero_count) (the per-layer sum-of-squares accumulators of the step). */
+int pg_decode_prologue(const int* tokens, const void* embed, const float* img, float* h, void* hb, float* ss,
+                       const float* norm_w, float* zero_buf, long long zero_count, int B, int D, int N, float text_scale,
+                       float img_scale, long long pad_token, long long image_token, void* stream);
 
 /* Packs gate_proj / up_proj [F,K] bf16 into the [64 gate | 64 up] row-interleaved [2F,K] layout PG_EPI_GEGLU expects.
  * (modeling_gemma.py:205-206 weights; F % 64 == 0) */
@@ -69,6 +101,11 @@ int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_
  * prefetch (cp.async.bulk.prefetch.L2) of `prefetch_bytes` at `prefetch_ptr` (upcoming weights), spread over the CTAs. */
 int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
                long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream);
+
+/* Warms L2 with `bytes` of immutable data at `ptr` (128 B aligned; upcoming weights).  Plain launch (no programmatic
+ * dependency): meant for a side stream that runs beside the latency-bound attention half of a decode layer.
+ * mode 0 = prefetch.global.L2, 1 = cp.async.bulk.prefetch.L2, 2 = ld.global.cg + discard; `ctas` blocks of 256 threads. */
+int pg_prefetch_l2(const void* ptr, long long bytes, int mode, int ctas, void* stream);
 
 /* SiglipVisionEmbeddings im2col (modeling_siglip.py:258-263,285-297): pixel fp32 [B,C,H,W] -> patches bf16
  * [B*(H/P)*(W/P), Kpad], column order (c, py, px) = Conv2d weight order, zero padded to Kpad. */

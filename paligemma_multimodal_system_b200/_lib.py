@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpaligemma_b200.so")
+LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(_HERE, "libpaligemma_b200.so")  # PG_LIB_PATH: A/B builds (profiling)
 
 EPI_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_GEGLU = 0, 1, 2, 3
 
@@ -26,11 +26,19 @@ SIGNATURES = {
     "pg_set_pdl": [i32],
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_attn_trace": [p],
+    "pg_debug_set_decode_gemm_cta_trace": [p],
+    "pg_debug_decode_gemm_blocks_per_sm": [i32],
+    "pg_debug_decode_gemm_max_clusters": [i32],
+    "pg_debug_set_decode_gemm_trace": [p],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
+    "pg_gemm_bf16_colnorm": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p, i32, f32, p],
+    "pg_gemm_decode": [p, i64, p, i64, i32, i32, i32, i32, i32, p, i64, p, p, i32, f32, p, i64, p, p, p],
+    "pg_decode_prologue": [p, p, p, p, p, p, p, p, i64, i32, i32, i32, f32, f32, i64, i64, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
     "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],
     "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p, i64, p],
+    "pg_prefetch_l2": [p, i64, i32, i32, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_add_pos_emb": [p, p, i32, i32, i32, p],
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
@@ -124,6 +132,35 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
     check(lib().pg_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
                              ptr(resid), 0 if resid is None else resid.stride(0), T, F, K, mode, int(act_gelu), float(scale),
                              swap, split_k, stream()), "pg_gemm_bf16")
+    return out
+
+
+DEC_F32, DEC_RESID_NORM = 0, 1
+
+
+def gemm_colnorm(x, w, out, *, mode, ss_in, norm_dim, eps=1e-6, bias=None, swap=1):
+    """Swap-AB (decode) GEMM whose epilogue applies the producer's RMSNorm factor rsqrt(ss_in[t]/norm_dim + eps) per token."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    assert ss_in.dtype == torch.float32 and ss_in.numel() >= x.shape[0]
+    T, K = x.shape
+    check(lib().pg_gemm_bf16_colnorm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
+                                     0, 0, T, w.shape[0], K, mode, 0, 1.0, swap, 1, ss_in.data_ptr(), int(norm_dim), float(eps),
+                                     stream()), "pg_gemm_bf16_colnorm")
+    return out
+
+
+def gemm_decode(x, w, out, *, mode, cluster_k, bias=None, ss_in=None, norm_dim=0, eps=1e-6, hb=None, norm_w=None, ss_out=None):
+    """Cluster split-K decode GEMM (csrc/gemm_decode.cu): DEC_F32 writes out fp32; DEC_RESID_NORM adds into the fp32 residual
+    stream `out` and emits hb = bf16(out * (1 + norm_w)) and ss_out += sum(out^2) for the next fused RMSNorm."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    T, K = x.shape
+    assert w.shape[1] == K
+    if mode == DEC_RESID_NORM:
+        assert hb.dtype == torch.bfloat16 and norm_w.dtype == torch.float32 and ss_out.dtype == torch.float32
+    check(lib().pg_gemm_decode(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), T, w.shape[0], K, mode, int(cluster_k),
+                               out.data_ptr(), out.stride(0), ptr(bias), ptr(ss_in), int(norm_dim), float(eps), ptr(hb),
+                               0 if hb is None else hb.stride(0), ptr(norm_w), ptr(ss_out), stream()), "pg_gemm_decode")
     return out
 
 

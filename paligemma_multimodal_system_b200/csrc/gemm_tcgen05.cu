@@ -13,6 +13,8 @@
 //   SWAP = false (prefill, many tokens):  UMMA M = 128 tokens,   N = BN features
 //   SWAP = true  (decode, tokens <= 128): UMMA M = 128 features, N = BN tokens  (weight streaming, HBM bound),
 //                                         optional split-K with fp32 red.global.add into the output
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"
@@ -27,7 +29,7 @@ constexpr int ACC_STAGES = 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
 __host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
-__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 : 0; }
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 0; }  // exchange area + per-token factors
 // decode (SWAP, BN <= 64): two CTAs per SM (115712 B each) so that, with programmatic dependent launch, the next
 // kernel's CTAs become resident and prefetch their weights while this kernel drains; otherwise one CTA with <= 200 KB
 __host__ __device__ constexpr bool two_per_sm(int BN, bool swap) { return swap && BN <= 64; }
@@ -54,6 +56,9 @@ struct GemmArgs {
   const float* bias;
   const float* resid;
   long long ldr;
+  // optional per-token RMSNorm factor of the producer of X (SWAP kernels): acc[f, t] *= rsqrt(ss_in[t] * inv_norm_dim + eps)
+  const float* ss_in;
+  float inv_norm_dim, eps;
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
 };
 
@@ -74,6 +79,54 @@ PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_k
 }
 
 PG_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+
+// Epilogue of one swap-AB tile for the non-GEGLU modes: thread = weight row (feature) fr, columns = tokens.  The mode is a
+// template parameter and the output pointer is advanced by a precomputed byte stride, so that one element costs a
+// handful of instructions (the epilogue of the decode GEMMs is issue-bound: 4 warps x 64 elements per tile).
+// rs_tab: optional per-token factors in shared memory (RMSNorm of the producer), already multiplied by args.scale.
+template <int BN, int MODE>
+PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, int j_base, bool first_split,
+                                  const float* __restrict__ rs_tab) {
+  const bool f_ok = fr < args.features;
+  const int nvalid = min(BN, args.tokens - j_base);
+  const float scale = args.scale;
+  const float bias_s = (args.bias != nullptr && f_ok && first_split) ? __ldg(args.bias + fr) * scale : 0.f;
+  constexpr int ESZ = MODE == PG_EPI_BF16 ? 2 : 4;
+  char* dst = reinterpret_cast<char*>(args.out) + (static_cast<long long>(j_base) * args.ldo + fr) * ESZ;
+  const long long step = args.ldo * ESZ;
+  const char* res = (MODE == PG_EPI_F32 && args.resid != nullptr)
+                        ? reinterpret_cast<const char*>(args.resid + static_cast<long long>(j_base) * args.ldr + fr) : nullptr;
+  const long long rstep = args.ldr * 4;
+  const bool gelu = MODE == PG_EPI_BF16 && args.act_gelu != 0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (c0 >= nvalid) break;  // warp-uniform
+    uint32_t r[16];
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+    if (!f_ok) continue;
+    const int n = min(16, nvalid - c0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float m = rs_tab != nullptr ? rs_tab[c0 + i] : scale;
+        float x = fmaf(__uint_as_float(r[i]), m, bias_s);
+        if (MODE == PG_EPI_BF16) {
+          if (gelu) x = gelu_tanh(x);
+          *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(x);
+        } else if (MODE == PG_EPI_F32) {
+          if (res != nullptr) x += *reinterpret_cast<const float*>(res);
+          *reinterpret_cast<float*>(dst) = x;
+        } else {
+          atomicAdd(reinterpret_cast<float*>(dst), x);
+        }
+      }
+      dst += step;
+      if (MODE == PG_EPI_F32) res += rstep;
+    }
+  }
+}
 
 template <int BN, bool SWAP>
 __global__ void __launch_bounds__(NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
@@ -312,69 +365,94 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
         const int fr = t.m_blk * BM + rl;
         const int j_base = t.n_blk * BN;
-        if (mode == PG_EPI_GEGLU) {
-          // packed rows: [64 gate | 64 up] per 128-row tile; out feature = m_blk*64 + rl%64
-          if (q >= 2) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-              if (j_base + c0 >= args.tokens) break;
-              uint32_t r[16];
-              tmem_ld16(taddr + c0, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) xch[(rl - 64) * BN + ((c0 + i) ^ ((rl - 64) & (BN - 1) & 31))] = __uint_as_float(r[i]);
-            }
+        // per-token RMSNorm factor of the producer (x args.scale), staged once per tile in shared memory
+        const float* rs_tab = nullptr;
+        if (args.ss_in != nullptr) {
+          float* tab = xch + 64 * BN;  // BN floats after the exchange area
+          const int et = (warp - 2) * 32 + lane;
+          named_bar_sync(1, 128);      // previous tile's readers are done
+          if (et < BN) {
+            const int j = j_base + et;
+            tab[et] = j < args.tokens ? rsqrtf(__ldg(args.ss_in + j) * args.inv_norm_dim + args.eps) * args.scale : 0.f;
           }
           named_bar_sync(1, 128);
-          if (q < 2) {
-            const int fo = t.m_blk * 64 + rl;
-            const bool f_ok = fo < args.features / 2;
+          rs_tab = tab;
+        }
+        if (mode == PG_EPI_GEGLU) {
+          // Packed rows: [64 gate | 64 up] per 128-row tile, so warps q<2 hold the gate rows and warps q>=2 the matching
+          // up rows of the same 64 output features.  The two halves of the token columns are exchanged through shared
+          // memory (gate warps finish columns [0, BN/2), up warps finish [BN/2, BN)), the bf16 results are transposed
+          // through shared memory and leave as 16-byte vectors (one 128-byte row of 64 features per token).
+          constexpr int HB = BN / 2;
+          constexpr int LDN = HB >= 16 ? 16 : 8;
+          const bool is_gate = q < 2;
+          const int r = rl & 63;
+          float* xsend = xch + (is_gate ? 64 * HB : 0);  // gate warps fill xch_g (second half), up warps xch_u
+          float* xrecv = xch + (is_gate ? 0 : 64 * HB);
+          const int send0 = is_gate ? HB : 0, keep0 = is_gate ? 0 : HB;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-              if (j_base + c0 >= args.tokens) break;
-              uint32_t r[16];
-              tmem_ld16(taddr + c0, r);
-              tmem_ld_wait();
+          for (int c0 = 0; c0 < HB; c0 += LDN) {
+            if (j_base + send0 + c0 >= args.tokens) break;
+            uint32_t v[16];
+            if constexpr (LDN == 16) tmem_ld16(taddr + send0 + c0, v); else tmem_ld8(taddr + send0 + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int j = j_base + c0 + i;
-                if (f_ok && j < args.tokens) {
-                  float val = gelu_tanh(__uint_as_float(r[i])) * xch[rl * BN + ((c0 + i) ^ (rl & (BN - 1) & 31))];
-                  out_bf[static_cast<long long>(j) * args.ldo + fo] = __float2bfloat16(val);
+            for (int i = 0; i < LDN; ++i) xsend[r * HB + ((c0 + i) ^ (r & (HB - 1) & 31))] = __uint_as_float(v[i]);
+          }
+          named_bar_sync(1, 128);
+          uint32_t pk[HB / 2];
+#pragma unroll
+          for (int c0 = 0; c0 < HB; c0 += LDN) {
+            uint32_t v[16];
+            if (j_base + keep0 + c0 < args.tokens) {
+              if constexpr (LDN == 16) tmem_ld16(taddr + keep0 + c0, v); else tmem_ld8(taddr + keep0 + c0, v);
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int i = 0; i < LDN; i += 2) {
+              float res[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                float mine = __uint_as_float(v[i + e]);
+                float other = xrecv[r * HB + ((c0 + i + e) ^ (r & (HB - 1) & 31))];
+                if (rs_tab != nullptr) {
+                  const float rs = rs_tab[keep0 + c0 + i + e];
+                  mine *= rs;
+                  other *= rs;
                 }
+                res[e] = is_gate ? gelu_tanh(mine) * other : gelu_tanh(other) * mine;
+              }
+              pk[(c0 + i) / 2] = pack_bf16(res[0], res[1]);
+            }
+          }
+          named_bar_sync(1, 128);  // every exchange value has been consumed: the area is reused for the transposed tile
+          __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(xch);  // [BN tokens][64 features]
+#pragma unroll
+          for (int c = 0; c < HB; c += 2) {
+            const __nv_bfloat162 two = *reinterpret_cast<const __nv_bfloat162*>(&pk[c / 2]);
+            out_s[(keep0 + c) * 64 + r] = two.x;
+            out_s[(keep0 + c + 1) * 64 + r] = two.y;
+          }
+          named_bar_sync(1, 128);
+          {
+            const int et = (warp - 2) * 32 + lane;  // 0..127
+            const int f0 = t.m_blk * 64;
+            if (f0 < args.features / 2) {
+#pragma unroll 1
+              for (int pc = et; pc < BN * 8; pc += 128) {
+                const int j = j_base + (pc >> 3), part = pc & 7;
+                if (j < args.tokens)
+                  *reinterpret_cast<uint4*>(out_bf + static_cast<long long>(j) * args.ldo + f0 + part * 8) =
+                      *reinterpret_cast<const uint4*>(out_s + (pc >> 3) * 64 + part * 8);
               }
             }
           }
           named_bar_sync(1, 128);
         } else {
-          const bool f_ok = fr < args.features;
-          const float bias = (args.bias != nullptr && f_ok && first_split) ? __ldg(args.bias + fr) : 0.f;
           // (measured: 16-byte REDG.F32x4 after a lane-quad transpose is ~2x SLOWER here than 4-byte coalesced reds)
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 16) {
-            if (j_base + c0 >= args.tokens) break;  // warp-uniform
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-            if (!f_ok) continue;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int j = j_base + c0 + i;
-              if (j < args.tokens) {
-                float x = (__uint_as_float(r[i]) + bias) * args.scale;
-                const long long o = static_cast<long long>(j) * args.ldo + fr;
-                if (mode == PG_EPI_BF16) {
-                  if (args.act_gelu) x = gelu_tanh(x);
-                  out_bf[o] = __float2bfloat16(x);
-                } else if (mode == PG_EPI_F32) {
-                  if (args.resid) x += args.resid[static_cast<long long>(j) * args.ldr + fr];
-                  out_f[o] = x;
-                } else {
-                  atomicAdd(out_f + o, x);
-                }
-              }
-            }
-          }
+          if (mode == PG_EPI_ATOMIC_F32) swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, fr, j_base, first_split, rs_tab);
+          else if (mode == PG_EPI_F32) swap_tile_epilogue<BN, PG_EPI_F32>(args, taddr, fr, j_base, first_split, rs_tab);
+          else swap_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, fr, j_base, first_split, rs_tab);
         }
       }
       tc_fence_before();
@@ -421,6 +499,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
       cudaGetLastError();  // do not leave a sticky error behind
       return PG_ERR_CUDA;
     }
+    if (getenv("PG_CARVEOUT") != nullptr)
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("PG_CARVEOUT")));
     configured = true;
   }
   const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
@@ -436,6 +516,14 @@ using namespace pg;
 extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
                             const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
                             int mode, int act_gelu, float scale, int swap, int split_k, void* stream) {
+  return pg_gemm_bf16_colnorm(x, ldx, w, ldw, out, ldo, bias, resid, ldr, tokens, features, K, mode, act_gelu, scale, swap,
+                              split_k, nullptr, 0, 0.f, stream);
+}
+
+extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                                    const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
+                                    int mode, int act_gelu, float scale, int swap, int split_k, const float* ss_in,
+                                    int norm_dim, float eps, void* stream) {
   if (tokens <= 0 || features <= 0 || K <= 0) return PG_ERR_ARG;
   if ((K % 8) != 0 || (ldx % 8) != 0 || (ldw % 8) != 0) return PG_ERR_ARG;  // TMA: 16 B pitch granularity
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return PG_ERR_ARG;
@@ -443,6 +531,7 @@ extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long lo
   if (mode == PG_EPI_GEGLU && (features % 128) != 0) return PG_ERR_ARG;
   if (swap < 0) swap = tokens <= 128 ? 1 : 0;
   if (swap && tokens > 128) return PG_ERR_ARG;
+  if (ss_in != nullptr && (!swap || norm_dim <= 0)) return PG_ERR_ARG;  // the per-token factor is a SWAP-kernel epilogue
   const int total_kb = (K + BK - 1) / BK;
   if (split_k <= 0) split_k = 1;
   if (mode != PG_EPI_ATOMIC_F32) split_k = 1;
@@ -455,7 +544,9 @@ extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long lo
 
   GemmArgs a;
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
-  a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr; a.trace = g_gemm_trace ? g_gemm_trace + 8 * (g_gemm_trace_idx++ % 64) : nullptr;
+  a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
+  a.ss_in = ss_in; a.inv_norm_dim = norm_dim > 0 ? 1.0f / static_cast<float>(norm_dim) : 0.f; a.eps = eps;
+  a.trace = g_gemm_trace ? g_gemm_trace + 8 * (g_gemm_trace_idx++ % 64) : nullptr;
 
   CUtensorMap ta, tb;
   int rc;

@@ -190,6 +190,17 @@ class GemmaModel(_ParamsOnly):
         self.norm = GemmaRMSNorm(config.hidden_size, **fk)
 
 
+def _pick_cluster(tiles_m, total_kb, env=None, sms=148):
+    """Cluster size (split-K ranks per output tile) for the decode GEMMs: enough CTAs to keep every SM streaming weights,
+    a power of two <= 16, at least two k-blocks per rank."""
+    if env and os.environ.get(env):
+        return int(os.environ[env])
+    s = 1
+    while s < 16 and tiles_m * s < sms - 20 and total_kb // (2 * s) >= 2:
+        s *= 2
+    return s
+
+
 def _pick_split(tiles_mn, total_kb, sms=148):
     """split-K so that roughly one wave of CTAs streams the weight matrix (decode GEMMs with few output tiles)."""
     if tiles_mn >= sms:
@@ -329,40 +340,58 @@ class GemmaForCausalLM(nn.Module):
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
         return dict(
             h=self._buf("d_h", (B, D), torch.float32), hn=self._buf("d_hn", (B, D), torch.bfloat16),
+            hb=self._buf("d_hb", (B, D), torch.bfloat16), ss=self._buf("d_ss", (2 * c.num_hidden_layers + 1, B), torch.float32),
             qkv=self._buf("d_qkv", (B, (Hq + 2 * Hkv) * dh), torch.float32),
             att=self._buf("d_att", (B, Hq * dh), torch.bfloat16), mid=self._buf("d_mid", (B, F), torch.bfloat16),
             logits=self._buf("d_logits", (B, V), torch.float32))
 
     @torch.no_grad()
+    def decode_prologue(self, bufs, B, tokens_i32=None, img=None, img_scale=1.0, pad_token=-1, image_token=-1):
+        """Token embedding (or the fp32 rows already in bufs['h'] when tokens_i32 is None) -> operands of the first fused
+        RMSNorm (hb = bf16(h * (1 + ln1_0)), ss[0] = sum h^2); zeroes the remaining sum-of-squares accumulators."""
+        c = self.text_config
+        pk = self._packed or self.pack()
+        D = c.hidden_size
+        ss = bufs["ss"]
+        _lib.check(_lib.lib().pg_decode_prologue(
+            _lib.ptr(tokens_i32), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), bufs["hb"].data_ptr(),
+            ss[0].data_ptr(), pk["layers"][0]["ln1"].data_ptr(), ss[1].data_ptr(), ss.numel() - ss.shape[1], B, D,
+            0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token if pad_token is not None else -1, image_token,
+            _lib.stream()), "pg_decode_prologue")
+
+    @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B):
-        """One decode step over all layers; reads bufs['h'] (fp32 embeddings), leaves fp32 logits in bufs['logits'].
-        Every launch reads its sizes from device counters, so the sequence can be captured in a CUDA graph."""
+        """One decode step over all layers.  Expects decode_prologue() to have filled bufs['h'], bufs['hb'], bufs['ss'][0];
+        leaves fp32 logits in bufs['logits'].  Five launches per layer: QKV GEMM (cluster split-K, input RMSNorm applied as
+        a per-token factor), fused RoPE + KV append + attention, O GEMM (+residual, emits the post-attention norm operands),
+        gate||up GEGLU GEMM, down GEMM (+residual, emits the next layer's norm operands).  Every launch reads its sizes from
+        device counters, so the sequence can be captured in a CUDA graph."""
         c = self.text_config
         pk = self._packed or self.pack()
         L, st = _lib.lib(), _lib.stream()
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        h, hn, qkv, att, mid = bufs["h"], bufs["hn"], bufs["qkv"], bufs["att"], bufs["mid"]
+        h, hb, ss, qkv, att, mid = bufs["h"], bufs["hb"], bufs["ss"], bufs["qkv"], bufs["att"], bufs["mid"]
         pos, kvl = kv_cache.counters[0], kv_cache.counters[2]
         max_pages = kv_cache.page_table.shape[1]
         scale = 1.0 / math.sqrt(dh)
         W = (Hq + 2 * Hkv) * dh
-        sp_qkv = _pick_split((W + 127) // 128, D // 64)
-        sp_o = _pick_split((D + 127) // 128, D // 64)
-        sp_down = _pick_split((D + 127) // 128, F // 64)
+        eps = 1e-6
+        s_qkv = _pick_cluster((W + 127) // 128, D // 64, "PG_S_QKV")
+        s_o = _pick_cluster((D + 127) // 128, D // 64, "PG_S_O")
+        s_down = _pick_cluster((D + 127) // 128, F // 64, "PG_S_DOWN")
+        n_layers = len(pk["layers"])
         for li, lw in enumerate(pk["layers"]):
-            _lib.rmsnorm(h, lw["ln1"], hn, zero_buf=qkv)
-            _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
+            _lib.gemm_decode(hb, lw["qkv_w"], qkv, mode=_lib.DEC_F32, cluster_k=s_qkv, ss_in=ss[2 * li], norm_dim=D, eps=eps)
             # RoPE + KV append + split-KV attention + combine: one launch
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
                 kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
-            _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_o)
-            _lib.rmsnorm(h, lw["ln2"], hn)
-            _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
-            _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
-        _lib.rmsnorm(h, pk["norm_w"], hn)
-        _lib.gemm(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], swap=1)
+            _lib.gemm_decode(att, lw["o_w"], h, mode=_lib.DEC_RESID_NORM, cluster_k=s_o, hb=hb, norm_w=lw["ln2"], ss_out=ss[2 * li + 1])
+            _lib.gemm_colnorm(hb, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, ss_in=ss[2 * li + 1], norm_dim=D, eps=eps)
+            next_w = pk["layers"][li + 1]["ln1"] if li + 1 < n_layers else pk["norm_w"]
+            _lib.gemm_decode(mid, lw["down_w"], h, mode=_lib.DEC_RESID_NORM, cluster_k=s_down, hb=hb, norm_w=next_w, ss_out=ss[2 * li + 2])
+        _lib.gemm_colnorm(hb, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], ss_in=ss[2 * n_layers], norm_dim=D, eps=eps)
         return bufs["logits"]
 
     # -- one-kernel decode step ------------------------------------------------------------------------------------------
@@ -382,9 +411,7 @@ class GemmaForCausalLM(nn.Module):
         L = _lib.lib()
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
         if not self.megakernel_ok(B):
-            _lib.check(L.pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
-                                         0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
-                                         _lib.stream()), "pg_embed_tokens")
+            self.decode_prologue(bufs, B, tokens_i32, img, img_scale, pad_token, image_token)
             return self.decode_layers(bufs, kv_cache, B)
         key = (B, bufs["hn"].data_ptr(), bufs["att"].data_ptr(), bufs["mid"].data_ptr())
         maps = self._step_maps.get(key)
@@ -442,6 +469,7 @@ class GemmaForCausalLM(nn.Module):
             kv_cache.counters[2].fill_(n + 1)
             bufs = self.decode_buffers(B)
             bufs["h"].copy_(h)
+            self.decode_prologue(bufs, B)
             logits = self.decode_layers(bufs, kv_cache, B).clone().view(B, 1, -1)
             kv_cache._set_len(n + 1, self.text_config.num_hidden_layers)
         else:

@@ -89,3 +89,26 @@ for pdl in (1,):
         _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
     graph_time("layer (no attention)", layer, (W * D + D * D + 3 * F * D) * 2)
     timeit("layer (no attention) eager", layer, (W * D + D * D + 3 * F * D) * 2)
+
+    # ---- L2 prefetch experiments: pull part of the MLP weights into L2 while the latency-bound attention half runs ----
+    def make_layer(pf_gu_mb, pf_down_mb, pf_next_attn):
+        def f(i):
+            gu = gu_w[i]; dn = down_w[i]
+            _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv, prefetch=gu if pf_gu_mb else None, prefetch_bytes=min(pf_gu_mb << 20, gu.numel() * 2))
+            _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
+            attn(i)
+            _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=9)
+            if pf_down_mb:
+                _lib.rmsnorm(h, ln_w, hn_out, prefetch=dn, prefetch_bytes=min(pf_down_mb << 20, dn.numel() * 2))
+            elif pf_next_attn:
+                _lib.rmsnorm(h, ln_w, hn_out, prefetch=qkv_w[(i + 1) % NL])
+            else:
+                _lib.rmsnorm(h, ln_w, hn_out)
+            _lib.gemm(hn_out, gu, midout, mode=_lib.EPI_GEGLU, swap=1)
+            _lib.gemm(midout, dn, h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=18)
+        return f
+    nbytes = (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4
+    for gu_mb in (0, 16, 32, 48, 64, 96, 128):
+        graph_time(f"FULL layer, L2-prefetch gu {gu_mb} MB", make_layer(gu_mb, 0, False), nbytes)
+    graph_time("FULL layer, pf gu 64 MB + next qkv", make_layer(64, 0, True), nbytes)
+    graph_time("FULL layer, pf gu 48 MB + down 32 MB", make_layer(48, 32, False), nbytes)
