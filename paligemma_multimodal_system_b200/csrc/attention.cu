@@ -10,6 +10,7 @@
 // Round-1 implementation: mma.sync m16n8k16 tensor-core tiles (attention is 1.4 % of the 224-px prefill FLOPs); the
 // tcgen05/TMEM version for the 448/896-px configs is the next step for this file.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "paligemma_b200.h"
@@ -928,6 +929,10 @@ extern "C" int pg_attention_decode(const void* q, const void* k_pages, const voi
   }
 }
 
+int pg_attention_decode_v3(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
+                           void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh, int num_pages,
+                           int max_pages, float sl2, int cluster_size, long long* trace, void* stream);  // attention_decode.cu
+
 static long long* g_attn_trace = nullptr;
 static int g_attn_trace_idx = 0;
 extern "C" int pg_debug_set_attn_trace(long long* p) { g_attn_trace = p; g_attn_trace_idx = 0; return 0; }
@@ -945,12 +950,16 @@ extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const
   p.page_table = page_table; p.out = static_cast<bf16*>(out);
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages;
   p.sl2 = scale * 1.4426950408889634f;
-  p.trace = g_attn_trace ? g_attn_trace + 8 * (g_attn_trace_idx++ % 64) : nullptr;
+  p.trace = g_attn_trace ? g_attn_trace + 8 * (g_attn_trace_idx++ % 32) : nullptr;
   // cluster size: as many CTAs as fit in ONE wave (the 3-deep page ring allows one CTA per SM), at most one page per
   // rank, at most 8 (portable cluster limit)
   int cs = 148 / (B * Hkv);
   if (cs > max_pages) cs = max_pages;
   cs = cs >= 8 ? 8 : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
+  static const bool use_v2 = getenv("PG_ATTN_V2") != nullptr;  // A/B switch: the second-generation kernel below
+  if (Hq / Hkv <= 8 && !use_v2)
+    return pg_attention_decode_v3(qkv, pos, kv_len, inv_freq, k_pages, v_pages, page_table, out, B, Hq, Hkv, dh, num_pages,
+                                  max_pages, p.sl2, cs, p.trace, stream);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {
     case 64: return launch_decode_fused<64>(p, num_pages, cs, st);

@@ -361,11 +361,47 @@ class GemmaForCausalLM(nn.Module):
 
     @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B):
-        """One decode step over all layers.  Expects decode_prologue() to have filled bufs['h'], bufs['hb'], bufs['ss'][0];
-        leaves fp32 logits in bufs['logits'].  Five launches per layer: QKV GEMM (cluster split-K, input RMSNorm applied as
-        a per-token factor), fused RoPE + KV append + attention, O GEMM (+residual, emits the post-attention norm operands),
-        gate||up GEGLU GEMM, down GEMM (+residual, emits the next layer's norm operands).  Every launch reads its sizes from
-        device counters, so the sequence can be captured in a CUDA graph."""
+        """One decode step over all layers; reads bufs['h'] (fp32 embeddings), leaves fp32 logits in bufs['logits'].
+        Seven launches per layer: RMSNorm, QKV GEMM, fused RoPE + KV append + attention, O GEMM, RMSNorm, gate||up GEGLU
+        GEMM, down GEMM; the three small-output GEMMs split K over CTAs and red.add their fp32 partials straight into the
+        residual stream / the pre-zeroed qkv buffer.  Every launch reads its sizes from device counters, so the sequence
+        can be captured in a CUDA graph.  (PG_DECODE_CLUSTER=1 selects the variant whose split-K reduction runs inside
+        thread-block clusters and folds the RMSNorms into the GEMM epilogues: measured slower on B200)"""
+        if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
+            return self.decode_layers_cluster(bufs, kv_cache, B)
+        c = self.text_config
+        pk = self._packed or self.pack()
+        L, st = _lib.lib(), _lib.stream()
+        D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
+        h, hn, qkv, att, mid = bufs["h"], bufs["hn"], bufs["qkv"], bufs["att"], bufs["mid"]
+        pos, kvl = kv_cache.counters[0], kv_cache.counters[2]
+        max_pages = kv_cache.page_table.shape[1]
+        scale = 1.0 / math.sqrt(dh)
+        W = (Hq + 2 * Hkv) * dh
+        sp_qkv = _pick_split((W + 127) // 128, D // 64)
+        sp_o = _pick_split((D + 127) // 128, D // 64)
+        sp_down = _pick_split((D + 127) // 128, F // 64, sms=296)
+        for li, lw in enumerate(pk["layers"]):
+            _lib.rmsnorm(h, lw["ln1"], hn, zero_buf=qkv)
+            _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
+            # RoPE + KV append + split-KV attention + combine: one launch
+            _lib.check(L.pg_attention_decode_fused(
+                qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
+                kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
+                kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
+            _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_o)
+            _lib.rmsnorm(h, lw["ln2"], hn)
+            _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
+            _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
+        _lib.rmsnorm(h, pk["norm_w"], hn)
+        _lib.gemm(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], swap=1)
+        return bufs["logits"]
+
+    @torch.no_grad()
+    def decode_layers_cluster(self, bufs, kv_cache: KVCache, B):
+        """Variant of decode_layers with five launches per layer: QKV GEMM (cluster split-K, input RMSNorm applied as a
+        per-token factor), attention, O GEMM (+residual, emits the post-attention norm operands), gate||up GEGLU GEMM, down
+        GEMM (+residual, emits the next layer's norm operands).  Needs decode_prologue() to have filled hb / ss[0]."""
         c = self.text_config
         pk = self._packed or self.pack()
         L, st = _lib.lib(), _lib.stream()
@@ -382,7 +418,6 @@ class GemmaForCausalLM(nn.Module):
         n_layers = len(pk["layers"])
         for li, lw in enumerate(pk["layers"]):
             _lib.gemm_decode(hb, lw["qkv_w"], qkv, mode=_lib.DEC_F32, cluster_k=s_qkv, ss_in=ss[2 * li], norm_dim=D, eps=eps)
-            # RoPE + KV append + split-KV attention + combine: one launch
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
@@ -411,7 +446,12 @@ class GemmaForCausalLM(nn.Module):
         L = _lib.lib()
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
         if not self.megakernel_ok(B):
-            self.decode_prologue(bufs, B, tokens_i32, img, img_scale, pad_token, image_token)
+            if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
+                self.decode_prologue(bufs, B, tokens_i32, img, img_scale, pad_token, image_token)
+            else:
+                _lib.check(L.pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
+                                             0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
+                                             _lib.stream()), "pg_embed_tokens")
             return self.decode_layers(bufs, kv_cache, B)
         key = (B, bufs["hn"].data_ptr(), bufs["att"].data_ptr(), bufs["mid"].data_ptr())
         maps = self._step_maps.get(key)
@@ -469,7 +509,8 @@ class GemmaForCausalLM(nn.Module):
             kv_cache.counters[2].fill_(n + 1)
             bufs = self.decode_buffers(B)
             bufs["h"].copy_(h)
-            self.decode_prologue(bufs, B)
+            if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
+                self.decode_prologue(bufs, B)
             logits = self.decode_layers(bufs, kv_cache, B).clone().view(B, 1, -1)
             kv_cache._set_len(n + 1, self.text_config.num_hidden_layers)
         else:

@@ -11,7 +11,7 @@ kvl=torch.full((B,), kvlen, device="cuda", dtype=torch.int32); posd=kvl.clone()
 inv_freq=(1.0/(10000.0**(torch.arange(0,dh,2,dtype=torch.int64).float()/dh))).cuda()
 qkvf=torch.randn(B, W, device="cuda")*0.5
 out=torch.empty(B, Hq*dh, device="cuda", dtype=torch.bfloat16)
-tr = torch.zeros(8 * 64, device="cuda", dtype=torch.int64)
+tr = torch.zeros(8 * 64 + 256, device="cuda", dtype=torch.int64)
 def attn(i):
     _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), out.data_ptr(), B, Hq, Hkv, dh, PAGE, B*max_pages, max_pages, 1.0/16, _lib.stream()), "attn")
 for i in range(NL): attn(i)
@@ -25,8 +25,15 @@ with torch.cuda.stream(s):
 torch.cuda.current_stream().wait_stream(s)
 for _ in range(3): g.replay()
 torch.cuda.synchronize()
-t = tr.cpu().numpy().astype("float64").reshape(64, 8)
-names = ["wait-returned", "Q staged", "first page landed", "pages done", "cta-merged", "cluster-sync1", "end"]
+t = tr.cpu().numpy().astype("float64")[:512].reshape(64, 8)
+import os
+names = ["wait-returned", "Q staged", "first page landed", "pages done", "cta-merged", "cluster-sync1", "end"] if os.environ.get("PG_ATTN_V2") else ["wait-returned", "Q staged", "pages landed", "rounds done", "cluster-sync1", "end", "-"]
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+print(f"{e0.elapsed_time(e1) * 1e3 / NL:.2f} us per launch")
 for k in (8, 9):
     d = (t[k, 1:8] - t[k, 0]) / 1.9e3
+    if not os.environ.get("PG_ATTN_V2"):
+        d1 = (t[k + 32, 1:8] - t[k, 0]) / 1.9e3
+        print(f"   rank 1 (entry {(t[k+32,0]-t[k,0])/1.9e3:5.2f}): " + " | ".join(f"{n} {v:5.2f}" for n, v in zip(names, d1)))
     print(f"launch {k}: " + " | ".join(f"{n} {v:5.2f}" for n, v in zip(names, d)) + f" | next entry {(t[k+1,0]-t[k,0])/1.9e3:5.2f}")
