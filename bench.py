@@ -275,7 +275,8 @@ def main():
         step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
         k_ms, k_bytes = time_dominant_kernel(model, B)
         k_gbs = k_bytes / (k_ms * 1e-3) / 1e9
-        graph_kernels = 3 + 9 * cfg["text_config"]["num_hidden_layers"] + 1 + 2  # embed + 9/layer + norm,head + sample,advance
+        # per decode step: embed + 7 per layer (norm, qkv, attention, o, norm, gate||up, down) + final norm + head + sampler + advance
+        graph_kernels = 7 * cfg["text_config"]["num_hidden_layers"] + 5
         line = {
             "metric": "decode_tokens_per_s", "value": decode_tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -287,7 +288,7 @@ def main():
                        "l2_policy": "inputs larger than L2 (5.0 GB of weights streamed per decode step)"},
             "e2e": {"value": K * B * T * world / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "generated tokens / wall incl. H2D, prefill, decode, D2H"},
-            "gpu_launches": int(eager_launches + K * max(T - 2, 0) * graph_kernels),
+            "gpu_launches": int(eager_launches + K * max(T - 1, 0) * graph_kernels),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<64,swap> gate||up decode GEMM", "achieved": k_gbs,
                          "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,

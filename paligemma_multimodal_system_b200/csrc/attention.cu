@@ -16,6 +16,11 @@
 #include "paligemma_b200.h"
 #include "tmap.cuh"
 
+int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
+                            int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off, long long kv_bs,
+                            long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts, long long o_hs,
+                            long long o_head_off, float scale, void* stream);  // attention_prefill_tc.cu
+
 namespace pg {
 
 typedef __nv_bfloat16 bf16;
@@ -889,6 +894,16 @@ extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v,
   if ((q_bs | q_ts | q_hs | q_head_off | kv_bs | kv_ts | kv_head_off) & 7) return PG_ERR_ARG;  // 16 B cp.async granularity
   if ((o_bs | o_ts | o_hs | o_head_off) & 1) return PG_ERR_ARG;
   if (B > 65535 || H > 65535) return PG_ERR_ARG;
+  {
+    // tcgen05 / TMEM kernel (attention_prefill_tc.cu) for every shape its TMA maps can express; the mma.sync kernel below
+    // only serves the rest (PG_ATTN_PREFILL_MMA=1 forces it: A/B profiling)
+    static const bool force_mma = getenv("PG_ATTN_PREFILL_MMA") != nullptr;
+    if (!force_mma) {
+      const int rc = pg_attention_prefill_tc(q, k, v, o, B, H, rows, keys, dh, group, q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts,
+                                             kv_head_off, o_bs, o_ts, o_hs, o_head_off, scale, stream);
+      if (rc <= 0) return rc;
+    }
+  }
   AttnPrefillParams p;
   p.q = static_cast<const bf16*>(q); p.k = static_cast<const bf16*>(k); p.v = static_cast<const bf16*>(v);
   p.o = static_cast<bf16*>(o);

@@ -1,0 +1,405 @@
+// Prefill attention on the 5th-generation tensor cores: non-causal softmax(Q K^T * scale) V, flash style, with both
+// GEMMs issued as tcgen05.mma (accumulators in TMEM) and all operands staged by TMA.
+//
+// Replaces the attention core of the reference at prefill: SigLIP MHA (modeling_siglip.py:96-136; dh = 72, fp32 softmax)
+// and the Gemma prefill MQA/GQA (modeling_gemma.py:307-339 with the all-zero mask of modeling_paligemma.py:154-156;
+// dh = 256; the G query heads of one KV head are stacked as consecutive rows of one problem, which replaces repeat_kv
+// modeling_gemma.py:185-196).
+//
+// One CTA = 128 query rows (one TMEM lane each) against all keys of its (batch, kv head), key tiles of BN keys:
+//   warp 0      TMA producer: Q once (5-D tensor map: dh, group, token, head, batch), then K / V tiles through two rings
+//   warp 1      tcgen05.mma issuer:  S_j = Q K_j^T  (M=128, N=BN, K=dh; both operands K-major, 128B swizzle)
+//                                    O  += P_j V_j  (M=128, N=dh, K=BN; P K-major from shared memory, V MN-major: the
+//                                                    [keys, dh] tile exactly as TMA delivers it)
+//   warps 2..5  softmax: thread = query row; S is read from TMEM (tcgen05.ld), P = exp2(s - m) goes to shared memory as
+//               bf16 in the swizzled A-operand layout, the row sum stays in registers.  The running maximum is only
+//               advanced when it grew by more than 2^8 (the O accumulator in TMEM then gets rescaled in place), which
+//               keeps the accumulator round trip off the common path.
+// S is double buffered in TMEM, so S_{j+1} is computed while the softmax of tile j runs, and P_j V_j runs while the
+// softmax of tile j+1 runs: the tensor pipe only idles when the softmax (MUFU exp2) is the longer stage (dh = 72).
+// Zero padding comes from TMA: columns beyond dh (72 -> 80) and key / query rows beyond the sequence are out-of-bounds
+// box elements and arrive as zeros; padded keys are masked to -inf before the softmax.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "paligemma_b200.h"
+#include "tmap.cuh"
+
+namespace pg {
+namespace ap {
+
+typedef __nv_bfloat16 bf16;
+
+struct Params {
+  bf16* o;
+  int rows, keys, group, dh;
+  long long o_bs, o_ts, o_hs, o_head_off;
+  float sl2;  // softmax scale * log2(e)
+};
+
+template <int DH>
+struct Cfg {
+  static constexpr int BM = 128;
+  static constexpr int BN = DH > 128 ? 64 : 128;       // keys per tile
+  static constexpr int DHP = (DH + 15) / 16 * 16;       // UMMA K (QK^T) / N (PV) extent: 72 -> 80
+  static constexpr int NKB = (DH + 63) / 64;            // 64-column (128 B) boxes along dh
+  static constexpr int Q_BOX = BM * 128;                // bytes of one Q box
+  static constexpr int KV_BOX = BN * 128;               // bytes of one K / V box
+  static constexpr int Q_BYTES = NKB * Q_BOX;
+  static constexpr int KV_BYTES = NKB * KV_BOX;
+  static constexpr int P_BOX = BM * 128;                // [128 rows x 64 keys]
+  static constexpr int P_BYTES = (BN / 64) * P_BOX;
+  static constexpr int KST = 2, VST = 2;                // ring depths
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KST * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + VST * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int COL_S = 0, COL_O = 2 * BN;
+  static_assert(2 * BN + DHP <= 512, "TMEM budget");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+PG_DEVINL void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+PG_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// registers -> TMEM: lane = TMEM lane, 16 consecutive fp32 columns
+PG_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+PG_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory descriptor of an MN-major operand tile as TMA lays it out ([k rows][64 mn columns = 128 B], 128B swizzle):
+// 8-row groups along K are 1024 B apart (stride byte offset), 64-column boxes along MN are `box_bytes` apart (leading
+// byte offset).  (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.)
+PG_DEVINL uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t box_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((box_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                          // version = 1
+  d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(192, 1)
+attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const Params p) {
+  using C = Cfg<DH>;
+  constexpr int BM = C::BM, BN = C::BN, DHP = C::DHP, NKB = C::NKB;
+  constexpr uint32_t IDESC_S = make_idesc_bf16(BM, BN);
+  constexpr uint32_t IDESC_O = make_idesc_bf16(BM, DHP, 0, 1);  // B (= V) is MN-major
+  extern __shared__ __align__(1024) uint8_t smem_ap[];
+  const uint32_t sbase = smem_u32(smem_ap);
+  if ((sbase & 1023u) != 0) __trap();
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  // barriers: q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full[2], o_done
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto s_full = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto s_empty = [&](int s) { return bar0 + 8u * (11 + s); };
+  auto p_full = [&](int s) { return bar0 + 8u * (13 + s); };
+  const uint32_t o_done = bar0 + 8u * 15;
+  const uint32_t tmem_slot = bar0 + 8u * 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_ap + C::OFF_BAR + 8 * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.keys + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
+      mbar_init(p_full(s), 4);
+    }
+    mbar_init(o_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      const int t0 = (m_blk * BM) / p.group;  // first token of this row tile (128 % group == 0)
+      mbar_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) tma_load_5d(sbase + kb * C::Q_BOX, &tmQ, q_full, kb * 64, 0, t0, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int ks = j % C::KST, vs = j % C::VST;
+        mbar_wait(k_empty(ks), ((j / C::KST) & 1) ^ 1);
+        mbar_expect_tx(k_full(ks), C::KV_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+          tma_load_4d(sbase + C::OFF_K + ks * C::KV_BYTES + kb * C::KV_BOX, &tmK, k_full(ks), kb * 64, j * BN, h, b);
+        mbar_wait(v_empty(vs), ((j / C::VST) & 1) ^ 1);
+        mbar_expect_tx(v_full(vs), C::KV_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+          tma_load_4d(sbase + C::OFF_V + vs * C::KV_BYTES + kb * C::KV_BOX, &tmV, v_full(vs), kb * 64, j * BN, h, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer ================================
+    if (lane == 0) {
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j % 2
+        const int ks = j % C::KST, sb = j & 1;
+        mbar_wait(k_full(ks), (j / C::KST) & 1);
+        mbar_wait(s_empty(sb), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + C::COL_S + sb * BN;
+        const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t adesc = make_sdesc_k_sw128(sbase + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
+          const uint64_t bdesc = make_sdesc_k_sw128(kaddr + (k >> 2) * C::KV_BOX) + 2 * (k & 3);
+          umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
+        }
+        umma_commit(k_empty(ks));
+        umma_commit(s_full(sb));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        const int vs = j % C::VST, pb = j & 1;
+        mbar_wait(v_full(vs), (j / C::VST) & 1);
+        mbar_wait(p_full(pb), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + C::COL_O;
+        const uint32_t paddr = sbase + C::OFF_P + pb * C::P_BYTES;
+        const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
+          const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);  // 16 keys = two 8-row groups
+          umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(v_empty(vs));
+        umma_commit(o_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== softmax / epilogue ========================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int row = m_blk * BM + r;
+    float m_used = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = sbase + C::OFF_P + r * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1;
+      mbar_wait(s_full(sb), (j >> 1) & 1);
+      tc_fence_after();
+      float s[BN];
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + C::COL_S + sb * BN + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[c0 + i] = __uint_as_float(v[i]) * p.sl2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(sb));  // the S buffer may be overwritten by S_{j+2}
+      const int nvalid = p.keys - j * BN;       // keys of this tile that exist
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        if (i >= nvalid) s[i] = -INFINITY;
+        mx = fmaxf(mx, s[i]);
+      }
+      // lazy running maximum: only move it when it grew by more than 8 (log2 units); probabilities stay <= 2^8
+      const bool need = mx > m_used + 8.0f;
+      const float m_new = need ? mx : m_used;
+      const float alpha = need ? exp2f(m_used - m_new) : 1.0f;  // first tile: m_used = -inf -> 0 (O is overwritten)
+      m_used = m_new;
+      float sum = 0.f;
+      const uint32_t pdst = p_row + sb * C::P_BYTES;
+#pragma unroll
+      for (int c = 0; c < BN / 8; ++c) {  // 16-byte chunks of 8 keys
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(s[c * 8 + 2 * e] - m_new), p1 = exp2f(s[c * 8 + 2 * e + 1] - m_new);
+          sum += p0 + p1;
+          pk[e] = pack_bf16(p0, p1);
+        }
+        const uint32_t addr = pdst + (c >> 3) * C::P_BOX + (((c & 7) ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      }
+      l_run = l_run * alpha + sum;
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
+        if (__any_sync(0xffffffffu, need)) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < DHP; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + C::COL_O + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(lane_addr + C::COL_O + c0, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(sb));
+    }
+    // ---- epilogue: O / l -> bf16 ----
+    mbar_wait(o_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const bool row_ok = row < p.rows;
+    bf16* orow = p.o + b * p.o_bs + h * p.o_head_off + static_cast<long long>(row / p.group) * p.o_ts +
+                 static_cast<long long>(row % p.group) * p.o_hs;
+#pragma unroll 1
+    for (int c0 = 0; c0 < DHP; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_addr + C::COL_O + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
+        if (c0 + 8 <= p.dh) *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (c0 + 16 <= p.dh) *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// n-D bf16 tensor map, 128B swizzle, OOB -> zeros.  dims/strides innermost first; strides in ELEMENTS (dim 0 is contiguous).
+static int make_tmap_nd(CUtensorMap* m, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return PG_ERR_DRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = static_cast<cuuint64_t>(dims[i]);
+    bx[i] = static_cast<cuuint32_t>(box[i]);
+    estr[i] = 1;
+    if (i > 0) {
+      long long sb = strides[i] * 2;
+      if (dims[i] == 1 && (sb <= 0 || (sb % 16) != 0)) sb = 16;  // the stride of an extent-1 dimension is never used
+      if (sb <= 0 || (sb % 16) != 0) return PG_ERR_ARG;
+      gstr[i - 1] = static_cast<cuuint64_t>(sb);
+    }
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
+}
+
+template <int DH>
+static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int B, int H, cudaStream_t st) {
+  using C = Cfg<DH>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+      cudaGetLastError();
+      return PG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((p.rows + C::BM - 1) / C::BM, H, B);
+  attn_prefill_tc_kernel<DH><<<grid, 192, C::SMEM, st>>>(tq, tk, tv, p);
+  pg_count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
+}  // namespace ap
+}  // namespace pg
+
+// Returns PG_OK when the problem was launched on the tcgen05 kernel, 1 when the shape / strides are not supported by it
+// (the caller then uses the mma.sync kernel), or a negative error.
+int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
+                            int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off, long long kv_bs,
+                            long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts, long long o_hs,
+                            long long o_head_off, float scale, void* stream) {
+  using namespace pg;
+  if (dh != 64 && dh != 72 && dh != 256) return 1;
+  if (group <= 0 || (128 % group) != 0 || (rows % group) != 0) return 1;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  auto ok8 = [](long long s) { return s > 0 && (s % 8) == 0; };
+  if (!al16(q) || !al16(k) || !al16(v) || !al16(o)) return 1;
+  const int tokens = rows / group;
+  if (!ok8(q_ts) || !ok8(kv_ts) || !ok8(o_ts) || (group > 1 && (!ok8(q_hs) || !ok8(o_hs)))) return 1;
+  if ((H > 1 && (!ok8(q_head_off) || !ok8(kv_head_off) || !ok8(o_head_off))) || (B > 1 && (!ok8(q_bs) || !ok8(kv_bs)))) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  {
+    const long long dims[5] = {dh, group, tokens, H, B};
+    const long long strides[5] = {1, q_hs, q_ts, q_head_off, q_bs};
+    const int box[5] = {64, group, 128 / group, 1, 1};
+    if ((rc = ap::make_tmap_nd(&tq, q, 5, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
+  }
+  const int BN = dh > 128 ? 64 : 128;
+  {
+    const long long dims[4] = {dh, keys, H, B};
+    const long long strides[4] = {1, kv_ts, kv_head_off, kv_bs};
+    const int box[4] = {64, BN, 1, 1};
+    if ((rc = ap::make_tmap_nd(&tk, k, 4, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
+    if ((rc = ap::make_tmap_nd(&tv, v, 4, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
+  }
+  ap::Params p;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.rows = rows; p.keys = keys; p.group = group; p.dh = dh;
+  p.o_bs = o_bs; p.o_ts = o_ts; p.o_hs = o_hs; p.o_head_off = o_head_off;
+  p.sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dh) {
+    case 64: return ap::launch<64>(tq, tk, tv, p, B, H, st);
+    case 72: return ap::launch<72>(tq, tk, tv, p, B, H, st);
+    default: return ap::launch<256>(tq, tk, tv, p, B, H, st);
+  }
+}

@@ -173,7 +173,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             kv.allocate(B, c.num_hidden_layers, c.num_key_value_heads, c.head_dim, S + T + 1)
             stt = dict(kv=kv, nxt=torch.empty(B, device=dev, dtype=torch.int32), cur=torch.empty(B, device=dev, dtype=torch.int32),
                        hist=torch.zeros(T, B, device=dev, dtype=torch.int32), step=torch.zeros(1, device=dev, dtype=torch.int32),
-                       img=torch.empty(B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32), graph=None)
+                       img=torch.empty(B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32), graph=None, graph_k=None)
             if len(self._graphs) >= 4:  # bound the number of cached geometries (each owns a KV cache)
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = stt
@@ -247,24 +247,38 @@ class PaliGemmaForConditionalGeneration(nn.Module):
 
         graphed = use_cuda_graph and not return_logits and forced is None
         done_at = T
-        for t in range(1, T):
-            if graphed and t >= 2:
+        GK = 8  # decode steps per replay of the multi-step graph (amortises the graph-launch latency)
+
+        def capture(n_steps):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(n_steps):
+                        decode_step()
+            torch.cuda.current_stream().wait_stream(side)
+            return g
+
+        t = 1  # tokens generated so far
+        while t < T:
+            t_prev = t
+            if graphed and (t >= 2 or stt["graph"] is not None):
                 if stt["graph"] is None:  # step 1 ran eagerly (lazy kernel attributes / driver entry points are warm)
-                    side = torch.cuda.Stream()
-                    side.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(side):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=side):
-                            decode_step()
-                    torch.cuda.current_stream().wait_stream(side)
-                    stt["graph"] = g
-                    # the capture itself does not execute: fall through to the replay for step t
-                stt["graph"].replay()
+                    stt["graph"] = capture(1)  # (the capture itself does not execute)
+                    stt["graph_k"] = capture(GK) if T - 2 >= GK else None
+                if T - t >= GK and stt.get("graph_k") is not None:
+                    stt["graph_k"].replay()
+                    t += GK
+                else:
+                    stt["graph"].replay()
+                    t += 1
             else:
                 decode_step(t)
-            if eos_token_id is not None and (t % 16 == 15 or t == T - 1):
-                if bool((hist[: t + 1] == eos_token_id).any(0).all()):
-                    done_at = t + 1
+                t += 1
+            if eos_token_id is not None and (t // 16 > t_prev // 16 or t == T):
+                if bool((hist[:t] == eos_token_id).any(0).all()):
+                    done_at = t
                     break
         kv._set_len(S + done_at - 1, c.num_hidden_layers)
         if ev:
