@@ -232,7 +232,9 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   t_cut = fmaxf(t_cut, 1e-3f);
   const float k0 = inv_temp * static_cast<float>(NB) / t_cut;  // u = (mx - x) * k0  in [0, NB) <=> t in [0, t_cut)
   const float c0 = mx * k0;
-  auto u_of = [&](float x) { return fmaf(-x, k0, c0); };
+  // (clamped at 0: c0 = mx * k0 is rounded, so the fused multiply-add can come out a hair NEGATIVE for the row maximum
+  //  itself, which would put it below bin 0 and leave every histogram empty)
+  auto u_of = [&](float x) { return fmaxf(fmaf(-x, k0, c0), 0.f); };
   auto w_of = [&](float x) { return exp2f(fmaf(x, c, -cm)); };
 
   auto clear_hist = [&]() {
