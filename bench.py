@@ -57,6 +57,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (64-token gate||up GEMM) from the committed
+    `ncu --set full` capture (profiles/r01b_decode_gemm_ncu_full.csv, first row), bytes per launch; None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_decode_gemm_ncu_full.csv")
+    try:
+        with open(path) as f:
+            rows = list(csv.reader(f))
+        hdr, row = rows[0], rows[1]
+        tot = 0.0
+        for name, val in zip(hdr, row):
+            if name.startswith("dram__bytes_read.sum") or name.startswith("dram__bytes_write.sum"):
+                unit = name[name.index("[") + 1:name.index("]")].lower()
+                tot += float(val) * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -291,7 +310,7 @@ def main():
             "gpu_launches": int(eager_launches + K * max(T - 1, 0) * graph_kernels),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<64,swap> gate||up decode GEMM", "achieved": k_gbs,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak, "traffic": ncu_traffic_per_launch() if B == 64 else None, "peak_source": peak_src,
                          "us_per_launch": 1e3 * k_ms, "algorithmic_bytes": k_bytes},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                               "algorithmic_bytes": step_bytes},
