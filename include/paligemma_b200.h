@@ -41,6 +41,8 @@ int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
 int pg_debug_set_decode_gemm_trace(long long* device_buffer); /* pg_gemm_decode: 8 stamps per launch */
+int pg_debug_decode_gemm_blocks_per_sm(int dynamic_smem_bytes); /* prints + returns cudaOccupancyMaxActiveBlocksPerMultiprocessor */
+int pg_debug_set_decode_gemm_cta_trace(long long* device_buffer); /* pg_gemm_decode: [grid][3] = smid, globaltimer in / out */
 int pg_debug_decode_gemm_max_clusters(int cluster_k); /* cudaOccupancyMaxActiveClusters of the 64-token decode GEMM */
 int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_decode_fused (8 stamps per launch) */
 
