@@ -45,6 +45,16 @@ PG_DEVINL float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + tanhf(inner));
 }
 
+// same with the hardware tanh (MUFU, max relative error 2^-11): for GEMM epilogues whose result is rounded to bf16
+// (relative 2^-9) right away; a fraction of the instructions of tanhf
+PG_DEVINL float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float inner = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
+
 PG_DEVINL uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -113,7 +113,7 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
         const float m = rs_tab != nullptr ? rs_tab[c0 + i] : scale;
         float x = fmaf(__uint_as_float(r[i]), m, bias_s);
         if (MODE == PG_EPI_BF16) {
-          if (gelu) x = gelu_tanh(x);
+          if (gelu) x = gelu_tanh_fast(x);
           *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(x);
         } else if (MODE == PG_EPI_F32) {
           if (res != nullptr) x += *reinterpret_cast<const float*>(res);
@@ -124,6 +124,108 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
       }
       dst += step;
       if (MODE == PG_EPI_F32) res += rstep;
+    }
+  }
+}
+
+// Epilogue of one token-major (non-swap) tile for the non-GEGLU modes: thread = token row, columns = features.
+// 64 columns per step: the fp32 residual of the whole step is requested first (16 independent 16-byte loads per thread),
+// then the accumulator is pulled out of TMEM, so that one global round trip covers 64 columns instead of 16 (the
+// residual read is what bounds the short-K GEMMs: out_proj / o_proj).
+template <int BN, int MODE>
+PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int tok, int n0, bool first_split) {
+  constexpr int STEP = BN >= 64 ? 64 : BN;
+  constexpr int NCH = STEP / 16;
+  const bool row_ok = tok < args.tokens;
+  const float scale = args.scale;
+  const bool has_bias = args.bias != nullptr && first_split;
+  const bool gelu = MODE == PG_EPI_BF16 && args.act_gelu != 0;
+  __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(tok) * args.ldo;
+  float* out_f = reinterpret_cast<float*>(args.out) + static_cast<long long>(tok) * args.ldo;
+  const float* res = (MODE == PG_EPI_F32 && args.resid != nullptr) ? args.resid + static_cast<long long>(tok) * args.ldr : nullptr;
+  // 16-byte vector access is possible when the row bases are 16 B aligned (n0 and the step are multiples of 16 columns)
+  const bool vec_ok = MODE == PG_EPI_BF16 ? ((reinterpret_cast<uintptr_t>(out_bf) & 15) == 0)
+                                          : (((reinterpret_cast<uintptr_t>(out_f) & 15) == 0) &&
+                                             (res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0));
+  const bool bias_vec = has_bias && ((reinterpret_cast<uintptr_t>(args.bias) & 15) == 0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += STEP) {
+    const int f0 = n0 + c0;
+    if (f0 >= args.features) break;  // warp-uniform
+    const bool full = (f0 + STEP <= args.features) && vec_ok;
+    float4 rr[STEP / 4];
+    if (MODE == PG_EPI_F32 && res != nullptr && full && row_ok) {
+#pragma unroll
+      for (int i = 0; i < STEP / 4; ++i) rr[i] = *reinterpret_cast<const float4*>(res + f0 + 4 * i);
+    }
+    uint32_t r[NCH][16];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) tmem_ld16(taddr + c0 + 16 * ch, r[ch]);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    if (full) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[ch][i]) * scale;
+        if (has_bias) {
+          if (bias_vec) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + f0 + 16 * ch) + i);
+              v[4 * i] = fmaf(b4.x, scale, v[4 * i]); v[4 * i + 1] = fmaf(b4.y, scale, v[4 * i + 1]);
+              v[4 * i + 2] = fmaf(b4.z, scale, v[4 * i + 2]); v[4 * i + 3] = fmaf(b4.w, scale, v[4 * i + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(__ldg(args.bias + f0 + 16 * ch + i), scale, v[i]);
+          }
+        }
+        if (MODE == PG_EPI_BF16) {
+          if (gelu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_fast(v[i]);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(out_bf + f0 + 16 * ch);
+          d4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          d4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        } else if (MODE == PG_EPI_F32) {
+          float4* d4 = reinterpret_cast<float4*>(out_f + f0 + 16 * ch);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 o4 = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            if (res != nullptr) {
+              const float4 q4 = rr[4 * ch + i];
+              o4.x += q4.x; o4.y += q4.y; o4.z += q4.z; o4.w += q4.w;
+            }
+            d4[i] = o4;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(out_f + f0 + 16 * ch + i, v[i]);
+        }
+      }
+    } else {  // feature tail / unaligned rows: element by element
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int f = f0 + 16 * ch + i;
+          if (f < args.features) {
+            float x = __uint_as_float(r[ch][i]) * scale;
+            if (has_bias) x = fmaf(__ldg(args.bias + f), scale, x);
+            if (MODE == PG_EPI_BF16) {
+              if (gelu) x = gelu_tanh_fast(x);
+              out_bf[f] = __float2bfloat16(x);
+            } else if (MODE == PG_EPI_F32) {
+              out_f[f] = x + (res != nullptr ? res[f] : 0.f);
+            } else {
+              atomicAdd(out_f + f, x);
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -294,8 +396,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  float a = gelu_tanh(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
-                  float b = gelu_tanh(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
+                  float a = gelu_tanh_fast(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
+                  float b = gelu_tanh_fast(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
                   pk[i] = pack_bf16(a, b);
                 }
                 uint4* dst = reinterpret_cast<uint4*>(out_bf + static_cast<long long>(tok) * args.ldo + f0);
@@ -304,62 +406,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               }
             }
           }
+        } else if (mode == PG_EPI_BF16) {
+          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split);
+        } else if (mode == PG_EPI_F32) {
+          rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split);
         } else {
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 16) {
-            const int f0 = t.n_blk * BN + c0;
-            if (f0 >= args.features) break;  // warp-uniform
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-            if (!row_ok) continue;
-            float v[16];
-            const bool full = (f0 + 16 <= args.features);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(r[i]);
-              if (args.bias != nullptr && first_split && (full || f0 + i < args.features)) x += __ldg(args.bias + f0 + i);
-              v[i] = x * args.scale;
-            }
-            if (mode == PG_EPI_BF16) {
-              if (args.act_gelu) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = gelu_tanh(v[i]);
-              }
-              __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
-              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
-                d4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                d4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-              } else {
-                for (int i = 0; i < 16; ++i)
-                  if (f0 + i < args.features) dst[i] = __float2bfloat16(v[i]);
-              }
-            } else if (mode == PG_EPI_F32) {
-              float* dst = out_f + static_cast<long long>(tok) * args.ldo + f0;
-              const float* res = args.resid ? args.resid + static_cast<long long>(tok) * args.ldr + f0 : nullptr;
-              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                  (res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
-                if (res) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float4 rr = *reinterpret_cast<const float4*>(res + 4 * i);
-                    v[4 * i] += rr.x; v[4 * i + 1] += rr.y; v[4 * i + 2] += rr.z; v[4 * i + 3] += rr.w;
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              } else {
-                for (int i = 0; i < 16; ++i)
-                  if (f0 + i < args.features) dst[i] = v[i] + (res ? res[i] : 0.f);
-              }
-            } else {  // PG_EPI_ATOMIC_F32
-              float* dst = out_f + static_cast<long long>(tok) * args.ldo + f0;
-              for (int i = 0; i < 16; ++i)
-                if (f0 + i < args.features) atomicAdd(dst + i, v[i]);
-            }
-          }
+          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split);
         }
       } else {
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
@@ -420,7 +472,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                   mine *= rs;
                   other *= rs;
                 }
-                res[e] = is_gate ? gelu_tanh(mine) * other : gelu_tanh(other) * mine;
+                res[e] = is_gate ? gelu_tanh_fast(mine) * other : gelu_tanh_fast(other) * mine;
               }
               pk[(c0 + i) / 2] = pack_bf16(res[0], res[1]);
             }
