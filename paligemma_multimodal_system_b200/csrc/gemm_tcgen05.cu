@@ -29,12 +29,13 @@ constexpr int ACC_STAGES = 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
 __host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
-__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 0; }  // exchange area + per-token factors
+// swap: GeGLU exchange area + per-token factors; token-major: four warp-private 4 KB transposition tiles (fp32 epilogue)
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 4 * 4096; }
 // decode (SWAP, BN <= 64): two CTAs per SM (115712 B each) so that, with programmatic dependent launch, the next
 // kernel's CTAs become resident and prefetch their weights while this kernel drains; otherwise one CTA with <= 200 KB
 __host__ __device__ constexpr bool two_per_sm(int BN, bool swap) { return swap && BN <= 64; }
 __host__ __device__ constexpr int num_stages(int BN, bool swap) {
-  int budget = two_per_sm(BN, swap) ? 115712 - 256 : 200 * 1024;
+  int budget = two_per_sm(BN, swap) ? 115712 - 256 : (swap ? 200 * 1024 : 232448 - 256);
   int s = (budget - xch_bytes(BN, swap)) / stage_bytes(BN);
   return s > 8 ? 8 : s;
 }
@@ -59,6 +60,7 @@ struct GemmArgs {
   // optional per-token RMSNorm factor of the producer of X (SWAP kernels): acc[f, t] *= rsqrt(ss_in[t] * inv_norm_dim + eps)
   const float* ss_in;
   float inv_norm_dim, eps;
+  int f32_coalesced;  // token-major fp32 epilogue through the shared-memory transposition (alignment checked by the host)
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
 };
 
@@ -226,6 +228,82 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
           }
         }
       }
+    }
+  }
+}
+
+// fp32 (+bias, +fp32 residual) epilogue of a token-major tile with COALESCED global access.  The accumulator comes out
+// of TMEM one row per thread; 32 columns at a time it is transposed through a warp-private, swizzled 4 KB shared-memory
+// tile into the mapping "8 lanes per row, 16 bytes per lane", so that every global load / store instruction of the
+// residual stream touches 4 full 128-byte lines instead of 32 partial ones (the row-per-thread version is bound by the
+// LSU's line throughput: 16 k cycles per 128x256 tile, more than the main loop of the K <= 2048 GEMMs).
+// The residual of slice s+1 is requested before slice s is finished.  Needs features % 4 == 0 and 16 B aligned rows.
+template <int BN>
+PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32_t taddr, int m0, int n0, bool first_split,
+                                                    uint32_t stage, int q, int lane) {
+  const float scale = args.scale;
+  const bool has_bias = args.bias != nullptr && first_split;
+  float* out = reinterpret_cast<float*>(args.out);
+  const float* res = args.resid;
+  const int row_base = m0 + q * 32;
+  const int sub = lane >> 3, piece = lane & 7;
+  const int nsl = (min(BN, args.features - n0) + 31) / 32;
+  auto load_res = [&](int sl, float4 (&dst)[8]) {
+    const int col = n0 + sl * 32 + piece * 4;
+    const bool col_ok = col < args.features;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int row = row_base + 4 * k + sub;
+      dst[k] = (col_ok && row < args.tokens) ? *reinterpret_cast<const float4*>(res + static_cast<long long>(row) * args.ldr + col)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 rr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (res != nullptr) load_res(0, rr);
+#pragma unroll 1
+  for (int sl = 0; sl < nsl; ++sl) {
+    uint32_t a0[16], a1[16];
+    tmem_ld16(taddr + sl * 32, a0);
+    tmem_ld16(taddr + sl * 32 + 16, a1);
+    tmem_ld_wait();
+    __syncwarp();  // the previous slice has been read out of the staging tile
+    const uint32_t my_row = stage + lane * 128;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((pc ^ (lane & 7)) << 4)), "r"(a0[4 * pc]),
+                   "r"(a0[4 * pc + 1]), "r"(a0[4 * pc + 2]), "r"(a0[4 * pc + 3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (((pc + 4) ^ (lane & 7)) << 4)), "r"(a1[4 * pc]),
+                   "r"(a1[4 * pc + 1]), "r"(a1[4 * pc + 2]), "r"(a1[4 * pc + 3]) : "memory");
+    }
+    __syncwarp();
+    float4 rn[8];
+    if (res != nullptr && sl + 1 < nsl) load_res(sl + 1, rn);
+    const int col = n0 + sl * 32 + piece * 4;
+    const bool col_ok = col < args.features;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bias && col_ok) {
+      b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col));
+      b4.x *= scale; b4.y *= scale; b4.z *= scale; b4.w *= scale;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r8 = 4 * k + sub;
+      const int row = row_base + r8;
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(stage + r8 * 128 + ((piece ^ (r8 & 7)) << 4)) : "memory");
+      if (col_ok && row < args.tokens) {
+        float4 o4;
+        o4.x = fmaf(v.x, scale, b4.x) + rr[k].x; o4.y = fmaf(v.y, scale, b4.y) + rr[k].y;
+        o4.z = fmaf(v.z, scale, b4.z) + rr[k].z; o4.w = fmaf(v.w, scale, b4.w) + rr[k].w;
+        *reinterpret_cast<float4*>(out + static_cast<long long>(row) * args.ldo + col) = o4;
+      }
+    }
+    if (res != nullptr && sl + 1 < nsl) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rr[k] = rn[k];
     }
   }
 }
@@ -409,7 +487,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         } else if (mode == PG_EPI_BF16) {
           rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split);
         } else if (mode == PG_EPI_F32) {
-          rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split);
+          // (measured: pulling the NEXT tile's residual rows into L2 from here does not help: o_proj 926 -> 824 TFLOP/s)
+          if (args.f32_coalesced)
+            rowmajor_tile_epilogue_f32_coalesced<BN>(args, taddr, t.m_blk * BM, t.n_blk * BN, first_split,
+                                                     smem_base + STAGES * STAGE_BYTES + q * 4096, q, lane);
+          else
+            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split);
         } else {
           rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split);
         }
@@ -598,6 +681,9 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
   a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
   a.ss_in = ss_in; a.inv_norm_dim = norm_dim > 0 ? 1.0f / static_cast<float>(norm_dim) : 0.f; a.eps = eps;
+  a.f32_coalesced = (!swap && mode == PG_EPI_F32 && (features % 4) == 0 && (ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+                     (resid == nullptr || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0))) ? 1 : 0;
   a.trace = g_gemm_trace ? g_gemm_trace + 8 * (g_gemm_trace_idx++ % 64) : nullptr;
 
   CUtensorMap ta, tb;
