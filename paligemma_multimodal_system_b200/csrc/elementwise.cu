@@ -102,6 +102,81 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Warp-per-row variants for the prefill (tens of thousands of short rows): the row lives in registers (D/128 float4 per
+// lane), the two reductions are warp shuffles, nothing goes through shared memory or a block barrier.  D % 128 == 0,
+// D <= 128 * NV * ... (NV float4 per lane).
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ y_bf,
+                                                             float* __restrict__ y_f, int rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nv = D >> 7;  // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      v[i] = xr[lane + 32 * i];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const int c4 = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      const float a = (v[i].x - mean) * rstd * g.x + bt.x, b = (v[i].y - mean) * rstd * g.y + bt.y;
+      const float c = (v[i].z - mean) * rstd * g.z + bt.z, d = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (y_bf) reinterpret_cast<uint2*>(y_bf + r * D)[c4] = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+      if (y_f) reinterpret_cast<float4*>(y_f + r * D)[c4] = make_float4(a, b, c, d);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           bf16* __restrict__ y, int rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nv = D >> 7;
+  const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+  float4 v[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      v[i] = xr[lane + 32 * i];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nv) {
+      const int c4 = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
+      reinterpret_cast<uint2*>(y + r * D)[c4] = make_uint2(pack_bf16(v[i].x * rstd * (1.0f + g.x), v[i].y * rstd * (1.0f + g.y)),
+                                                          pack_bf16(v[i].z * rstd * (1.0f + g.z), v[i].w * rstd * (1.0f + g.w)));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // im2col for the patch-embedding conv (modeling_siglip.py:258-263): column = c*P*P + ky*P + kx
 // ---------------------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const float* __restrict__ px, bf16* __restrict__ out, int C, int H, int W, int P, int Kpad,
@@ -332,22 +407,22 @@ __global__ void __launch_bounds__(128) rope_kv_append_kernel(const void* __restr
     const int page = page_table[b * max_pages + slot / page_size];
     kv_row = (static_cast<long long>(page) * page_size + slot % page_size) * Hkv * dh;
   }
-  // q and k heads: rotate pairs (i, i + dh/2)
-  for (int idx = threadIdx.x; idx < (Hq + Hkv) * half; idx += blockDim.x) {
-    const int head = idx / half, i = idx % half;
-    const float ang = p * inv_freq[i];
+  // q and k heads: rotate pairs (i, i + dh/2); the angle depends on (token, i) only, so one sincos serves every head
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
     float sn, cs;
-    sincosf(ang, &sn, &cs);
-    const float x1 = ld(head * dh + i), x2 = ld(head * dh + i + half);
-    const bf16 y1 = __float2bfloat16(x1 * cs - x2 * sn);
-    const bf16 y2 = __float2bfloat16(x2 * cs + x1 * sn);
-    if (head < Hq) {
-      q_out[t * Hq * dh + head * dh + i] = y1;
-      q_out[t * Hq * dh + head * dh + i + half] = y2;
-    } else {
-      const int hk = head - Hq;
-      if (k_out) { k_out[t * Hkv * dh + hk * dh + i] = y1; k_out[t * Hkv * dh + hk * dh + i + half] = y2; }
-      if (kv_row >= 0) { k_pages[kv_row + hk * dh + i] = y1; k_pages[kv_row + hk * dh + i + half] = y2; }
+    sincosf(p * inv_freq[i], &sn, &cs);
+    for (int head = 0; head < Hq + Hkv; ++head) {
+      const float x1 = ld(head * dh + i), x2 = ld(head * dh + i + half);
+      const bf16 y1 = __float2bfloat16(x1 * cs - x2 * sn);
+      const bf16 y2 = __float2bfloat16(x2 * cs + x1 * sn);
+      if (head < Hq) {
+        q_out[t * Hq * dh + head * dh + i] = y1;
+        q_out[t * Hq * dh + head * dh + i + half] = y2;
+      } else {
+        const int hk = head - Hq;
+        if (k_out) { k_out[t * Hkv * dh + hk * dh + i] = y1; k_out[t * Hkv * dh + hk * dh + i + half] = y2; }
+        if (kv_row >= 0) { k_pages[kv_row + hk * dh + i] = y1; k_pages[kv_row + hk * dh + i + half] = y2; }
+      }
     }
   }
   for (int idx = threadIdx.x; idx < Hkv * dh; idx += blockDim.x) {
@@ -441,6 +516,12 @@ extern "C" int pg_check_device(void) {
 extern "C" int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows,
                             int D, float eps, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                    reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(y_f32)) & 15) == 0;
+  if (rows >= 1024 && (D % 128) == 0 && D <= 2048 && al) {  // prefill: one warp per row, the row stays in registers
+    layernorm_warp_kernel<16><<<(rows + 7) / 8, 256, 0, PG_ST(stream)>>>(x, gamma, beta, static_cast<bf16*>(y_bf16), y_f32, rows, D, eps);
+    PG_RET();
+  }
   layernorm_kernel<<<rows, 256, (D + 33) * sizeof(float), PG_ST(stream)>>>(x, gamma, beta, static_cast<bf16*>(y_bf16), y_f32, D, eps);
   PG_RET();
 }
@@ -449,6 +530,11 @@ extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows
                           long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
   if (prefetch_ptr != nullptr && ((reinterpret_cast<uintptr_t>(prefetch_ptr) & 15) || prefetch_bytes < 0)) return PG_ERR_ARG;
+  if (rows >= 1024 && (D % 128) == 0 && D <= 2048 && zero_buf == nullptr && prefetch_ptr == nullptr &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y_bf16)) & 15) == 0) {
+    rmsnorm_warp_kernel<16><<<(rows + 7) / 8, 256, 0, PG_ST(stream)>>>(x, w, static_cast<bf16*>(y_bf16), rows, D, eps);
+    PG_RET();
+  }
   return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), (D + 33) * sizeof(float), PG_ST(stream), x, w,
                        static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count, static_cast<const uint8_t*>(prefetch_ptr),
                        prefetch_bytes) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
