@@ -60,6 +60,8 @@ struct GemmArgs {
   // optional per-token RMSNorm factor of the producer of X (SWAP kernels): acc[f, t] *= rsqrt(ss_in[t] * inv_norm_dim + eps)
   const float* ss_in;
   float inv_norm_dim, eps;
+  int n_fast;  // tile raster order (decode_tile)
+  int debug_skip_epilogue;  // profiling: 1 = no epilogue work at all, 2 = TMEM reads only (no global stores)
   int f32_coalesced;  // token-major fp32 epilogue through the shared-memory transposition (alignment checked by the host)
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
 };
@@ -68,12 +70,26 @@ struct TileInfo {
   int m_blk, n_blk, kb0, kb1;
 };
 
-PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_kb, int split_k) {
+// Tile order of the persistent grid.  m-fast: concurrently running CTAs share one weight (B) tile and walk the token
+// (A) tiles, right when A fits in L2 or the weight matrix is huge (gate||up).  n-fast: concurrently running CTAs cover
+// every feature tile of a few token tiles, so each A tile is fetched from DRAM once and the (small) weight matrix stays
+// L2 resident: down_proj / fc2 re-read their 0.1-0.5 GB activation matrix once per feature tile otherwise (ncu: 4.1 GB
+// of DRAM reads for a 0.6 GB problem).
+PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_kb, int split_k, int n_fast = 0) {
   TileInfo t;
-  t.m_blk = tile % m_blocks;
-  int rest = tile / m_blocks;
-  t.n_blk = rest % n_blocks;
-  int split = rest / n_blocks;
+  int rest;
+  if (n_fast) {
+    t.n_blk = tile % n_blocks;
+    rest = tile / n_blocks;
+    t.m_blk = rest % m_blocks;
+    rest /= m_blocks;
+  } else {
+    t.m_blk = tile % m_blocks;
+    rest = tile / m_blocks;
+    t.n_blk = rest % n_blocks;
+    rest /= n_blocks;
+  }
+  int split = rest;
   int kb_per = (total_kb + split_k - 1) / split_k;
   t.kb0 = split * kb_per;
   t.kb1 = min(total_kb, t.kb0 + kb_per);
@@ -130,12 +146,37 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
   }
 }
 
+// Stores 32 rows x 128 bytes held one row per lane (pk = the lane's 8 16-byte pieces) as full 128-byte lines: the rows
+// go through a warp-private swizzled 4 KB shared-memory tile and leave with 8 lanes per row, so one store instruction
+// writes 4 complete lines instead of 32 16-byte fragments (the L2 write-request rate of the row-per-thread layout,
+// 4096 requests per 128x256 bf16 tile, is what bounds the token-major epilogues: 923 vs 1490 TFLOP/s without stores).
+PG_DEVINL void warp_store_rows_128B(uint32_t stage, int lane, const uint32_t (&pk)[32], char* gbase, long long pitch_bytes,
+                                    int rows_valid, bool cols_ok) {
+  __syncwarp();  // the previous user of the tile has read it out
+  const uint32_t my_row = stage + lane * 128;
+#pragma unroll
+  for (int pc = 0; pc < 8; ++pc)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((pc ^ (lane & 7)) << 4)), "r"(pk[4 * pc]),
+                 "r"(pk[4 * pc + 1]), "r"(pk[4 * pc + 2]), "r"(pk[4 * pc + 3]) : "memory");
+  __syncwarp();
+  const int sub = lane >> 3, piece = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r8 = 4 * k + sub;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(stage + r8 * 128 + ((piece ^ (r8 & 7)) << 4)) : "memory");
+    if (cols_ok && r8 < rows_valid) *reinterpret_cast<uint4*>(gbase + r8 * pitch_bytes + piece * 16) = v;
+  }
+}
+
 // Epilogue of one token-major (non-swap) tile for the non-GEGLU modes: thread = token row, columns = features.
 // 64 columns per step: the fp32 residual of the whole step is requested first (16 independent 16-byte loads per thread),
 // then the accumulator is pulled out of TMEM, so that one global round trip covers 64 columns instead of 16 (the
 // residual read is what bounds the short-K GEMMs: out_proj / o_proj).
 template <int BN, int MODE>
-PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int tok, int n0, bool first_split) {
+PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int tok, int n0, bool first_split,
+                                       uint32_t stage, int rows_valid, int lane) {
   constexpr int STEP = BN >= 64 ? 64 : BN;
   constexpr int NCH = STEP / 16;
   const bool row_ok = tok < args.tokens;
@@ -164,8 +205,11 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) tmem_ld16(taddr + c0 + 16 * ch, r[ch]);
     tmem_ld_wait();
-    if (!row_ok) continue;
-    if (full) {
+    // bf16, 64 full columns, aligned rows: warp-collective coalesced store (every lane takes part, valid row or not)
+    const bool collective = MODE == PG_EPI_BF16 && STEP == 64 && __all_sync(0xffffffffu, (f0 + STEP <= args.features) && vec_ok);
+    if (!row_ok && !collective) continue;
+    uint32_t pkc[32];
+    if (full || collective) {
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         float v[16];
@@ -189,9 +233,14 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_fast(v[i]);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(out_bf + f0 + 16 * ch);
-          d4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          d4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          if (collective) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pkc[(8 * ch + i) & 31] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          } else {
+            uint4* d4 = reinterpret_cast<uint4*>(out_bf + f0 + 16 * ch);
+            d4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            d4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          }
         } else if (MODE == PG_EPI_F32) {
           float4* d4 = reinterpret_cast<float4*>(out_f + f0 + 16 * ch);
 #pragma unroll
@@ -208,6 +257,9 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
           for (int i = 0; i < 16; ++i) atomicAdd(out_f + f0 + 16 * ch + i, v[i]);
         }
       }
+      if (collective)
+        warp_store_rows_128B(stage, lane, pkc, reinterpret_cast<char*>(out_bf - static_cast<long long>(lane) * args.ldo + f0),
+                             args.ldo * 2, rows_valid, args.debug_skip_epilogue != 3);
     } else {  // feature tail / unaligned rows: element by element
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -379,7 +431,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       // pipeline stages are fetched BEFORE griddepcontrol.wait, i.e. while the previous kernel is still running.
       int pre = 0;
       if (SWAP && static_cast<int>(blockIdx.x) < num_tiles) {
-        const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k);
+        const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         pre = min(STAGES, t.kb1 - t.kb0);
         for (int s = 0; s < pre; ++s) {
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
@@ -391,7 +443,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       if (tr) args.trace[2] = clock64();  // previous kernel complete
       griddep_launch_dependents();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           if (pre > 0) {  // weights of this stage are already in flight
@@ -415,7 +467,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -448,7 +500,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
     float* out_f = reinterpret_cast<float*>(args.out);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k);
+      const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
       mbar_wait(tfull_bar(acc), acc_phase);
       if (tr && threadIdx.x == 64) args.trace[3] = clock64();  // accumulator ready (first tile)
       tc_fence_after();
@@ -456,45 +508,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int rl = q * 32 + lane;  // row inside the tile
       const bool first_split = (t.kb0 == 0);
 
-      if constexpr (!SWAP) {
+      if (args.debug_skip_epilogue == 1 || args.debug_skip_epilogue == 2) {
+        if (args.debug_skip_epilogue == 2) {
+          uint32_t sink = 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sink ^= r[i];
+          }
+          if (sink == 0x12345678u) reinterpret_cast<uint32_t*>(args.out)[0] = sink;
+        }
+      } else if constexpr (!SWAP) {
         const int tok = t.m_blk * BM + rl;
         const bool row_ok = tok < args.tokens;
+        const uint32_t wstage = smem_base + STAGES * STAGE_BYTES + q * 4096;  // this warp's transposition tile
+        const int rows_valid = max(0, min(32, args.tokens - (t.m_blk * BM + q * 32)));
         if (mode == PG_EPI_GEGLU) {
-          // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c
+          // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c.  The 64 bf16
+          // results of a block (one 128-byte row per token) leave through the warp transposition tile as full lines.
+          const bool al = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo % 8) == 0);
 #pragma unroll 1
           for (int blk = 0; blk < BN / 128; ++blk) {
-#pragma unroll 1
+            const int f0 = t.n_blk * (BN / 2) + blk * 64;
+            if (f0 >= args.features / 2) break;  // warp-uniform (features % 128 == 0)
+            uint32_t pk[32];
+#pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
               uint32_t g[16], u[16];
               tmem_ld16(taddr + blk * 128 + c0, g);
               tmem_ld16(taddr + blk * 128 + 64 + c0, u);
               tmem_ld_wait();
-              const int f0 = t.n_blk * (BN / 2) + blk * 64 + c0;
-              if (row_ok && f0 < args.features / 2) {
-                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float a = gelu_tanh_fast(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
-                  float b = gelu_tanh_fast(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
-                  pk[i] = pack_bf16(a, b);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(out_bf + static_cast<long long>(tok) * args.ldo + f0);
-                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              for (int i = 0; i < 8; ++i) {
+                float a = gelu_tanh_fast(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
+                float b = gelu_tanh_fast(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
+                pk[(c0 / 2 + i) & 31] = pack_bf16(a, b);
               }
+            }
+            if (al) {
+              warp_store_rows_128B(wstage, lane, pk, reinterpret_cast<char*>(out_bf + static_cast<long long>(t.m_blk * BM + q * 32) * args.ldo + f0),
+                                   args.ldo * 2, rows_valid, args.debug_skip_epilogue != 3);
+            } else if (row_ok) {
+              __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(dst + 2 * i) = pk[i];
             }
           }
         } else if (mode == PG_EPI_BF16) {
-          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split);
+          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
         } else if (mode == PG_EPI_F32) {
           // (measured: pulling the NEXT tile's residual rows into L2 from here does not help: o_proj 926 -> 824 TFLOP/s)
           if (args.f32_coalesced)
             rowmajor_tile_epilogue_f32_coalesced<BN>(args, taddr, t.m_blk * BM, t.n_blk * BN, first_split,
-                                                     smem_base + STAGES * STAGE_BYTES + q * 4096, q, lane);
+                                                     wstage, q, lane);
           else
-            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split);
+            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
         } else {
-          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split);
+          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
         }
       } else {
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
@@ -681,6 +754,16 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
   a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
   a.ss_in = ss_in; a.inv_norm_dim = norm_dim > 0 ? 1.0f / static_cast<float>(norm_dim) : 0.f; a.eps = eps;
+  a.n_fast = 0;
+  if (!swap && split_k == 1) {  // DRAM traffic estimate of the two raster orders (100 MB of the 126 MB L2 usable)
+    const double l2 = 100e6, A = 2.0 * tokens * K, Bw = 2.0 * features * K;
+    const int mb = (tokens + BM - 1) / BM;
+    const int nb256 = (features + 255) / 256;
+    const double m_fast = (A > l2 ? A * nb256 : A) + Bw;
+    const double n_fast = A + (Bw > l2 ? Bw * ((static_cast<double>(mb) * nb256 + 147) / 148) : Bw);
+    a.n_fast = n_fast < 0.8 * m_fast ? 1 : 0;
+  }
+  a.debug_skip_epilogue = getenv("PG_DEBUG_SKIP_EPILOGUE") ? atoi(getenv("PG_DEBUG_SKIP_EPILOGUE")) : 0;
   a.f32_coalesced = (!swap && mode == PG_EPI_F32 && (features % 4) == 0 && (ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
                      (resid == nullptr || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0))) ? 1 : 0;

@@ -135,6 +135,8 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
 // -------------------------------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 
+__device__ int g_topp_retries = 0;  // profiling: how often the estimated bracket failed verification
+
 struct TopPShared {
   float h_mass[2048];
   int h_cnt[2048];
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     const bool ok = (sel0 >= 0) && (bh == NB - 1 || S.s_tot_mass > thresh) && (bl == 0 || base_mass <= thresh);
     __syncthreads();
     if (ok) break;
+    if (tid == 0 && rank == 0) atomicAdd(&g_topp_retries, 1);
     bl = 0;
     bh = NB - 1;
   }
@@ -513,6 +516,12 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_debug_topp_retries(void) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, pg::g_topp_retries, sizeof(int));
+  return v;
+}
 
 extern "C" int pg_argmax(const float* logits, long long ld, int* out, int B, int V, void* stream) {
   if (B <= 0 || V <= 0) return PG_ERR_ARG;
