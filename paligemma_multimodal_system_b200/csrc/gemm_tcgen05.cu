@@ -105,20 +105,20 @@ PG_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0,
 // rs_tab: optional per-token factors in shared memory (RMSNorm of the producer), already multiplied by args.scale.
 template <int BN, int MODE>
 PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, int j_base, bool first_split,
-                                  const float* __restrict__ rs_tab) {
+                                  const float* __restrict__ rs_tab, int col_begin = 0, int col_end = BN) {
   const bool f_ok = fr < args.features;
-  const int nvalid = min(BN, args.tokens - j_base);
+  const int nvalid = min(min(BN, col_end), args.tokens - j_base);
   const float scale = args.scale;
   const float bias_s = (args.bias != nullptr && f_ok && first_split) ? __ldg(args.bias + fr) * scale : 0.f;
   constexpr int ESZ = MODE == PG_EPI_BF16 ? 2 : 4;
-  char* dst = reinterpret_cast<char*>(args.out) + (static_cast<long long>(j_base) * args.ldo + fr) * ESZ;
+  char* dst = reinterpret_cast<char*>(args.out) + (static_cast<long long>(j_base + col_begin) * args.ldo + fr) * ESZ;
   const long long step = args.ldo * ESZ;
   const char* res = (MODE == PG_EPI_F32 && args.resid != nullptr)
-                        ? reinterpret_cast<const char*>(args.resid + static_cast<long long>(j_base) * args.ldr + fr) : nullptr;
+                        ? reinterpret_cast<const char*>(args.resid + static_cast<long long>(j_base + col_begin) * args.ldr + fr) : nullptr;
   const long long rstep = args.ldr * 4;
   const bool gelu = MODE == PG_EPI_BF16 && args.act_gelu != 0;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  for (int c0 = col_begin; c0 < BN; c0 += 16) {
     if (c0 >= nvalid) break;  // warp-uniform
     uint32_t r[16];
     tmem_ld16(taddr + c0, r);
@@ -360,10 +360,15 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
   }
 }
 
-template <int BN, bool SWAP>
-__global__ void __launch_bounds__(NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
+// SPLITK = true: swap-AB kernel specialised for the split-K red.add epilogue with EIGHT epilogue warps (two per TMEM lane
+// quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
+// instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
+// red.add epilogue is compiled out, which keeps the 320-thread CTA at two per SM.
+template <int BN, bool SWAP, bool SPLITK = false>
+__global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
+  static_assert(!SPLITK || SWAP, "the 8-warp split-K epilogue exists for the swap-AB kernel only");
   constexpr int STAGES = num_stages(BN, SWAP);
   static_assert(STAGES >= 3, "pipeline too shallow");
   constexpr int STAGE_BYTES = stage_bytes(BN);
@@ -406,7 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), SPLITK ? 8 : 4);
     }
     mbar_fence_init();
   }
@@ -508,7 +513,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int rl = q * 32 + lane;  // row inside the tile
       const bool first_split = (t.kb0 == 0);
 
-      if (args.debug_skip_epilogue == 1 || args.debug_skip_epilogue == 2) {
+      if constexpr (SPLITK) {
+        // eight epilogue warps: warps 2-5 take the token columns [0, BN/2), warps 6-9 the rest (BN >= 32)
+        constexpr int HALF_COLS = BN >= 32 ? BN / 2 : BN;
+        const int half = (warp - 2) >> 2;
+        if (half * HALF_COLS < BN)
+          swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split, nullptr,
+                                                    half * HALF_COLS, (half + 1) * HALF_COLS);
+      } else if (args.debug_skip_epilogue == 1 || args.debug_skip_epilogue == 2) {
         if (args.debug_skip_epilogue == 2) {
           uint32_t sink = 0;
 #pragma unroll 1
@@ -698,22 +710,22 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool SWAP>
+template <int BN, bool SWAP, bool SPLITK = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
   static bool configured = false;
   constexpr int smem = smem_bytes(BN, SWAP);
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();  // do not leave a sticky error behind
       return PG_ERR_CUDA;
     }
     if (getenv("PG_CARVEOUT") != nullptr)
-      cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("PG_CARVEOUT")));
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("PG_CARVEOUT")));
     configured = true;
   }
   const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
   const int grid = num_tiles < slots ? num_tiles : slots;
-  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP>, dim3(grid), dim3(NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess ? PG_OK
+  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess ? PG_OK
                                                                                                                          : PG_ERR_CUDA;
 }
 
@@ -776,6 +788,8 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     if ((rc = make_tmap_2d(&ta, w, features, K, ldw, BM)) != PG_OK) return rc;
     if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
     const int tiles = ((features + BM - 1) / BM) * split_k;
+    static const bool no8 = getenv("PG_NO_SPLITK8") != nullptr;  // A/B switch
+    if (mode == PG_EPI_ATOMIC_F32 && ss_in == nullptr && BN == 64 && !no8) return launch<64, true, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 16: return launch<16, true>(ta, tb, a, tiles, st);
       case 32: return launch<32, true>(ta, tb, a, tiles, st);
