@@ -59,9 +59,9 @@ def peaks():
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (64-token gate||up GEMM) from the committed
-    `ncu --set full` capture (profiles/r01b_decode_gemm_ncu_full.csv, first row), bytes per launch; None if absent."""
+    `ncu --set full` capture (profiles/r01c_decode_gemm_ncu_full.csv, first row), bytes per launch; None if absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01b_decode_gemm_ncu_full.csv")
+    path = os.path.join(ROOT, "profiles", "r01c_decode_gemm_ncu_full.csv")
     try:
         with open(path) as f:
             rows = list(csv.reader(f))

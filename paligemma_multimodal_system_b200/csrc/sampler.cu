@@ -135,7 +135,8 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
 // -------------------------------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 
-__device__ int g_topp_retries = 0;  // profiling: how often the estimated bracket failed verification
+__device__ int g_topp_retries = 0;
+__device__ int g_topp_bracket = 0;   // profiling: > 0 overrides the half-width (in coarse bins) of the estimated bracket  // profiling: how often the estimated bracket failed verification
 
 struct TopPShared {
   float h_mass[2048];
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     merge_hist();
     const int est = scan_select(0.f, 0, top_p * z_est);
     if (est >= 0) {
-      const int D = max(8, static_cast<int>(0.25f * static_cast<float>(NB) / t_cut) + 1);
+      const int D = g_topp_bracket > 0 ? g_topp_bracket : max(8, static_cast<int>(0.25f * static_cast<float>(NB) / t_cut) + 1);
       bl = max(0, est - D);
       bh = min(NB - 1, est + D);
     }
@@ -516,6 +517,10 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_debug_set_topp_bracket(int d) {
+  return cudaMemcpyToSymbol(pg::g_topp_bracket, &d, sizeof(int)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int pg_debug_topp_retries(void) {
   int v = 0;
