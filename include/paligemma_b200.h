@@ -45,6 +45,7 @@ int pg_debug_decode_gemm_blocks_per_sm(int dynamic_smem_bytes); /* prints + retu
 int pg_debug_set_decode_gemm_cta_trace(long long* device_buffer); /* pg_gemm_decode: [grid][3] = smid, globaltimer in / out */
 int pg_debug_decode_gemm_max_clusters(int cluster_k); /* cudaOccupancyMaxActiveClusters of the 64-token decode GEMM */
 int pg_debug_set_topp_bracket(int half_width_bins); /* > 0 overrides the estimated-bracket half width of pg_sample_top_p */
+int pg_debug_topp_trace(long long* host_out16); /* clock64 stamps of CTA 0 after each phase of the last pg_sample_top_p */
 int pg_debug_topp_retries(void); /* rows whose estimated top-p bracket failed verification (second full pass), cumulative */
 int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_decode_fused (8 stamps per launch) */
 

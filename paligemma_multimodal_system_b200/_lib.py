@@ -27,6 +27,7 @@ SIGNATURES = {
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_attn_trace": [p],
     "pg_debug_topp_retries": [],
+    "pg_debug_topp_trace": [p],
     "pg_debug_set_topp_bracket": [i32],
     "pg_debug_set_decode_gemm_cta_trace": [p],
     "pg_debug_decode_gemm_blocks_per_sm": [i32],

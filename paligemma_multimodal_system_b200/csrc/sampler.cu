@@ -136,7 +136,8 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
 namespace cg = cooperative_groups;
 
 __device__ int g_topp_retries = 0;
-__device__ int g_topp_bracket = 0;   // profiling: > 0 overrides the half-width (in coarse bins) of the estimated bracket  // profiling: how often the estimated bracket failed verification
+__device__ int g_topp_bracket = 0;
+__device__ long long g_topp_trace[16];  // profiling: clock64 of CTA 0 / thread 0 after each phase of the last launch   // profiling: > 0 overrides the half-width (in coarse bins) of the estimated bracket  // profiling: how often the estimated bracket failed verification
 
 struct TopPShared {
   float h_mass[2048];
@@ -145,7 +146,7 @@ struct TopPShared {
   int c_sum[2048];
   float seg_kept[32];     // kept mass of each warp's segment
   int seg_cnt[32];
-  float cta_val[4];       // per-CTA scalars published to the cluster: [0] max, [1] below, [2] inside+above (mass), [3] spare
+  float cta_val[4];       // per-CTA scalars published to the cluster: [0] max, [1..3] the sums that ride on merge_hist
   int cta_cnt[2];         // [0] below count
   float cand_w[1024];     // elements of coarse bin sel0: weight, fine bin, owning warp
   short cand_fine[1024];
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     return acc;
   };
 
+  const bool trc = blockIdx.x == 0 && tid == 0;
+  if (trc) g_topp_trace[0] = clock64();
   // ---- P0: row max ----
   float m_loc = -INFINITY;
   for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float v, int) { m_loc = fmaxf(m_loc, v); });
@@ -223,8 +226,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     cluster.sync();
     float acc = -INFINITY;
     for (int r = 0; r < R; ++r) acc = fmaxf(acc, *remote(&S.cta_val[0], r));
-    cluster.sync();
-    m_loc = acc;
+    m_loc = acc;  // (cta_val[0] is never written again in this launch: no second barrier needed)
   }
   const float mx = m_loc;
   const float c = inv_temp * 1.4426950408889634f;  // w = exp((x - mx) * inv_temp) = exp2(x * c - mx * c)
@@ -246,9 +248,16 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     if (tid == 0) S.n_cand = 0;
     __syncthreads();
   };
-  // merged histogram of the cluster (fixed rank order => bitwise identical in every CTA)
-  auto merge_hist = [&]() {
+  // merged histogram of the cluster (fixed rank order => bitwise identical in every CTA).  `nscal` per-CTA scalars
+  // (block-reduced by the caller into S.cta_val[1..nscal]) ride on the same two barriers; their cluster sums land in sums[].
+  float sums[3] = {0.f, 0.f, 0.f};
+  auto merge_hist = [&](int nscal = 0) {
     cluster.sync();
+    for (int k = 0; k < nscal; ++k) {
+      float acc = 0.f;
+      for (int r = 0; r < R; ++r) acc += remote(S.cta_val, r)[1 + k];
+      sums[k] = acc;
+    }
     for (int i = tid; i < NB; i += 1024) {
       float m = 0.f;
       int n = 0;
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     return sel;
   };
 
+  if (trc) g_topp_trace[1] = clock64();
   // ---- PS: subsample -> bracket ----
   int bl = 0, bh = NB - 1;
   if (V >= 16384) {
@@ -309,16 +319,21 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
         }
       }
     }
-    const float z_est = cluster_sum_f(zs, 3);
-    merge_hist();
+    {
+      const float t = block_reduce_sum(zs, S.red);
+      if (tid == 0) S.cta_val[1] = t;
+    }
+    merge_hist(1);
+    const float z_est = sums[0];
     const int est = scan_select(0.f, 0, top_p * z_est);
     if (est >= 0) {
-      const int D = g_topp_bracket > 0 ? g_topp_bracket : max(8, static_cast<int>(0.25f * static_cast<float>(NB) / t_cut) + 1);
+      const int D = g_topp_bracket > 0 ? g_topp_bracket : 8;
       bl = max(0, est - D);
       bh = min(NB - 1, est + D);
     }
   }
 
+  if (trc) g_topp_trace[2] = clock64();
   // ---- P1: exact Z, exact coarse bin (bracket verified, else redone over every bin) ----
   int sel0 = 0;
   float Z = 0.f, thresh = 0.f, base_mass = 0.f;
@@ -351,12 +366,18 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
       wn += __shfl_xor_sync(0xffffffffu, wn, o);
     }
     if (lane == 0) { S.seg_kept[warp] = wm; S.seg_cnt[warp] = wn; }
-    base_mass = cluster_sum_f(m_below, 1);
-    const float rest = cluster_sum_f(m_rest, 2);
-    base_cnt = static_cast<int>(cluster_sum_f(static_cast<float>(n_below), 3) + 0.5f);
+    {
+      const float t1 = block_reduce_sum(m_below, S.red);
+      const float t2 = block_reduce_sum(m_rest, S.red);
+      const float t3 = block_reduce_sum(static_cast<float>(n_below), S.red);
+      if (tid == 0) { S.cta_val[1] = t1; S.cta_val[2] = t2; S.cta_val[3] = t3; }
+    }
+    merge_hist(3);
+    base_mass = sums[0];
+    const float rest = sums[1];
+    base_cnt = static_cast<int>(sums[2] + 0.5f);
     Z = base_mass + rest;
     thresh = top_p * Z;
-    merge_hist();
     sel0 = scan_select(base_mass, base_cnt, thresh);
     const bool ok = (sel0 >= 0) && (bh == NB - 1 || S.s_tot_mass > thresh) && (bl == 0 || base_mass <= thresh);
     __syncthreads();
@@ -371,6 +392,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   int above_cnt = S.s_before_cnt;
   __syncthreads();
 
+  if (trc) g_topp_trace[3] = clock64();
   // ---- P2: bins [bl, sel0) of the bracket are kept; bin sel0 -> fine histogram + candidate list ----
   {
     const float blf = static_cast<float>(bl);
@@ -430,6 +452,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   }
   if (tid == 0 && rank == 0 && want_cnt) kept_count[row_idx] = kept_total_cnt;
 
+  if (trc) g_topp_trace[4] = clock64();
   // ---- P3: pick the segment, walk it ----
   cluster.sync();  // seg_kept of every CTA is final
   const int step = step_ptr ? *step_ptr : 0;
@@ -512,11 +535,16 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
     }
   }
   cluster.sync();  // keep shared memory alive until every CTA has read the segment sums
+  if (trc) g_topp_trace[5] = clock64();
 }
 
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_debug_topp_trace(long long* host_out16) {
+  return cudaMemcpyFromSymbol(host_out16, pg::g_topp_trace, 16 * sizeof(long long)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int pg_debug_set_topp_bracket(int d) {
   return cudaMemcpyToSymbol(pg::g_topp_bracket, &d, sizeof(int)) == cudaSuccess ? 0 : -2;

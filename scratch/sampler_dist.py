@@ -15,6 +15,10 @@ def run(name, logits, reps=20):
     e0.record()
     for _ in range(reps): f()
     e1.record(); torch.cuda.synchronize()
+    import ctypes
+    buf = (ctypes.c_longlong * 16)(); L.pg_debug_topp_trace(ctypes.addressof(buf))
+    ph = [(buf[i + 1] - buf[i]) / 1.9e3 for i in range(5)]
+    print("      phases us: P0 %.1f | PS %.1f | P1 %.1f | P2 %.1f | P3 %.1f" % tuple(ph))
     print(f"{name:28s} {e0.elapsed_time(e1) * 1e3 / reps:7.1f} us   kept median {cnt.float().median().item():9.0f}   retries/launch {(L.pg_debug_topp_retries() - r0) / (reps + 1):5.1f} of {B}")
 import os
 L.pg_debug_set_topp_bracket(int(os.environ.get("BRK", "0")))
