@@ -360,6 +360,87 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
   }
 }
 
+// GeGLU epilogue of a swap-AB tile for ONE group of four epilogue warps that owns CG token columns starting at column
+// `cb` of the tile (CG = BN with four epilogue warps, BN / 2 with eight).  Packed weight rows: [64 gate | 64 up] per
+// 128-row tile, so warps q<2 hold the gate rows and warps q>=2 the matching up rows of the same 64 output features.
+// The two halves of the group's columns are exchanged through shared memory (gate warps finish [0, CG/2), up warps
+// [CG/2, CG)), the bf16 results are transposed through shared memory and leave as 16-byte vectors (one 128-byte row of
+// 64 features per token).  `xg` = the group's exchange area (64 * CG floats), `bar` = its named barrier.
+template <int CG>
+PG_DEVINL void geglu_swap_epilogue_group(const GemmArgs& args, uint32_t taddr, float* xg, int bar, int q, int lane, int et,
+                                         int j0, int m_blk, const float* rs_tab) {
+  constexpr int HB = CG / 2;
+  constexpr int LDN = HB >= 16 ? 16 : 8;
+  __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
+  const bool is_gate = q < 2;
+  const int r = (q * 32 + lane) & 63;
+  float* xsend = xg + (is_gate ? 64 * HB : 0);  // gate warps fill the second half of the area, up warps the first
+  float* xrecv = xg + (is_gate ? 0 : 64 * HB);
+  const int send0 = is_gate ? HB : 0, keep0 = is_gate ? 0 : HB;
+#pragma unroll 1
+  for (int c0 = 0; c0 < HB; c0 += LDN) {
+    if (j0 + send0 + c0 >= args.tokens) break;
+    uint32_t v[16];
+    if constexpr (LDN == 16) tmem_ld16(taddr + send0 + c0, v); else tmem_ld8(taddr + send0 + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < LDN; ++i) xsend[r * HB + ((c0 + i) ^ (r & (HB - 1) & 31))] = __uint_as_float(v[i]);
+  }
+  named_bar_sync(bar, 128);
+  uint32_t pk[HB / 2];
+#pragma unroll
+  for (int c0 = 0; c0 < HB; c0 += LDN) {
+    uint32_t v[16];
+    if (j0 + keep0 + c0 < args.tokens) {
+      if constexpr (LDN == 16) tmem_ld16(taddr + keep0 + c0, v); else tmem_ld8(taddr + keep0 + c0, v);
+      tmem_ld_wait();
+    }
+#pragma unroll
+    for (int i = 0; i < LDN; i += 2) {
+      float res[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float mine = __uint_as_float(v[i + e]);
+        float other = xrecv[r * HB + ((c0 + i + e) ^ (r & (HB - 1) & 31))];
+        if (rs_tab != nullptr) {
+          const float rs = rs_tab[keep0 + c0 + i + e];
+          mine *= rs;
+          other *= rs;
+        }
+        res[e] = is_gate ? gelu_tanh_fast(mine) * other : gelu_tanh_fast(other) * mine;
+      }
+      pk[(c0 + i) / 2] = pack_bf16(res[0], res[1]);
+    }
+  }
+  named_bar_sync(bar, 128);  // every exchange value has been consumed: the area is reused for the transposed tile
+  __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(xg);  // [CG tokens][64 features]
+#pragma unroll
+  for (int c = 0; c < HB; c += 2) {
+    const __nv_bfloat162 two = *reinterpret_cast<const __nv_bfloat162*>(&pk[c / 2]);
+    out_s[(keep0 + c) * 64 + r] = two.x;
+    out_s[(keep0 + c + 1) * 64 + r] = two.y;
+  }
+  named_bar_sync(bar, 128);
+  {
+    const int f0 = m_blk * 64;
+    if (f0 < args.features / 2) {
+#pragma unroll 1
+      for (int pc = et; pc < CG * 8; pc += 128) {
+        const int j = j0 + (pc >> 3), part = pc & 7;
+        if (j < args.tokens)
+          *reinterpret_cast<uint4*>(out_bf + static_cast<long long>(j) * args.ldo + f0 + part * 8) =
+              *reinterpret_cast<const uint4*>(out_s + (pc >> 3) * 64 + part * 8);
+      }
+    }
+  }
+  named_bar_sync(bar, 128);
+}
+template <int BN>
+PG_DEVINL void geglu_swap_epilogue(const GemmArgs& args, uint32_t taddr, float* xch, int bar, int q, int lane, int et,
+                                   int j_base, int m_blk, const float* rs_tab) {
+  geglu_swap_epilogue_group<BN>(args, taddr, xch, bar, q, lane, et, j_base, m_blk, rs_tab);
+}
+
 // SPLITK = true: swap-AB kernel specialised for the split-K red.add epilogue with EIGHT epilogue warps (two per TMEM lane
 // quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
@@ -517,9 +598,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // eight epilogue warps: warps 2-5 take the token columns [0, BN/2), warps 6-9 the rest (BN >= 32)
         constexpr int HALF_COLS = BN >= 32 ? BN / 2 : BN;
         const int half = (warp - 2) >> 2;
-        if (half * HALF_COLS < BN)
+        if (mode == PG_EPI_GEGLU) {
+          if constexpr (BN >= 32)
+            geglu_swap_epilogue_group<HALF_COLS>(args, taddr + half * HALF_COLS, xch + half * 64 * HALF_COLS, 1 + half, q, lane,
+                                                 ((warp - 2) & 3) * 32 + lane, t.n_blk * BN + half * HALF_COLS, t.m_blk, nullptr);
+        } else if (half * HALF_COLS < BN) {
           swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split, nullptr,
                                                     half * HALF_COLS, (half + 1) * HALF_COLS);
+        }
       } else if (args.debug_skip_epilogue == 1 || args.debug_skip_epilogue == 2) {
         if (args.debug_skip_epilogue == 2) {
           uint32_t sink = 0;
@@ -599,75 +685,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           rs_tab = tab;
         }
         if (mode == PG_EPI_GEGLU) {
-          // Packed rows: [64 gate | 64 up] per 128-row tile, so warps q<2 hold the gate rows and warps q>=2 the matching
-          // up rows of the same 64 output features.  The two halves of the token columns are exchanged through shared
-          // memory (gate warps finish columns [0, BN/2), up warps finish [BN/2, BN)), the bf16 results are transposed
-          // through shared memory and leave as 16-byte vectors (one 128-byte row of 64 features per token).
-          constexpr int HB = BN / 2;
-          constexpr int LDN = HB >= 16 ? 16 : 8;
-          const bool is_gate = q < 2;
-          const int r = rl & 63;
-          float* xsend = xch + (is_gate ? 64 * HB : 0);  // gate warps fill xch_g (second half), up warps xch_u
-          float* xrecv = xch + (is_gate ? 0 : 64 * HB);
-          const int send0 = is_gate ? HB : 0, keep0 = is_gate ? 0 : HB;
-#pragma unroll 1
-          for (int c0 = 0; c0 < HB; c0 += LDN) {
-            if (j_base + send0 + c0 >= args.tokens) break;
-            uint32_t v[16];
-            if constexpr (LDN == 16) tmem_ld16(taddr + send0 + c0, v); else tmem_ld8(taddr + send0 + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < LDN; ++i) xsend[r * HB + ((c0 + i) ^ (r & (HB - 1) & 31))] = __uint_as_float(v[i]);
-          }
-          named_bar_sync(1, 128);
-          uint32_t pk[HB / 2];
-#pragma unroll
-          for (int c0 = 0; c0 < HB; c0 += LDN) {
-            uint32_t v[16];
-            if (j_base + keep0 + c0 < args.tokens) {
-              if constexpr (LDN == 16) tmem_ld16(taddr + keep0 + c0, v); else tmem_ld8(taddr + keep0 + c0, v);
-              tmem_ld_wait();
-            }
-#pragma unroll
-            for (int i = 0; i < LDN; i += 2) {
-              float res[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                float mine = __uint_as_float(v[i + e]);
-                float other = xrecv[r * HB + ((c0 + i + e) ^ (r & (HB - 1) & 31))];
-                if (rs_tab != nullptr) {
-                  const float rs = rs_tab[keep0 + c0 + i + e];
-                  mine *= rs;
-                  other *= rs;
-                }
-                res[e] = is_gate ? gelu_tanh_fast(mine) * other : gelu_tanh_fast(other) * mine;
-              }
-              pk[(c0 + i) / 2] = pack_bf16(res[0], res[1]);
-            }
-          }
-          named_bar_sync(1, 128);  // every exchange value has been consumed: the area is reused for the transposed tile
-          __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(xch);  // [BN tokens][64 features]
-#pragma unroll
-          for (int c = 0; c < HB; c += 2) {
-            const __nv_bfloat162 two = *reinterpret_cast<const __nv_bfloat162*>(&pk[c / 2]);
-            out_s[(keep0 + c) * 64 + r] = two.x;
-            out_s[(keep0 + c + 1) * 64 + r] = two.y;
-          }
-          named_bar_sync(1, 128);
-          {
-            const int et = (warp - 2) * 32 + lane;  // 0..127
-            const int f0 = t.m_blk * 64;
-            if (f0 < args.features / 2) {
-#pragma unroll 1
-              for (int pc = et; pc < BN * 8; pc += 128) {
-                const int j = j_base + (pc >> 3), part = pc & 7;
-                if (j < args.tokens)
-                  *reinterpret_cast<uint4*>(out_bf + static_cast<long long>(j) * args.ldo + f0 + part * 8) =
-                      *reinterpret_cast<const uint4*>(out_s + (pc >> 3) * 64 + part * 8);
-              }
-            }
-          }
-          named_bar_sync(1, 128);
+          geglu_swap_epilogue<BN>(args, taddr, xch, 1, q, lane, (warp - 2) * 32 + lane, j_base, t.m_blk, rs_tab);
         } else {
           // (measured: 16-byte REDG.F32x4 after a lane-quad transpose is ~2x SLOWER here than 4-byte coalesced reds)
           if (mode == PG_EPI_ATOMIC_F32) swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, fr, j_base, first_split, rs_tab);
@@ -789,7 +807,8 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
     const int tiles = ((features + BM - 1) / BM) * split_k;
     static const bool no8 = getenv("PG_NO_SPLITK8") != nullptr;  // A/B switch
-    if (mode == PG_EPI_ATOMIC_F32 && ss_in == nullptr && BN == 64 && !no8) return launch<64, true, true>(ta, tb, a, tiles, st);
+    if ((mode == PG_EPI_ATOMIC_F32 || mode == PG_EPI_GEGLU) && ss_in == nullptr && BN == 64 && !no8)
+      return launch<64, true, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 16: return launch<16, true>(ta, tb, a, tiles, st);
       case 32: return launch<32, true>(ta, tb, a, tiles, st);
