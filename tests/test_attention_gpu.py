@@ -147,3 +147,31 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
         assert torch.equal(v_pages[pg_, off], vn.bfloat16())
     changed = (k_pages != k_before).any(-1).sum().item()
     assert changed <= B
+
+
+@pytest.mark.parametrize("B,H,N,dh,group", [(1, 16, 4096, 72, 1), (1, 1, 4100, 256, 8), (2, 2, 333, 64, 4), (1, 3, 129, 72, 1)])
+def test_prefill_attention_tcgen05_long_and_ragged(B, H, N, dh, group):
+    """tcgen05 / TMEM prefill attention at the 896-px lengths (many key tiles: lazy running-max rescale, ring reuse) and
+    at lengths that are not multiples of the 128-row / 64-128-key tiles; GQA rows stacked per token (group)."""
+    from paligemma_multimodal_system_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = (torch.randn(B, N, H, group, dh, device="cuda", generator=g) * 0.8).bfloat16()
+    k = (torch.randn(B, N, H, dh, device="cuda", generator=g) * 0.8).bfloat16()
+    v = (torch.randn(B, N, H, dh, device="cuda", generator=g) * 0.8).bfloat16()
+    # a few large-magnitude keys late in the sequence force the running maximum to move (O rescale path)
+    k[:, N // 2, :, :] *= 6.0
+    k[:, N - 3, :, :] *= 9.0
+    out = torch.full((B, N, H, group, dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = dh ** -0.5
+    rc = _lib.lib().pg_attention_prefill(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, N * group, N, dh, group,
+        N * H * group * dh, H * group * dh, dh, group * dh, N * H * dh, H * dh, dh,
+        N * H * group * dh, H * group * dh, dh, group * dh, scale, _lib.stream())
+    _lib.check(rc, "attn")
+    torch.cuda.synchronize()
+    qf = q.float().permute(0, 2, 3, 1, 4)                    # [B,H,G,N,dh]
+    kf = k.float().permute(0, 2, 1, 3).unsqueeze(2)          # [B,H,1,N,dh]
+    vf = v.float().permute(0, 2, 1, 3).unsqueeze(2)
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf   # [B,H,G,N,dh]
+    ref = ref.permute(0, 3, 1, 2, 4)
+    _close(out, ref, 2e-2, "tcgen05 prefill attention")

@@ -126,3 +126,31 @@ def test_gemm_rejects_bad_args():
     out = torch.empty(16, 64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         _lib.gemm(x, w, out, mode=_lib.EPI_BF16)
+
+
+@pytest.mark.parametrize("T,F,K,resid", [(16500, 1152, 4304, True), (16640, 2048, 6400, True), (16390, 1152, 4304, False)])
+def test_gemm_prefill_n_fast_raster_f32(T, F, K, resid):
+    """Large activation matrix (> 100 MB) x small weight matrix: the persistent grid walks feature tiles first
+    (decode_tile n_fast) and the fp32 epilogue goes through the coalescing transposition tile; token tail not a multiple
+    of 128."""
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K, 11)
+    bias = torch.randn(F, device="cuda")
+    r = torch.randn(T, F, device="cuda") if resid else None
+    out = r.clone() if resid else torch.full((T, F), float("nan"), device="cuda")
+    ref = _ref(x, w) + bias + (r if resid else 0)
+    _lib.gemm(x, w, out, mode=_lib.EPI_F32, bias=bias, resid=out if resid else None, swap=0)
+    torch.cuda.synchronize()
+    _close(out, ref, 2e-3, "n-fast f32")
+
+
+@pytest.mark.parametrize("T,F,K", [(33000, 2560, 2048), (16400, 3456, 1152)])
+def test_gemm_prefill_bf16_coalesced_store(T, F, K):
+    """bf16 epilogue through the warp transposition tile (full 128-byte lines), with bias + gelu and a token tail."""
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K, 12)
+    bias = torch.randn(F, device="cuda") * 0.2
+    out = torch.full((T, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.gemm(x, w, out, mode=_lib.EPI_BF16, bias=bias, act_gelu=True, swap=0)
+    torch.cuda.synchronize()
+    _close(out, torch.nn.functional.gelu(_ref(x, w) + bias, approximate="tanh"), 1e-2, "bf16 coalesced + gelu")
