@@ -5,6 +5,7 @@
 // whose bins accumulate probability MASS); the token is then drawn by inverse CDF over the kept set in vocabulary order
 // with a counter-based RNG.  One CTA per row; the row (1 MB at V = 257 216) stays L2 resident across the passes.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "paligemma_b200.h"
@@ -538,6 +539,193 @@ __global__ void __launch_bounds__(1024) sample_top_p_kernel(const float* __restr
   if (trc) g_topp_trace[5] = clock64();
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// top-p by rejection (used when the caller does not ask for the kept-set size): a token drawn from the FULL softmax and
+// accepted iff it lies in the kept set {t : mass of strictly more probable tokens <= top_p * Z} is distributed exactly as
+// the renormalised kept set of inference.py:90-106.  The kept set carries >= top_p of the mass, so a candidate is accepted
+// with probability >= top_p; four independent candidates are verified in one pass (all four rejected: <= 1e-4 at
+// top_p = 0.9, then four more are drawn).  Three passes over the row, no histogram, no shared-memory atomics:
+//   P0 row max   P1 per-warp segment masses (-> Z, inverse-CDF draw of the candidates, their warps walk 1/64 of the row)
+//   P2 mass strictly above each candidate's logit -> first accepted candidate wins.
+// One cluster of R CTAs per row; every element is weighted by ONE float expression in all passes.
+// -------------------------------------------------------------------------------------------------------------------
+struct RejShared {
+  BlockRed red;
+  float seg[32];        // this CTA's per-warp segment masses (read remotely)
+  float all_seg[256];   // every segment of the row, gathered locally
+  float cta_max;        // published
+  float cand_x[4];      // candidate logits (written by the owning warp into EVERY rank)
+  int cand_i[4];        // candidate token ids
+  float mass[4];        // this CTA's mass strictly above each candidate (published)
+  float target[4], toff[4];
+  int tseg[4];
+  float z;
+  int accepted;
+};
+
+__global__ void __launch_bounds__(1024) sample_top_p_rej_kernel(const float* __restrict__ logits, long long ld, int* __restrict__ out,
+                                                                int V, float inv_temp, float top_p, unsigned long long seed,
+                                                                const int* __restrict__ step_ptr) {
+  __shared__ RejShared S;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int R = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int row_idx = blockIdx.x / R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ row = logits + row_idx * ld;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
+
+  const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int nseg = R * 32;
+  const int seg_len = ((V + nseg - 1) / nseg + 127) / 128 * 128;
+  const int seg = rank * 32 + warp;
+  const int seg_lo = min(V, seg * seg_len), seg_hi = min(V, seg_lo + seg_len);
+  auto remote = [&](auto* ptr, int r) { return cluster.map_shared_rank(ptr, r); };
+
+  // ---- P0: row max ----
+  float mx = -INFINITY;
+  for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float v, int) { mx = fmaxf(mx, v); });
+  {
+    const float t = block_reduce_max(mx, S.red);
+    if (tid == 0) S.cta_max = t;
+    cluster.sync();
+    float acc = -INFINITY;
+    for (int r = 0; r < R; ++r) acc = fmaxf(acc, *remote(&S.cta_max, r));
+    mx = acc;
+  }
+  const float c = inv_temp * 1.4426950408889634f;  // w = exp((x - mx) * inv_temp) = exp2(x * c - mx * c)
+  const float cm = mx * c;
+  auto w_of = [&](float x) { return exp2f(fmaf(x, c, -cm)); };
+
+  // ---- P1: segment masses ----
+  {
+    float m = 0.f;
+    for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int) { m += w_of(x); });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0) S.seg[warp] = m;
+  }
+  cluster.sync();
+  if (tid < nseg) S.all_seg[tid] = remote(S.seg, tid >> 5)[tid & 31];
+  __syncthreads();
+  if (tid == 0) {
+    float z = 0.f;
+    for (int sg = 0; sg < nseg; ++sg) z += S.all_seg[sg];
+    S.z = z;
+    S.accepted = -1;
+  }
+  __syncthreads();
+  const float Z = S.z;
+  const int step = step_ptr ? *step_ptr : 0;
+  const uint64_t base_rnd = splitmix64(seed ^ splitmix64((static_cast<uint64_t>(step) << 32) | static_cast<uint32_t>(row_idx)));
+
+  for (int round = 0; round < 64; ++round) {
+    // ---- draw four candidates from the full distribution (inverse CDF over the segment masses, same in every rank) ----
+    if (tid < 4) {
+      const uint64_t rnd = splitmix64(base_rnd + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(4 * round + tid + 1));
+      const float u01 = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
+      const float target = u01 * Z;
+      int tseg = -1, last_nonempty = -1;
+      float toff = 0.f, last_off = 0.f, acc = 0.f;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const float v = S.all_seg[sg];
+        if (v > 0.f) { last_nonempty = sg; last_off = acc; }
+        if (tseg < 0 && v > 0.f && target < acc + v) { tseg = sg; toff = acc; }
+        acc += v;
+      }
+      if (tseg < 0) { tseg = last_nonempty; toff = last_off; }
+      S.tseg[tid] = tseg;
+      S.toff[tid] = toff;
+      S.target[tid] = target;
+    }
+    __syncthreads();
+    // ---- the warps that own the target segments walk them; the result goes to every rank ----
+    for (int k = 0; k < 4; ++k) {
+      if (S.tseg[k] != seg) continue;  // warp-uniform
+      const float target = S.target[k];
+      float acc2 = S.toff[k];
+      int found = -1, last_el = -1;
+      for (int base = seg_lo; base < seg_hi && found < 0; base += 128) {
+        const int i0 = base + lane * 4;
+        float w[4];
+        float lsum = 0.f;
+        int lk = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = i0 + j < seg_hi;
+          w[j] = ok ? w_of(row[i0 + j]) : -1.f;  // -1 marks "no element"
+          if (ok) { lk = i0 + j; lsum += w[j]; }
+        }
+        float inc = lsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const bool hit = (lk >= 0) && (target < acc2 + inc);
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        const uint32_t has = __ballot_sync(0xffffffffu, lk >= 0);
+        if (has) last_el = __shfl_sync(0xffffffffu, lk, 31 - __clz(has));
+        if (hits) {
+          const int hl = __ffs(hits) - 1;
+          float a = acc2 + inc - lsum;
+          int f = -1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (f < 0 && w[j] >= 0.f) {
+              a += w[j];
+              if (target < a) f = i0 + j;
+            }
+          }
+          if (f < 0) f = lk;
+          found = __shfl_sync(0xffffffffu, f, hl);
+        }
+        acc2 += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (found < 0) found = last_el;
+      if (lane < R) {
+        *remote(&S.cand_x[k], lane) = row[found];
+        *remote(&S.cand_i[k], lane) = found;
+      }
+    }
+    cluster.sync();
+    // ---- P2: mass strictly above each candidate ----
+    const float cx0 = S.cand_x[0], cx1 = S.cand_x[1], cx2 = S.cand_x[2], cx3 = S.cand_x[3];
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int) {
+      const float w = w_of(x);
+      m0 += x > cx0 ? w : 0.f;
+      m1 += x > cx1 ? w : 0.f;
+      m2 += x > cx2 ? w : 0.f;
+      m3 += x > cx3 ? w : 0.f;
+    });
+    {
+      const float t0 = block_reduce_sum(m0, S.red), t1 = block_reduce_sum(m1, S.red);
+      const float t2 = block_reduce_sum(m2, S.red), t3 = block_reduce_sum(m3, S.red);
+      if (tid == 0) { S.mass[0] = t0; S.mass[1] = t1; S.mass[2] = t2; S.mass[3] = t3; }
+    }
+    cluster.sync();
+    if (tid == 0) {
+      int acc_k = -1;
+      for (int k = 0; k < 4 && acc_k < 0; ++k) {
+        float above = 0.f;
+        for (int r = 0; r < R; ++r) above += remote(S.mass, r)[k];
+        if (above <= top_p * Z) acc_k = k;  // (the most probable token always passes: nothing lies above it)
+      }
+      S.accepted = acc_k;
+    }
+    __syncthreads();
+    const int acc_k = S.accepted;
+    cluster.sync();  // every rank has read the published masses / candidates before the next round overwrites them
+    if (acc_k >= 0) {
+      if (tid == 0 && rank == 0) out[row_idx] = S.cand_i[acc_k];
+      break;
+    }
+  }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -569,6 +757,8 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
   // cluster of R CTAs per row: enough CTAs to cover the GPU when the batch alone cannot
   int R = 1;
   if (V >= 65536) R = 2;  // (64 regs x 1024 threads = one CTA per SM: 2 x 64 rows covers 128 of the 148 SMs)
+  static const bool force_hist = getenv("PG_TOPP_HIST") != nullptr;  // A/B switch: the histogram-select kernel
+  const bool rejection = kept_count == nullptr && !force_hist && top_p > 0.f;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(B) * R);
   cfg.blockDim = dim3(1024);
@@ -584,6 +774,9 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
   cfg.attrs = attr;
   cfg.numAttrs = pg_pdl_enabled() ? 2 : 1;
   pg_count_launch(1);
+  if (rejection)
+    return cudaLaunchKernelEx(&cfg, sample_top_p_rej_kernel, logits, ld, out, V, inv_temperature, top_p, seed, step_ptr) == cudaSuccess
+               ? PG_OK : PG_ERR_CUDA;
   return cudaLaunchKernelEx(&cfg, sample_top_p_kernel, logits, ld, out, kept_count, V, inv_temperature, top_p, seed, step_ptr) ==
                  cudaSuccess
              ? PG_OK
