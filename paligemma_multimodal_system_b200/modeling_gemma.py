@@ -381,6 +381,10 @@ class GemmaForCausalLM(nn.Module):
         sp_qkv = _pick_split((W + 127) // 128, D // 64)
         sp_o = _pick_split((D + 127) // 128, D // 64)
         sp_down = _pick_split((D + 127) // 128, F // 64, sms=296)
+        if getattr(self, "deterministic_decode", False):
+            # one CTA per output tile: the fp32 red.add has a single writer per element, so the step is bitwise
+            # reproducible run to run (the split-K partials otherwise arrive in a different order every launch)
+            sp_qkv = sp_o = sp_down = 1
         for li, lw in enumerate(pk["layers"]):
             _lib.rmsnorm(h, lw["ln1"], hn, zero_buf=qkv)
             _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)

@@ -140,9 +140,12 @@ def test_batched_generate_rows_equal_single_row_runs():
 
 
 def test_sampled_generate_stays_in_reference_kept_set():
-    # R1: well conditioned, so the run-to-run fp32 red.add ordering of the split-K GEMMs cannot flip a sample
     sd = make_state_dict(TINY_CONFIG, "R1", seed=3)
     model = build_model(TINY_CONFIG, sd)
+    # bitwise reproducible decode (no split-K): the fp32 red.add order of the split-K GEMMs changes the logits in the last
+    # bits from launch to launch, and an inverse-CDF draw sits within that distance of one of its V boundaries about once
+    # per thousand draws, which would make the a == b check below flaky
+    model.language_model.deterministic_decode = True
     inp = make_inputs(TINY_CONFIG, batch=4, prompt_len=5, seed=9)
     a = model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), 12, do_sample=True, seed=7)
     b = model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), 12, do_sample=True, seed=7)
