@@ -29,8 +29,8 @@ constexpr int ACC_STAGES = 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
 __host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
-// swap: GeGLU exchange area + per-token factors; token-major: four warp-private 4 KB transposition tiles (fp32 epilogue)
-__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 4 * 4096; }
+// swap: GeGLU exchange area + per-token factors; token-major: eight warp-private 4 KB transposition tiles (coalescing epilogues)
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 8 * 4096; }
 // decode (SWAP, BN <= 64): two CTAs per SM (115712 B each) so that, with programmatic dependent launch, the next
 // kernel's CTAs become resident and prefetch their weights while this kernel drains; otherwise one CTA with <= 200 KB
 __host__ __device__ constexpr bool two_per_sm(int BN, bool swap) { return swap && BN <= 64; }
@@ -176,7 +176,7 @@ PG_DEVINL void warp_store_rows_128B(uint32_t stage, int lane, const uint32_t (&p
 // residual read is what bounds the short-K GEMMs: out_proj / o_proj).
 template <int BN, int MODE>
 PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int tok, int n0, bool first_split,
-                                       uint32_t stage, int rows_valid, int lane) {
+                                       uint32_t stage, int rows_valid, int lane, int c_begin = 0, int c_end = BN) {
   constexpr int STEP = BN >= 64 ? 64 : BN;
   constexpr int NCH = STEP / 16;
   const bool row_ok = tok < args.tokens;
@@ -192,7 +192,7 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
                                              (res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0));
   const bool bias_vec = has_bias && ((reinterpret_cast<uintptr_t>(args.bias) & 15) == 0);
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += STEP) {
+  for (int c0 = c_begin; c0 < c_end; c0 += STEP) {
     const int f0 = n0 + c0;
     if (f0 >= args.features) break;  // warp-uniform
     const bool full = (f0 + STEP <= args.features) && vec_ok;
@@ -292,14 +292,14 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
 // The residual of slice s+1 is requested before slice s is finished.  Needs features % 4 == 0 and 16 B aligned rows.
 template <int BN>
 PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32_t taddr, int m0, int n0, bool first_split,
-                                                    uint32_t stage, int q, int lane) {
+                                                    uint32_t stage, int q, int lane, int sl_begin = 0, int sl_end = BN / 32) {
   const float scale = args.scale;
   const bool has_bias = args.bias != nullptr && first_split;
   float* out = reinterpret_cast<float*>(args.out);
   const float* res = args.resid;
   const int row_base = m0 + q * 32;
   const int sub = lane >> 3, piece = lane & 7;
-  const int nsl = (min(BN, args.features - n0) + 31) / 32;
+  const int nsl = min(sl_end, (min(BN, args.features - n0) + 31) / 32);
   auto load_res = [&](int sl, float4 (&dst)[8]) {
     const int col = n0 + sl * 32 + piece * 4;
     const bool col_ok = col < args.features;
@@ -313,9 +313,9 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
   float4 rr[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (res != nullptr) load_res(0, rr);
+  if (res != nullptr && sl_begin < nsl) load_res(sl_begin, rr);
 #pragma unroll 1
-  for (int sl = 0; sl < nsl; ++sl) {
+  for (int sl = sl_begin; sl < nsl; ++sl) {
     uint32_t a0[16], a1[16];
     tmem_ld16(taddr + sl * 32, a0);
     tmem_ld16(taddr + sl * 32 + 16, a1);
@@ -449,7 +449,8 @@ template <int BN, bool SWAP, bool SPLITK = false>
 __global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
-  static_assert(!SPLITK || SWAP, "the 8-warp split-K epilogue exists for the swap-AB kernel only");
+  // (token-major kernel: SPLITK = true selects the same 320-thread shape, eight epilogue warps that split the columns;
+  //  it pays for the short-K SigLIP GEMMs whose epilogue outlasts the main loop, and costs registers on the long-K ones)
   constexpr int STAGES = num_stages(BN, SWAP);
   static_assert(STAGES >= 3, "pipeline too shallow");
   constexpr int STAGE_BYTES = stage_bytes(BN);
@@ -594,7 +595,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int rl = q * 32 + lane;  // row inside the tile
       const bool first_split = (t.kb0 == 0);
 
-      if constexpr (SPLITK) {
+      if constexpr (SPLITK && SWAP) {
         // eight epilogue warps: warps 2-5 take the token columns [0, BN/2), warps 6-9 the rest (BN >= 32)
         constexpr int HALF_COLS = BN >= 32 ? BN / 2 : BN;
         const int half = (warp - 2) >> 2;
@@ -622,14 +623,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       } else if constexpr (!SWAP) {
         const int tok = t.m_blk * BM + rl;
         const bool row_ok = tok < args.tokens;
-        const uint32_t wstage = smem_base + STAGES * STAGE_BYTES + q * 4096;  // this warp's transposition tile
+        // eight epilogue warps: two per TMEM lane quadrant, each takes half of the tile's columns
+        const int half = SPLITK ? ((warp - 2) >> 2) : 0;
+        const uint32_t wstage = smem_base + STAGES * STAGE_BYTES + (warp - 2) * 4096;  // this warp's transposition tile
         const int rows_valid = max(0, min(32, args.tokens - (t.m_blk * BM + q * 32)));
+        // column range of this warp: halves of >= 64 columns (BN = 64: the first warp of the pair takes everything)
+        const int cb = !SPLITK ? 0 : (BN >= 128 ? half * (BN / 2) : (half == 0 ? 0 : BN));
+        const int ce = !SPLITK ? BN : (BN >= 128 ? cb + BN / 2 : BN);
         if (mode == PG_EPI_GEGLU) {
           // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c.  The 64 bf16
           // results of a block (one 128-byte row per token) leave through the warp transposition tile as full lines.
           const bool al = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo % 8) == 0);
 #pragma unroll 1
-          for (int blk = 0; blk < BN / 128; ++blk) {
+          for (int blk = ((SPLITK && BN >= 256) ? half : 0); blk < ((SPLITK && BN >= 256) ? half + 1 : (half == 0 ? BN / 128 : 0)); ++blk) {
             const int f0 = t.n_blk * (BN / 2) + blk * 64;
             if (f0 >= args.features / 2) break;  // warp-uniform (features % 128 == 0)
             uint32_t pk[32];
@@ -656,16 +662,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             }
           }
         } else if (mode == PG_EPI_BF16) {
-          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
+          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
         } else if (mode == PG_EPI_F32) {
           // (measured: pulling the NEXT tile's residual rows into L2 from here does not help: o_proj 926 -> 824 TFLOP/s)
           if (args.f32_coalesced)
             rowmajor_tile_epilogue_f32_coalesced<BN>(args, taddr, t.m_blk * BM, t.n_blk * BN, first_split,
-                                                     wstage, q, lane);
+                                                     wstage, q, lane, cb / 32, ce / 32);
           else
-            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
+            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
         } else {
-          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane);
+          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
         }
       } else {
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
@@ -829,6 +835,9 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
     const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;
+    // short reduction (K <= 1536: the SigLIP projections): the epilogue outlasts the main loop, so it gets eight warps
+    static const bool no8p = getenv("PG_NO_PREFILL_EPI8") != nullptr;
+    if (BN == 256 && K <= 1536 && !no8p) return launch<256, false, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 64: return launch<64, false>(ta, tb, a, tiles, st);
       case 128: return launch<128, false>(ta, tb, a, tiles, st);
