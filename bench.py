@@ -49,12 +49,26 @@ def algorithmic_bytes_per_decode_step(cfg, batch, kv_len_avg):
     return weights + kv_read + kv_write
 
 
+def algorithmic_flops_per_image(cfg, S):
+    """full non-causal attention as in the reference, last-position lm_head only."""
+    vc, tc = cfg["vision_config"], cfg["text_config"]
+    Dv, Fv, Lv = vc["hidden_size"], vc["intermediate_size"], vc["num_hidden_layers"]
+    N = (vc["image_size"] // vc["patch_size"]) ** 2
+    D, F, L, V = tc["hidden_size"], tc["intermediate_size"], tc["num_hidden_layers"], tc["vocab_size"]
+    Hq, Hkv, dh = tc["num_attention_heads"], tc["num_key_value_heads"], tc["head_dim"]
+    siglip = N * (2 * 3 * vc["patch_size"] ** 2 * Dv + Lv * (2 * (4 * Dv * Dv + 2 * Dv * Fv) + 4 * N * Dv))
+    proj = N * 2 * Dv * D
+    gemma = S * L * (2 * (Hq * dh * D + 2 * Hkv * dh * D + D * D + 3 * D * F) + 4 * S * Hq * dh)
+    head = 2 * D * V
+    return float(siglip + proj + gemma + head)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("bf16_tflops_sustained", 1400.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1400.0
 
 
 def ncu_traffic_per_launch():
@@ -307,7 +321,7 @@ def main():
         K = args.steps
         dec_steps = T - 1
         decode_tok_s = K * B * dec_steps * world / (dec_ms / 1e3)
-        hbm_peak, peak_src = peaks()
+        hbm_peak, peak_src, tf_peak = peaks()
         step_bytes = algorithmic_bytes_per_decode_step(cfg, B, S + T / 2)
         step_ms = dec_ms / (K * dec_steps)
         step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
@@ -333,6 +347,11 @@ def main():
                          "us_per_launch": 1e3 * k_ms, "algorithmic_bytes": k_bytes},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                               "algorithmic_bytes": step_bytes},
+            "roofline_prefill": {"bound": "tensor", "achieved": algorithmic_flops_per_image(cfg, S) / (pre_ms / (K * B) * 1e-3) / 1e12,
+                                 "peak": tf_peak, "unit": "TFLOP/s",
+                                 "frac": algorithmic_flops_per_image(cfg, S) / (pre_ms / (K * B) * 1e-3) / 1e12 / tf_peak,
+                                 "algorithmic_flops_per_image": algorithmic_flops_per_image(cfg, S),
+                                 "peak_source": peak_src + " bf16_tflops_sustained (cuBLAS, seconds-long loop)"},
             "steady_state_decode": None if steady_ms <= 0 else {
                 "ms_per_token_step": steady_ms, "tokens_per_s": B * world / (steady_ms / 1e3),
                 "frac_of_hbm_peak": step_bytes / (steady_ms * 1e-3) / 1e9 / hbm_peak,
