@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(256) attn_decode_v3_kernel(const __grid_consta
   // byte offset of element (row r, column c) inside a swizzled K (or V) page
   auto swz = [&](int r, int c) -> int { return (c >> 6) * BOX_BYTES + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
 
+  // (measured, not kept: computing sincos before the wait, and signalling the rank merge through per-rank mbarriers
+  //  instead of the cluster barrier -- the cluster-scope release of the pushed partials costs the ~1.5 us, not the barrier)
   griddep_wait();  // the qkv row of the new token
   if (tr) trp[1] = clock64();
   if (threadIdx.x == 0) griddep_launch_dependents();
