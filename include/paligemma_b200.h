@@ -112,6 +112,19 @@ int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, fl
  * mode 0 = prefetch.global.L2, 1 = cp.async.bulk.prefetch.L2, 2 = ld.global.cg + discard; `ctas` blocks of 256 threads. */
 int pg_prefetch_l2(const void* ptr, long long bytes, int mode, int ctas, void* stream);
 
+/*
+ * Image path of PaliGemmaProcessor (processing_paligemma.py:13-73) on the GPU, bit-exact with the reference's CPU path:
+ * Pillow's 8-bit bicubic resize as two separable fixed-point passes, then rescale / normalise / HWC->CHW.
+ *   pg_resample_h_u8:      src uint8 [H, W, 3] -> dst uint8 [H, S, 3]     (image.resize, horizontal pass, :17-19)
+ *   pg_resample_v_u8_norm: src uint8 [H, Wd, 3] -> out fp32 [3, S, Wd]    (vertical pass + lut[256] = the reference's
+ *                          (u * 1/255).astype(float32), (x - 0.5) / 0.5 of :21-33, + the transpose of :71)
+ * kk int32 [S, ksize] 22-bit fixed-point weights and bounds int32 [S, 2] = (first input index, count) are built by the
+ * host exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc do (image_preprocess.py).
+ */
+int pg_resample_h_u8(const void* src, void* dst, int H, int W, int S, const int* kk, const int* bounds, int ksize, void* stream);
+int pg_resample_v_u8_norm(const void* src, float* out, int H, int Wd, int S, const int* kk, const int* bounds, int ksize,
+                          const float* lut, void* stream);
+
 /* SiglipVisionEmbeddings im2col (modeling_siglip.py:258-263,285-297): pixel fp32 [B,C,H,W] -> patches bf16
  * [B*(H/P)*(W/P), Kpad], column order (c, py, px) = Conv2d weight order, zero padded to Kpad. */
 int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream);

@@ -42,6 +42,8 @@ SIGNATURES = {
     "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],
     "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p, i64, p],
     "pg_prefetch_l2": [p, i64, i32, i32, p],
+    "pg_resample_h_u8": [p, p, i32, i32, i32, p, p, i32, p],
+    "pg_resample_v_u8_norm": [p, p, i32, i32, i32, p, p, i32, p, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_add_pos_emb": [p, p, i32, i32, i32, p],
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],

@@ -61,12 +61,18 @@ class PaliGemmaProcessor:
         self.tokenizer.add_tokens(extra)
         self.tokenizer.image_token_id = self.tokenizer.convert_tokens_to_ids(self.IMAGE_TOKEN)
 
-    def __call__(self, images, text: List[str], padding: str = "longest", truncation: bool = True) -> dict:
+    def __call__(self, images, text: List[str], padding: str = "longest", truncation: bool = True, device=None) -> dict:
+        """`device="cuda"`: the image path (bicubic resize, rescale, normalise, CHW) runs on the GPU
+        (image_preprocess.process_images_gpu, bit-exact with the PIL / numpy path) and `pixel_values` stays on the device."""
         from PIL import Image
         if len(images) != len(text) or len(text) == 0:
             raise AssertionError(f"need one prompt per image, got {len(images)} images and {len(text)} prompts")
-        pixel_values = process_images(images, self.image_size, scale_factor=1 / 255.0, resampling=Image.Resampling.BICUBIC)
-        pixel_values = torch.tensor(np.stack(pixel_values, axis=0))
+        if device is not None and str(device).startswith("cuda"):
+            from .image_preprocess import process_images_gpu
+            pixel_values = process_images_gpu(images, self.image_size, scale_factor=1 / 255.0)
+        else:
+            pixel_values = process_images(images, self.image_size, scale_factor=1 / 255.0, resampling=Image.Resampling.BICUBIC)
+            pixel_values = torch.tensor(np.stack(pixel_values, axis=0))
         strings = [create_gemma_string(p, self.image_seq_len, self.IMAGE_TOKEN, self.tokenizer.bos_token) for p in text]
         tokens = self.tokenizer(strings, return_tensors="pt", truncation=truncation, padding=padding)
         return {"pixel_values": pixel_values, **tokens}
