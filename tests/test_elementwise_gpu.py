@@ -150,3 +150,30 @@ def test_rope_kv_append(f32in):
             pg_, off = table[b, slot // page].item(), slot % page
             assert torch.equal(kp[pg_, off], ko[b * Sq + s])
             assert torch.equal(vp[pg_, off], vo[b * Sq + s])
+
+
+@pytest.mark.parametrize("rows,D", [(1025, 256), (16384, 1152), (4099, 2048)])
+def test_layernorm_warp_per_row(rows, D):
+    """rows >= 1024 and D % 128 == 0 dispatch to the register-resident warp-per-row kernel (prefill)."""
+    from paligemma_multimodal_system_b200 import _lib
+    x = torch.randn(rows, D, device="cuda") * 3 + 1
+    g, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    yb = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    yf = torch.full((rows, D), float("nan"), device="cuda")
+    _lib.layernorm(x, g, b, 1e-6, yb, yf)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    _close(yf, ref, 1e-5, "layernorm f32 (warp per row)")
+    _close(yb, ref, 5e-3, "layernorm bf16 (warp per row)")
+
+
+@pytest.mark.parametrize("rows,D", [(1024, 256), (16640, 2048), (1031, 1152)])
+def test_rmsnorm_warp_per_row(rows, D):
+    from paligemma_multimodal_system_b200 import _lib
+    x = torch.randn(rows, D, device="cuda") * 5
+    w = torch.randn(D, device="cuda") * 0.1
+    y = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.rmsnorm(x, w, y, 1e-6)
+    torch.cuda.synchronize()
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * (1.0 + w)
+    assert (y.float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6  # one bf16 rounding
