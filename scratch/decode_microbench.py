@@ -80,6 +80,16 @@ for pdl in (1,):
         _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
         _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=18)
     graph_time("FULL layer", full_layer, (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4)
+    for sq, so, sd in ((7, 9, 36), (7, 9, 24), (14, 9, 18), (7, 18, 18), (5, 8, 18), (10, 9, 18)):
+        def fl(i, sq=sq, so=so, sd=sd):
+            _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv)
+            _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sq)
+            attn(i)
+            _lib.gemm(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=so)
+            _lib.rmsnorm(h, ln_w, hn_out)
+            _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+            _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sd)
+        graph_time(f"FULL layer splits qkv {sq} o {so} down {sd}", fl, (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4)
     def layer(i):
         _lib.rmsnorm(h, ln_w, hn_out, zero_buf=qkv)
         _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=7)
