@@ -342,7 +342,7 @@ def main():
                     "note": "generated tokens / wall incl. H2D, prefill, decode, D2H"},
             "gpu_launches": int(eager_launches + K * max(T - 1, 0) * graph_kernels),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<64,swap> gate||up decode GEMM", "achieved": k_gbs,
+            "roofline": {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<64,1,1> (swap-AB, 8 epilogue warps) gate||up decode GEMM", "achieved": k_gbs,
                          "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak, "traffic": ncu_traffic_per_launch() if B == 64 else None, "peak_source": peak_src,
                          "us_per_launch": 1e3 * k_ms, "algorithmic_bytes": k_bytes},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
