@@ -99,6 +99,14 @@ PG_DEVINL uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t box_bytes) {
   return d;
 }
 
+
+// One MUFU ex2 per score (ftz; -inf -> +0, so masked keys weigh exactly nothing).
+PG_DEVINL float exp2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DH>
 __global__ void __launch_bounds__(192, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -257,7 +265,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(s[c * 8 + 2 * e] - m_new), p1 = exp2f(s[c * 8 + 2 * e + 1] - m_new);
+          // (measured: moving every other exponential to the FMA pipe with a degree-4 polynomial + exponent-field add makes
+          //  the dh = 72 kernel 40 % SLOWER: the softmax warps are bound by instruction issue, not by the MUFU rate)
+          const float p0 = exp2_mufu(s[c * 8 + 2 * e] - m_new), p1 = exp2_mufu(s[c * 8 + 2 * e + 1] - m_new);
           sum += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
         }
