@@ -145,6 +145,19 @@ int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, i
                          long long o_hs, long long o_head_off, float scale, void* stream);
 
 /*
+ * pg_attention_prefill for a ragged batch (prompts of different lengths in one prefill; the reference
+ * runs B = 1, inference.py:69, and never masks padding, modeling_paligemma.py:154-156): problem b attends only to its first
+ * key_lens[b] keys (int32 [B] on the device, clamped to [1, keys]).  Rows past a problem's length are computed and must be
+ * ignored by the caller; K/V rows in [key_lens[b], keys) must hold finite values.  tcgen05 kernel only (dh 64 / 72 / 256,
+ * 128 % group == 0, 16-byte aligned strides): other shapes return PG_ERR_ARG.
+ */
+int pg_attention_prefill_varlen(const void* q, const void* k, const void* v, void* o, const int* key_lens, int B, int H,
+                                int rows, int keys, int dh, int group, long long q_bs, long long q_ts, long long q_hs,
+                                long long q_head_off, long long kv_bs, long long kv_ts, long long kv_head_off,
+                                long long o_bs, long long o_ts, long long o_hs, long long o_head_off, float scale,
+                                void* stream);
+
+/*
  * RoPE + KV append (modeling_gemma.py:116-151,285-302 and KVCache.update :18-57): reads qkv [T, (Hq+2Hkv)*dh]
  * (bf16, or fp32 when qkv_is_f32), rotates q and k (rotate-half, fp32 angle = pos[t] * inv_freq[i], inv_freq fp32 [dh/2] built by the host exactly as
  * GemmaRotaryEmbedding.__init__ does), writes q_out bf16
@@ -215,6 +228,13 @@ int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count
  * counters[c*B + b] += 1 for c < n_counters (position ids, KV write slots, KV lengths); step += 1.  B <= 1024. */
 int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counters, int n_counters, int* step, int B,
                       void* stream);
+
+/* pg_advance_decode for continuous batching (the inference.py:45-79 loop state of B independent requests, one per slot):
+ * tok_ring[(step % ring)*B + b] = next[b]; cur_tok[b] = next[b]; the three counters of slot b (int32 [3, B]: position id, KV
+ * write slot, KV length) advance only while counters[2][b] < kv_limit[b] -- a slot that has used its budget (finished or
+ * idle) is frozen until the host re-arms it; step += 1. */
+int pg_advance_decode_slots(const int* next, int* tok_ring, int ring, int* cur_tok, int* counters, const int* kv_limit,
+                            int* step, int B, void* stream);
 
 /*
  * A whole Gemma decode step (token embedding, L x [RMSNorm, QKV, RoPE + KV append + attention, O, RMSNorm, gate||up GEGLU,

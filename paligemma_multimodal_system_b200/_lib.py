@@ -47,6 +47,7 @@ SIGNATURES = {
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_add_pos_emb": [p, p, i32, i32, i32, p],
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
+    "pg_attention_prefill_varlen": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
     "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],
@@ -57,6 +58,7 @@ SIGNATURES = {
     "pg_argmax": [p, i64, p, i32, i32, p],
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
+    "pg_advance_decode_slots": [p, p, i32, p, p, p, p, i32, p],
     "pg_decode_step": [p, p],
     "pg_decode_step_encode_maps": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32],
 }

@@ -19,7 +19,7 @@
 int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
                             int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off, long long kv_bs,
                             long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts, long long o_hs,
-                            long long o_head_off, float scale, void* stream);  // attention_prefill_tc.cu
+                            long long o_head_off, float scale, const int* key_lens, void* stream);  // attention_prefill_tc.cu
 
 namespace pg {
 
@@ -900,7 +900,7 @@ extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v,
     static const bool force_mma = getenv("PG_ATTN_PREFILL_MMA") != nullptr;
     if (!force_mma) {
       const int rc = pg_attention_prefill_tc(q, k, v, o, B, H, rows, keys, dh, group, q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts,
-                                             kv_head_off, o_bs, o_ts, o_hs, o_head_off, scale, stream);
+                                             kv_head_off, o_bs, o_ts, o_hs, o_head_off, scale, nullptr, stream);
       if (rc <= 0) return rc;
     }
   }
@@ -919,6 +919,19 @@ extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v,
     case 256: return launch_prefill<256, 8>(p, B, H, st);
     default: return PG_ERR_ARG;
   }
+}
+
+extern "C" int pg_attention_prefill_varlen(const void* q, const void* k, const void* v, void* o, const int* key_lens, int B, int H,
+                                           int rows, int keys, int dh, int group, long long q_bs, long long q_ts, long long q_hs,
+                                           long long q_head_off, long long kv_bs, long long kv_ts, long long kv_head_off,
+                                           long long o_bs, long long o_ts, long long o_hs, long long o_head_off, float scale,
+                                           void* stream) {
+  if (B <= 0 || H <= 0 || rows <= 0 || keys <= 0 || group <= 0 || key_lens == nullptr) return PG_ERR_ARG;
+  if (B > 65535 || H > 65535) return PG_ERR_ARG;
+  // ragged key counts exist on the tcgen05 kernel only: a shape its TMA maps cannot express is an argument error here
+  const int rc = pg_attention_prefill_tc(q, k, v, o, B, H, rows, keys, dh, group, q_bs, q_ts, q_hs, q_head_off, kv_bs, kv_ts,
+                                         kv_head_off, o_bs, o_ts, o_hs, o_head_off, scale, key_lens, stream);
+  return rc > 0 ? PG_ERR_ARG : rc;
 }
 
 extern "C" long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_splits) {

@@ -35,6 +35,7 @@ struct Params {
   int rows, keys, group, dh;
   long long o_bs, o_ts, o_hs, o_head_off;
   float sl2;  // softmax scale * log2(e)
+  const int* key_lens;  // optional [B]: problem b only attends to its first key_lens[b] keys (ragged prompts); else nullptr
 };
 
 template <int DH>
@@ -134,7 +135,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.keys + BN - 1) / BN;
+  // ragged batches: keys [key_lens[b], keys) of problem b exist in memory (padding tokens, finite values) but weigh nothing
+  const int n_keys = p.key_lens ? max(1, min(p.keys, __ldg(p.key_lens + b))) : p.keys;
+  const int n_tiles = (n_keys + BN - 1) / BN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -246,7 +249,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(sb));  // the S buffer may be overwritten by S_{j+2}
-      const int nvalid = p.keys - j * BN;       // keys of this tile that exist
+      const int nvalid = n_keys - j * BN;       // keys of this tile that exist
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < BN; ++i) {
@@ -375,7 +378,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys, int dh,
                             int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off, long long kv_bs,
                             long long kv_ts, long long kv_head_off, long long o_bs, long long o_ts, long long o_hs,
-                            long long o_head_off, float scale, void* stream) {
+                            long long o_head_off, float scale, const int* key_lens, void* stream) {
   using namespace pg;
   if (dh != 64 && dh != 72 && dh != 256) return 1;
   if (group <= 0 || (128 % group) != 0 || (rows % group) != 0) return 1;
@@ -406,6 +409,7 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   p.rows = rows; p.keys = keys; p.group = group; p.dh = dh;
   p.o_bs = o_bs; p.o_ts = o_ts; p.o_hs = o_hs; p.o_head_off = o_head_off;
   p.sl2 = scale * 1.4426950408889634f;
+  p.key_lens = key_lens;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {
     case 64: return ap::launch<64>(tq, tk, tv, p, B, H, st);

@@ -462,6 +462,29 @@ __global__ void advance_decode_kernel(const int* __restrict__ next, int* __restr
   if (threadIdx.x == 0) *step = st + 1;
 }
 
+// Continuous batching (slot = one row of the decode batch, refilled by the host between graph replays): the token log is a
+// ring of `ring` steps, and a slot only advances while its kv length is below its budget kv_limit[b] (prompt + new tokens).
+// A slot at its budget (finished or idle) is frozen: it keeps recomputing its last position, which is harmless.
+__global__ void advance_decode_slots_kernel(const int* __restrict__ next, int* __restrict__ tok_ring, int ring,
+                                            int* __restrict__ cur_tok, int* __restrict__ counters,
+                                            const int* __restrict__ kv_limit, int* __restrict__ step, int B) {
+  const int b = threadIdx.x;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  const int st = *step;
+  if (b < B) {
+    const int t = next[b];
+    tok_ring[static_cast<long long>(st % ring) * B + b] = t;
+    cur_tok[b] = t;
+    if (counters[2 * B + b] < kv_limit[b]) {
+      counters[b] += 1;
+      counters[B + b] += 1;
+      counters[2 * B + b] += 1;
+    }
+  }
+  __syncthreads();  // single block: every thread has read *step
+  if (threadIdx.x == 0) *step = st + 1;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // L2 warm-up of an immutable weight range, meant to run on a SIDE stream concurrently with the latency-bound part of a
@@ -632,6 +655,13 @@ extern "C" int pg_kv_gather(const void* pages, const int* page_table, void* dens
   kv_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, PG_ST(stream)>>>(
       static_cast<const bf16*>(pages), page_table, static_cast<bf16*>(dense), len, Hkv, dh, page_size, max_pages, total);
   PG_RET();
+}
+
+extern "C" int pg_advance_decode_slots(const int* next, int* tok_ring, int ring, int* cur_tok, int* counters, const int* kv_limit,
+                                       int* step, int B, void* stream) {
+  if (B <= 0 || B > 1024 || ring <= 0 || !next || !tok_ring || !cur_tok || !counters || !kv_limit || !step) return PG_ERR_ARG;
+  return launch_kernel(advance_decode_slots_kernel, dim3(1), dim3(1024), 0, PG_ST(stream), next, tok_ring, ring, cur_tok,
+                       counters, kv_limit, step, B) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counters, int n_counters, int* step, int B,

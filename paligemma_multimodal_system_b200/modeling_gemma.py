@@ -279,8 +279,14 @@ class GemmaForCausalLM(nn.Module):
 
     # -- prefill ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def prefill(self, h, pos, B, S, kv_cache: Optional[KVCache], last_only: bool, reserve_tokens: int = 0):
-        """h fp32 [B*S, D] (merged, scaled embeddings; overwritten), pos int32 [B*S] -> logits fp32 [B, S|1, V]."""
+    def prefill(self, h, pos, B, S, kv_cache: Optional[KVCache], last_only: bool, reserve_tokens: int = 0, lens=None,
+                slots=None):
+        """h fp32 [B*S, D] (merged, scaled embeddings; overwritten), pos int32 [B*S] -> logits fp32 [B, S|1, V].
+
+        Ragged batches (serving.py): `lens` int32 [B] on the device = true prompt length of each row (rows are right-padded
+        to S; row b only attends to its first lens[b] keys and `last_only` picks position lens[b]-1); `slots` int64 [B] =
+        rows of an already allocated, larger `kv_cache` that receive the keys/values (its length bookkeeping is left to
+        the caller)."""
         c = self.text_config
         pk = self._packed or self.pack()
         L, st = _lib.lib(), _lib.stream()
@@ -288,11 +294,18 @@ class GemmaForCausalLM(nn.Module):
         T = B * S
         dev = h.device
         have_cache = kv_cache is not None
-        if have_cache:
+        page_table = None
+        if have_cache and slots is not None:
+            if kv_cache._geom is None or kv_cache.capacity < S:
+                raise ValueError("prefill into slots needs an allocated KVCache with capacity >= the padded prompt length")
+            page_table = kv_cache.page_table.index_select(0, slots).contiguous()
+            slot_base = torch.zeros(B, device=dev, dtype=torch.int32)
+        elif have_cache:
             if kv_cache._geom is None or kv_cache._geom != (B, c.num_hidden_layers, Hkv, dh):
                 kv_cache.allocate(B, c.num_hidden_layers, Hkv, dh, S + max(kv_cache.reserve_tokens, reserve_tokens))
             kv_cache.ensure_capacity(S + 1)
             slot_base = torch.zeros(B, device=dev, dtype=torch.int32)
+            page_table = kv_cache.page_table
         hn = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
         qkv = torch.empty(T, (Hq + 2 * Hkv) * dh, device=dev, dtype=torch.bfloat16)
         q = torch.empty(T, Hq * dh, device=dev, dtype=torch.bfloat16)
@@ -308,22 +321,31 @@ class GemmaForCausalLM(nn.Module):
             _lib.check(L.pg_rope_kv_append(
                 qkv.data_ptr(), 0, pos.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
                 kv_cache.k_pages[li].data_ptr() if have_cache else 0, kv_cache.v_pages[li].data_ptr() if have_cache else 0,
-                kv_cache.page_table.data_ptr() if have_cache else 0, slot_base.data_ptr() if have_cache else 0,
-                B, S, Hq, Hkv, dh, PAGE, kv_cache.page_table.shape[1] if have_cache else 0, pk["inv_freq"].data_ptr(), st),
+                page_table.data_ptr() if have_cache else 0, slot_base.data_ptr() if have_cache else 0,
+                B, S, Hq, Hkv, dh, PAGE, page_table.shape[1] if have_cache else 0, pk["inv_freq"].data_ptr(), st),
                 "pg_rope_kv_append")
             # MQA/GQA: the G query heads of a KV head are consecutive rows of one attention problem (no repeat_kv)
-            _lib.check(L.pg_attention_prefill(
-                q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), B, Hkv, S * G, S, dh, G,
-                S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
-                S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill")
+            if lens is None:
+                _lib.check(L.pg_attention_prefill(
+                    q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), B, Hkv, S * G, S, dh, G,
+                    S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
+                    S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill")
+            else:
+                _lib.check(L.pg_attention_prefill_varlen(
+                    q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), lens.data_ptr(), B, Hkv, S * G, S, dh, G,
+                    S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
+                    S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill_varlen")
             _lib.gemm_residual(att, lw["o_w"], h)
             _lib.rmsnorm(h, lw["ln2"], hn)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=0 if T > 128 else 1)
             _lib.gemm_residual(mid, lw["down_w"], h)
-        if have_cache:
+        if have_cache and slots is None:
             kv_cache._set_len(S, c.num_hidden_layers)
         if last_only:
-            last = h.view(B, S, D)[:, -1, :].contiguous()
+            if lens is None:
+                last = h.view(B, S, D)[:, -1, :].contiguous()
+            else:
+                last = h.view(B, S, D)[torch.arange(B, device=dev), lens.long() - 1].contiguous()
             ln = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
             _lib.rmsnorm(last, pk["norm_w"], ln)
             logits = torch.empty(B, V, device=dev, dtype=torch.float32)
@@ -335,15 +357,18 @@ class GemmaForCausalLM(nn.Module):
         return logits.view(B, S, V)
 
     # -- decode ----------------------------------------------------------------------------------------------------
-    def decode_buffers(self, B):
+    def decode_buffers(self, B, private: bool = False):
+        """Activation buffers of one decode step.  Cached per batch size: captured CUDA graphs (generate(), serving.py) hold
+        these addresses, so a buffer must never be replaced once handed out; `private` returns a fresh set owned by the
+        caller."""
         c = self.text_config
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        return dict(
-            h=self._buf("d_h", (B, D), torch.float32), hn=self._buf("d_hn", (B, D), torch.bfloat16),
-            hb=self._buf("d_hb", (B, D), torch.bfloat16), ss=self._buf("d_ss", (2 * c.num_hidden_layers + 1, B), torch.float32),
-            qkv=self._buf("d_qkv", (B, (Hq + 2 * Hkv) * dh), torch.float32),
-            att=self._buf("d_att", (B, Hq * dh), torch.bfloat16), mid=self._buf("d_mid", (B, F), torch.bfloat16),
-            logits=self._buf("d_logits", (B, V), torch.float32))
+        shapes = dict(h=((B, D), torch.float32), hn=((B, D), torch.bfloat16), hb=((B, D), torch.bfloat16),
+                      ss=((2 * c.num_hidden_layers + 1, B), torch.float32), qkv=((B, (Hq + 2 * Hkv) * dh), torch.float32),
+                      att=((B, Hq * dh), torch.bfloat16), mid=((B, F), torch.bfloat16), logits=((B, V), torch.float32))
+        if private:
+            return {k: torch.empty(*shp, device="cuda", dtype=dt) for k, (shp, dt) in shapes.items()}
+        return {k: self._buf(f"d_{k}_{B}", shp, dt) for k, (shp, dt) in shapes.items()}
 
     @torch.no_grad()
     def decode_prologue(self, bufs, B, tokens_i32=None, img=None, img_scale=1.0, pad_token=-1, image_token=-1):

@@ -122,3 +122,23 @@ def make_inputs(config: dict, batch: int, prompt_len: int = 4, seed: int = 0, de
         px.append(_bf16_round(torch.rand(vc.get("num_channels", 3), vc["image_size"], vc["image_size"], generator=g) * 2 - 1))
     input_ids = torch.stack(ids).to(device)
     return dict(input_ids=input_ids, attention_mask=torch.ones_like(input_ids), pixel_values=torch.stack(px).to(device))
+
+
+def make_requests(config: dict, n: int, min_prompt_len: int = 2, max_prompt_len: int = 8, seed: int = 0):
+    """Synthetic request stream with RAGGED prompts (serving.py): request r = `<image>`*N + bos(2) + random tokens, text
+    length cycling through [min_prompt_len, max_prompt_len], the last token random per request (so that even the
+    degenerate random-init regimes, which echo the last prompt token, give every request its own continuation); pixel
+    values as in make_inputs.  Returns a list of (input_ids int64 [S_r], pixel_values [3, H, W])."""
+    vc, tc = config["vision_config"], config["text_config"]
+    N = (vc["image_size"] // vc["patch_size"]) ** 2
+    V_text = min(config["image_token_index"], tc["vocab_size"])
+    out = []
+    span = max_prompt_len - min_prompt_len + 1
+    for r in range(n):
+        g = torch.Generator(device="cpu").manual_seed(seed * 1000003 + 7919 * r + 1)
+        t = min_prompt_len + (r * 5) % span
+        text = torch.cat([torch.tensor([2]), torch.randint(3, V_text, (t - 1,), generator=g)]).long()
+        ids = torch.cat([torch.full((N,), config["image_token_index"]).long(), text])
+        px = _bf16_round(torch.rand(vc.get("num_channels", 3), vc["image_size"], vc["image_size"], generator=g) * 2 - 1)
+        out.append((ids, px))
+    return out

@@ -1,0 +1,249 @@
+"""Variable-length prompts and continuous batching on top of the paged KVCache.
+
+The reference loop (inference.py:45-79) serves ONE request (`assert next_token.size() == (1, 1)`, :69): prefill, then one
+token per step until EOS has been appended (:71-74) or `max_tokens_to_generate` is reached.  Here B such loops share one
+decode batch.  A *slot* is one row of that batch: it owns a row of the page table, three device counters (position id, KV
+write slot, KV length), a KV budget and its projected image features.  The decode step reads all of that from device
+memory, so ONE captured CUDA graph of `steps_per_replay` steps serves every mix of requests; between replays the host
+  * reads the ring of sampled tokens, trims every request at its first EOS / at its token budget and retires it,
+  * admits queued requests into free slots with ONE ragged prefill (prompts right-padded to the longest of the group;
+    row b attends to its own lens[b] keys only -- pg_attention_prefill_varlen -- and its keys/values land in its slot's
+    pages), samples their first token from the last *real* position and re-arms the slots' counters.
+Every request therefore sees exactly the arithmetic of its own B = 1 run (unpadded prompt, positions 1..S, its own KV
+length), which is what the parity tests check against `generate()` at B = 1 and against vectors of the unmodified
+reference.  The reference's own treatment of right padding (pads zeroed, position 1, never masked:
+modeling_paligemma.py:125-127,154-156,195) stays available through `forward()` with an attention_mask.
+
+`SlotScheduler` is the host-side bookkeeping alone (no tensors; CPU-testable); `ContinuousBatcher` is the device engine.
+"""
+import collections
+import dataclasses
+import time
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .modeling_gemma import KVCache
+
+
+@dataclasses.dataclass
+class Request:
+    rid: int
+    input_ids: torch.Tensor      # int64 [S]: N image tokens followed by the text prompt (processing_paligemma.py:77-89)
+    pixel_values: torch.Tensor   # [3, H, W]
+    max_new_tokens: int
+    tokens: List[int] = dataclasses.field(default_factory=list)
+
+
+class SlotScheduler:
+    """FIFO queue -> free slots; token accounting with the reference loop's stop rule (EOS is appended, then the request
+    stops, inference.py:71-74; otherwise it stops after max_new_tokens)."""
+
+    def __init__(self, num_slots: int, eos_token_id: Optional[int] = None, min_admit: int = 1):
+        if num_slots <= 0:
+            raise ValueError("num_slots must be positive")
+        self.num_slots = num_slots
+        self.eos_token_id = eos_token_id
+        self.min_admit = max(1, int(min_admit))
+        self.free: List[int] = list(range(num_slots))
+        self.queue = collections.deque()
+        self.active: Dict[int, Request] = {}
+        self.finished: Dict[int, List[int]] = {}
+
+    def submit(self, req: Request):
+        self.queue.append(req)
+
+    def idle(self) -> bool:
+        return not self.queue and not self.active
+
+    def plan_admission(self) -> List[Tuple[int, Request]]:
+        """Requests to prefill now, lowest free slot first.  A prefill of very few rows costs as much as several decode
+        steps of the whole batch, so while other slots are busy the scheduler waits until `min_admit` rows (or the whole
+        remaining queue) can be admitted together."""
+        n = min(len(self.free), len(self.queue))
+        if n == 0:
+            return []
+        if self.active and n < min(self.min_admit, len(self.queue)):
+            return []
+        self.free.sort()
+        pairs = []
+        for _ in range(n):
+            slot = self.free.pop(0)
+            req = self.queue.popleft()
+            self.active[slot] = req
+            pairs.append((slot, req))
+        return pairs
+
+    def consume(self, slot: int, toks: List[int]) -> bool:
+        """Appends the tokens a slot produced (in order); returns True when the request finished (slot freed).  Tokens
+        after the stop point (the slot keeps stepping until the replay ends) are dropped."""
+        req = self.active[slot]
+        for t in toks:
+            req.tokens.append(int(t))
+            if len(req.tokens) >= req.max_new_tokens or (self.eos_token_id is not None and int(t) == self.eos_token_id):
+                self.finished[req.rid] = req.tokens
+                del self.active[slot]
+                self.free.append(slot)
+                return True
+        return False
+
+
+class ContinuousBatcher:
+    def __init__(self, model, num_slots: int, max_prompt_len: int, max_new_tokens: int, do_sample: bool = False,
+                 temperature: float = 0.8, top_p: float = 0.9, eos_token_id: Optional[int] = None, seed: int = 0,
+                 steps_per_replay: int = 8, min_admit: int = 1, use_cuda_graph: bool = True,
+                 keep_admit_logits: bool = False):
+        """max_prompt_len counts the image tokens too (S = num_image_tokens + text tokens)."""
+        _lib.require_device()
+        self.model = model
+        self.lm, self.c = model.language_model, model.text_config
+        c = self.c
+        self.B = int(num_slots)
+        if self.B > 1024:
+            raise ValueError("at most 1024 slots")
+        self.max_prompt_len, self.max_new_tokens = int(max_prompt_len), int(max_new_tokens)
+        self.do_sample, self.inv_t, self.top_p, self.seed = bool(do_sample), 1.0 / float(temperature), float(top_p), int(seed)
+        self.GK = max(1, int(steps_per_replay))
+        self.use_cuda_graph = use_cuda_graph
+        self.sched = SlotScheduler(self.B, eos_token_id, min_admit)
+        dev = torch.device("cuda")
+        self.kv = KVCache()
+        self.kv.allocate(self.B, c.num_hidden_layers, c.num_key_value_heads, c.head_dim, self.max_prompt_len + self.max_new_tokens)
+        self.kv._set_len(1, c.num_hidden_layers)  # "decode phase" for anything that asks num_items()
+        self.cur = torch.zeros(self.B, device=dev, dtype=torch.int32)
+        self.nxt = torch.zeros(self.B, device=dev, dtype=torch.int32)
+        self.ring = torch.zeros(self.GK, self.B, device=dev, dtype=torch.int32)
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.limit = torch.ones(self.B, device=dev, dtype=torch.int32)
+        self.img = torch.zeros(self.B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32)
+        self.kv.image_feats = self.img
+        self._set_idle(list(range(self.B)))
+        self.bufs = self.lm.decode_buffers(self.B, private=True)  # the captured graph owns these addresses
+        self.graph = None
+        self.admit_logits = {} if keep_admit_logits else None  # request id -> fp32 logits of its first token (tests)
+        self._next_rid = 0
+        self.stats = dict(prefill_groups=0, prefill_rows=0, decode_replays=0, decode_steps=0, tokens=0)
+
+    # -- host API --------------------------------------------------------------------------------------------------
+    def submit(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, max_new_tokens: Optional[int] = None) -> int:
+        ids = input_ids.reshape(-1).to("cpu", torch.int64)
+        m = self.max_new_tokens if max_new_tokens is None else int(max_new_tokens)
+        if ids.numel() > self.max_prompt_len or ids.numel() < 1:
+            raise ValueError(f"prompt of {ids.numel()} tokens does not fit max_prompt_len = {self.max_prompt_len}")
+        if not 1 <= m <= self.max_new_tokens:
+            raise ValueError(f"max_new_tokens must lie in [1, {self.max_new_tokens}]")
+        rid = self._next_rid
+        self._next_rid += 1
+        self.sched.submit(Request(rid, ids, pixel_values, m))
+        return rid
+
+    @torch.no_grad()
+    def run(self) -> Dict[int, torch.Tensor]:
+        """Serves every submitted request; returns {request id: int64 tokens} (EOS included when it was emitted)."""
+        t0 = time.perf_counter()
+        while not self.sched.idle():
+            pairs = self.sched.plan_admission()
+            if pairs:
+                self._admit(pairs)
+            if self.sched.active:
+                self._decode_group()
+        torch.cuda.synchronize()
+        self.stats["wall_s"] = self.stats.get("wall_s", 0.0) + time.perf_counter() - t0
+        out = {rid: torch.tensor(t, dtype=torch.int64) for rid, t in self.sched.finished.items()}
+        self.sched.finished = {}
+        return out
+
+    # -- device side -----------------------------------------------------------------------------------------------
+    def _set_idle(self, slots: List[int]):
+        if not slots:
+            return
+        s = torch.tensor(slots, device="cuda", dtype=torch.int64)
+        one = torch.ones(len(slots), device="cuda", dtype=torch.int32)
+        self.kv.counters[0].index_copy_(0, s, one)      # position id 1
+        self.kv.counters[1].index_copy_(0, s, one - 1)  # write slot 0
+        self.kv.counters[2].index_copy_(0, s, one)      # one key
+        self.limit.index_copy_(0, s, one)               # kv_len == limit: frozen
+        self.cur.index_fill_(0, s, 0)
+
+    def _sample(self, logits, out, rows, seed):
+        L, V = _lib.lib(), self.c.vocab_size
+        if self.do_sample:
+            _lib.check(L.pg_sample_top_p(logits.data_ptr(), V, out.data_ptr(), 0, rows, V, self.inv_t, self.top_p, seed,
+                                         self.step.data_ptr(), _lib.stream()), "pg_sample_top_p")
+        else:
+            _lib.check(L.pg_argmax(logits.data_ptr(), V, out.data_ptr(), rows, V, _lib.stream()), "pg_argmax")
+
+    def _admit(self, pairs: List[Tuple[int, Request]]):
+        model, c = self.model, self.c
+        g = len(pairs)
+        lens = [int(r.input_ids.numel()) for _, r in pairs]
+        S = max(lens)
+        fill = model.pad_token_id if model.pad_token_id is not None and model.pad_token_id >= 0 else 0
+        ids = torch.full((g, S), fill, dtype=torch.int64)
+        mask = torch.zeros(g, S, dtype=torch.int64)
+        for i, (_, r) in enumerate(pairs):
+            ids[i, : lens[i]] = r.input_ids
+            mask[i, : lens[i]] = 1
+        px = torch.stack([r.pixel_values for _, r in pairs]).to("cuda", non_blocking=True)
+        slots_t = torch.tensor([s for s, _ in pairs], device="cuda", dtype=torch.int64)
+        lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+        budget = torch.tensor([r.max_new_tokens for _, r in pairs], device="cuda", dtype=torch.int32)
+        img = model.image_features(px)
+        self.img.index_copy_(0, slots_t, img)
+        h, pos = model._merge(ids.cuda(), mask.cuda(), img)
+        logits = self.lm.prefill(h, pos, g, S, self.kv, last_only=True, lens=lens_t, slots=slots_t).view(g, c.vocab_size)
+        if self.admit_logits is not None:
+            for i, (_, r) in enumerate(pairs):
+                self.admit_logits[r.rid] = logits[i].clone()
+        first = torch.empty(g, device="cuda", dtype=torch.int32)
+        self._sample(logits, first, g, self.seed ^ 0x5DEECE66D)  # admissions draw from their own RNG stream
+        self.cur.index_copy_(0, slots_t, first)
+        # next token: position id S+1 (1-based positions, modeling_paligemma.py:189), written at cache slot S, kv length S+1
+        self.kv.counters[0].index_copy_(0, slots_t, lens_t + 1)
+        self.kv.counters[1].index_copy_(0, slots_t, lens_t)
+        self.kv.counters[2].index_copy_(0, slots_t, lens_t + 1)
+        self.limit.index_copy_(0, slots_t, lens_t + budget - 1)  # the step that produces token max_new-1 is the last to advance
+        self.stats["prefill_groups"] += 1
+        self.stats["prefill_rows"] += g
+        done = [slot for (slot, _), t in zip(pairs, first.tolist()) if self._consume(slot, [t])]
+        self._set_idle(done)
+
+    def _consume(self, slot, toks):
+        before = len(self.sched.active[slot].tokens)
+        req = self.sched.active[slot]
+        fin = self.sched.consume(slot, toks)
+        self.stats["tokens"] += len(req.tokens) - before
+        return fin
+
+    def _step(self):
+        lg = self.model._decode_step(self.cur, self.kv, self.bufs, self.B)
+        self._sample(lg, self.nxt, self.B, self.seed)
+        _lib.check(_lib.lib().pg_advance_decode_slots(self.nxt.data_ptr(), self.ring.data_ptr(), self.GK, self.cur.data_ptr(),
+                                                      self.kv.counters.data_ptr(), self.limit.data_ptr(), self.step.data_ptr(),
+                                                      self.B, _lib.stream()), "pg_advance_decode_slots")
+
+    def _capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(self.GK):
+                    self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        return g
+
+    def _decode_group(self):
+        if self.use_cuda_graph and self.graph is None and self.stats["decode_replays"] > 0:
+            self.graph = self._capture()  # the first group ran eagerly: lazy kernel attributes / entry points are warm
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            for _ in range(self.GK):
+                self._step()
+        ring = self.ring.cpu()  # [GK, B]; the one host sync per group
+        self.stats["decode_replays"] += 1
+        self.stats["decode_steps"] += self.GK
+        done = [slot for slot in list(self.sched.active) if self._consume(slot, ring[:, slot].tolist())]
+        self._set_idle(done)
