@@ -12,7 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from paligemma_multimodal_system_b200.random_init import TINY_CONFIG, make_requests, make_state_dict  # noqa: E402
-from tests.parity_utils import build_model, stats  # noqa: E402
+from parity_utils import build_model, stats  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(ROOT, "tests", "golden", "serving_reference.npz"))
