@@ -280,13 +280,13 @@ class GemmaForCausalLM(nn.Module):
     # -- prefill ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def prefill(self, h, pos, B, S, kv_cache: Optional[KVCache], last_only: bool, reserve_tokens: int = 0, lens=None,
-                slots=None):
+                page_rows=None):
         """h fp32 [B*S, D] (merged, scaled embeddings; overwritten), pos int32 [B*S] -> logits fp32 [B, S|1, V].
 
         Ragged batches (serving.py): `lens` int32 [B] on the device = true prompt length of each row (rows are right-padded
-        to S; row b only attends to its first lens[b] keys and `last_only` picks position lens[b]-1); `slots` int64 [B] =
-        rows of an already allocated, larger `kv_cache` that receive the keys/values (its length bookkeeping is left to
-        the caller)."""
+        to S; row b only attends to its first lens[b] keys and `last_only` picks position lens[b]-1); `page_rows` int32
+        [B, max_pages] = page-table rows (into the pages of an already allocated `kv_cache`) that receive the keys/values of
+        the B rows; the cache's own page table and length bookkeeping are left to the caller."""
         c = self.text_config
         pk = self._packed or self.pack()
         L, st = _lib.lib(), _lib.stream()
@@ -295,10 +295,10 @@ class GemmaForCausalLM(nn.Module):
         dev = h.device
         have_cache = kv_cache is not None
         page_table = None
-        if have_cache and slots is not None:
-            if kv_cache._geom is None or kv_cache.capacity < S:
-                raise ValueError("prefill into slots needs an allocated KVCache with capacity >= the padded prompt length")
-            page_table = kv_cache.page_table.index_select(0, slots).contiguous()
+        if have_cache and page_rows is not None:
+            if kv_cache._geom is None or page_rows.shape[1] * PAGE < S or page_rows.shape[0] != B:
+                raise ValueError("prefill through page_rows needs an allocated KVCache and rows that hold the padded prompt")
+            page_table = page_rows.to(torch.int32).contiguous()
             slot_base = torch.zeros(B, device=dev, dtype=torch.int32)
         elif have_cache:
             if kv_cache._geom is None or kv_cache._geom != (B, c.num_hidden_layers, Hkv, dh):
@@ -339,7 +339,7 @@ class GemmaForCausalLM(nn.Module):
             _lib.rmsnorm(h, lw["ln2"], hn)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=0 if T > 128 else 1)
             _lib.gemm_residual(mid, lw["down_w"], h)
-        if have_cache and slots is None:
+        if have_cache and page_rows is None:
             kv_cache._set_len(S, c.num_hidden_layers)
         if last_only:
             if lens is None:

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--slots", type=int, default=64)
     ap.add_argument("--min-admit", type=int, default=8)
     ap.add_argument("--steps-per-replay", type=int, default=8)
+    ap.add_argument("--stage", type=int, default=16)
     ap.add_argument("--greedy", action="store_true")
     args = ap.parse_args()
     cfg = paligemma_3b_config(224)
@@ -40,7 +41,7 @@ def main():
 
     def run_cb():
         cb = ContinuousBatcher(model, num_slots=args.slots, max_prompt_len=256 + 12, max_new_tokens=128, min_admit=args.min_admit,
-                               steps_per_replay=args.steps_per_replay, **gen)
+                               steps_per_replay=args.steps_per_replay, stage=args.stage, **gen)
         for rep in range(2):  # first wave: warm-up + graph capture
             for (ids, px), m in zip(reqs, budgets):
                 cb.submit(ids, px, m)
@@ -49,7 +50,7 @@ def main():
             out = cb.run()
             dt = time.perf_counter() - t0
             st = dict(cb.stats)
-            cb.stats = dict(prefill_groups=0, prefill_rows=0, decode_replays=0, decode_steps=0, tokens=0)
+            cb.reset_stats()
         assert sum(len(v) for v in out.values()) == useful
         return dt, st
 
@@ -70,7 +71,7 @@ def main():
 
     dt_s = run_static()
     dt_c, st = run_cb()
-    print(f"requests {n}, slots {args.slots}, useful tokens {useful}, budgets 16..128, prompts 258..268 tokens")
+    print(f"requests {n}, slots {args.slots}, stage {args.stage}, min_admit {args.min_admit}, useful tokens {useful}, budgets 16..128, prompts 258..268 tokens")
     print(f"static batching   : {dt_s * 1e3:8.1f} ms  {useful / dt_s:9.0f} useful tok/s  ({n / dt_s:.1f} requests/s)")
     print(f"continuous batching: {dt_c * 1e3:8.1f} ms  {useful / dt_c:9.0f} useful tok/s  ({n / dt_c:.1f} requests/s)  "
           f"[{st['prefill_groups']} prefill groups, {st['decode_steps']} decode steps, slot occupancy "

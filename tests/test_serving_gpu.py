@@ -88,17 +88,18 @@ def _serve(model, reqs, budgets, **kw):
 
 
 @pytest.mark.parametrize("regime", ["R0", "R1"])
-@pytest.mark.parametrize("graph", [False, True])
-def test_continuous_batching_reproduces_the_reference_request_by_request(regime, graph):
+@pytest.mark.parametrize("graph,stage,min_admit", [(False, 0, 1), (True, 0, 1), (True, 3, 2), (True, 8, 4)])
+def test_continuous_batching_reproduces_the_reference_request_by_request(regime, graph, stage, min_admit):
     """10 ragged requests through 4 slots (so slots are refilled while others are mid-generation), different token budgets:
     every request must produce exactly what the unmodified reference produced for it alone."""
     model = build_model(TINY_CONFIG, make_state_dict(TINY_CONFIG, regime, seed=11))
     reqs = make_requests(TINY_CONFIG, 10, 2, 8, seed=21)
     budgets = [12, 5, 9, 1, 12, 7, 3, 12, 10, 6]
-    toks, cb = _serve(model, reqs, budgets, num_slots=4, steps_per_replay=4, use_cuda_graph=graph)
+    toks, cb = _serve(model, reqs, budgets, num_slots=4, steps_per_replay=4, use_cuda_graph=graph, stage=stage, min_admit=min_admit)
     for r in range(10):
         assert toks[r] == G[f"{regime}_tokens"][r][: budgets[r]].tolist(), (r, toks[r])
-    assert cb.stats["prefill_rows"] == 10 and cb.stats["prefill_groups"] >= 3 and cb.stats["tokens"] == sum(budgets)
+    assert cb.stats["prefill_rows"] == 10 and cb.stats["prefill_groups"] >= 2 and cb.stats["tokens"] == sum(budgets)
+    assert sorted(cb.sched.free_sets) == list(range(4 + stage)) and sorted(cb.sched.free_slots) == [0, 1, 2, 3]
     # the batcher is reusable (captured graph, slots back to idle): a second wave gives the same answers
     rids = [cb.submit(*reqs[r], 8) for r in (9, 0, 5)]
     out = cb.run()
@@ -106,14 +107,15 @@ def test_continuous_batching_reproduces_the_reference_request_by_request(regime,
         assert out[rid].tolist() == G[f"{regime}_tokens"][r][:8].tolist()
 
 
-def test_continuous_batching_stops_at_eos_and_refills():
+@pytest.mark.parametrize("stage", [0, 2])
+def test_continuous_batching_stops_at_eos_and_refills(stage):
     """The reference appends EOS and stops (inference.py:71-74).  In R1 request r keeps emitting its own last prompt token,
     so declaring request 1's token the EOS id ends that request after one token while the others run to their budgets."""
     model = build_model(TINY_CONFIG, make_state_dict(TINY_CONFIG, "R1", seed=11))
     reqs = make_requests(TINY_CONFIG, 6, 2, 8, seed=21)
     eos = int(G["R1_tokens"][1][0])
     assert all(eos not in G["R1_tokens"][r].tolist() for r in (0, 2, 3, 4, 5))
-    toks, cb = _serve(model, reqs, [10] * 6, num_slots=2, steps_per_replay=3, eos_token_id=eos)
+    toks, cb = _serve(model, reqs, [10] * 6, num_slots=2, steps_per_replay=3, eos_token_id=eos, stage=stage)
     assert toks[1] == [eos]
     for r in (0, 2, 3, 4, 5):
         assert toks[r] == G["R1_tokens"][r][:10].tolist()
@@ -126,7 +128,7 @@ def test_ragged_prefill_logits_and_single_request_runs_R2():
     from paligemma_multimodal_system_b200.serving import ContinuousBatcher
     model = build_model(TINY_CONFIG, make_state_dict(TINY_CONFIG, "R2", seed=11))
     reqs = make_requests(TINY_CONFIG, 10, 2, 8, seed=21)
-    cb = ContinuousBatcher(model, num_slots=8, max_prompt_len=264, max_new_tokens=12, keep_admit_logits=True)
+    cb = ContinuousBatcher(model, num_slots=6, max_prompt_len=264, max_new_tokens=12, keep_admit_logits=True, stage=2, min_admit=2)
     rids = [cb.submit(ids, px) for ids, px in reqs]
     out = cb.run()
     for r in range(10):
