@@ -182,6 +182,49 @@ def cpu_oracle_sample(cfg, sd_cpu, rows, new_tokens, threads):
     return dict(prefill_s_per_image=(t1 - t0) / rows, decode_tok_s=rows * new_tokens / (t2 - t1), seconds=t2 - t0)
 
 
+def measure_serving(model, cfg, n_requests=256, slots=64, stage=32, min_admit=16, steps_per_replay=8, greedy=False, static=True):
+    """a ragged request stream (text prompts of 2..12 tokens, token budgets uniform in [16, 128] standing
+    in for EOS-terminated answers) through serving.ContinuousBatcher, beside static batching of the same stream through
+    generate() (arrival order, `slots` at a time, each batch runs to its longest budget; one prompt length per batch, i.e.
+    with perfect length bucketing).  Useful tokens = sum of the budgets in both arms; wall clock around the whole stream,
+    host scheduling, H2D of the pixels and D2H of the tokens included; the first pass of each arm is the warm-up."""
+    from paligemma_multimodal_system_b200.random_init import make_inputs, make_requests
+    from paligemma_multimodal_system_b200.serving import ContinuousBatcher
+    reqs = make_requests(cfg, n_requests, 2, 12, seed=3)
+    budgets = torch.randint(16, 129, (n_requests,), generator=torch.Generator().manual_seed(5)).tolist()
+    useful = sum(budgets)
+    gen = dict(do_sample=not greedy, temperature=TEMPERATURE, top_p=TOP_P, seed=1)
+    N = (cfg["vision_config"]["image_size"] // cfg["vision_config"]["patch_size"]) ** 2
+    res = {"requests": n_requests, "slots": slots, "stage": stage, "min_admit": min_admit, "useful_tokens": useful,
+           "stream": "prompts of N+2..N+12 tokens, budgets uniform 16..128, " + ("greedy" if greedy else "top-p 0.9 temp 0.8")}
+    if static:
+        inp = make_inputs(cfg, batch=slots, prompt_len=7, seed=9)
+        dev = {k: v.cuda() for k, v in inp.items()}
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for lo in range(0, n_requests, slots):
+                model.generate(dev["input_ids"], dev["pixel_values"], dev["attention_mask"], max(budgets[lo:lo + slots]), **gen).cpu()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        res["static_useful_tokens_per_s"] = useful / dt
+    cb = ContinuousBatcher(model, num_slots=slots, max_prompt_len=N + 12, max_new_tokens=128, min_admit=min_admit, stage=stage,
+                           steps_per_replay=steps_per_replay, **gen)
+    for _ in range(2):
+        cb.reset_stats()
+        for (ids, px), m in zip(reqs, budgets):
+            cb.submit(ids, px, m)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = cb.run()
+        dt = time.perf_counter() - t0
+    assert sum(len(v) for v in out.values()) == useful
+    st = cb.stats
+    res.update({"useful_tokens_per_s": useful / dt, "requests_per_s": n_requests / dt, "prefill_groups": st["prefill_groups"],
+                "decode_steps": st["decode_steps"], "slot_occupancy": useful / max(1, st["decode_steps"] * slots)})
+    return res
+
+
 def run_reference_arm(args, cfg):
     """`--impl reference`: the reference algorithm (oracle port; the Python reference itself cannot travel to the GPU box)
     on the host cores, same config/metric, bounded sample per step."""
@@ -222,6 +265,7 @@ def main():
     ap.add_argument("--image-size", type=int, default=224)
     ap.add_argument("--greedy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-serving", action="store_true", help="skip the continuous-batching sample (N = 1 only)")
     args = ap.parse_args()
 
     from paligemma_multimodal_system_b200.random_init import make_inputs, paligemma_3b_config
@@ -357,6 +401,11 @@ def main():
                 "frac_of_hbm_peak": step_bytes / (steady_ms * 1e-3) / 1e9 / hbm_peak,
                 "note": "8-step decode graph replayed back to back without the preceding prefill burst (SM clocks at max)"},
         }
+        if world == 1 and not args.no_serving and args.image_size == 224:
+            try:
+                line["serving"] = measure_serving(model, cfg, slots=B, greedy=args.greedy)
+            except Exception as e:  # a reported extra, never allowed to take the headline line down
+                line["serving"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sd_cpu = {k: v.float().cpu() for k, v in sd.items()}

@@ -98,7 +98,7 @@ def test_continuous_batching_reproduces_the_reference_request_by_request(regime,
     toks, cb = _serve(model, reqs, budgets, num_slots=4, steps_per_replay=4, use_cuda_graph=graph, stage=stage, min_admit=min_admit)
     for r in range(10):
         assert toks[r] == G[f"{regime}_tokens"][r][: budgets[r]].tolist(), (r, toks[r])
-    assert cb.stats["prefill_rows"] == 10 and cb.stats["prefill_groups"] >= 2 and cb.stats["tokens"] == sum(budgets)
+    assert cb.stats["prefill_rows"] == 10 and cb.stats["prefill_groups"] >= (3 if stage == 0 else 1) and cb.stats["tokens"] == sum(budgets)
     assert sorted(cb.sched.free_sets) == list(range(4 + stage)) and sorted(cb.sched.free_slots) == [0, 1, 2, 3]
     # the batcher is reusable (captured graph, slots back to idle): a second wave gives the same answers
     rids = [cb.submit(*reqs[r], 8) for r in (9, 0, 5)]
