@@ -19,6 +19,28 @@ def shard_requests(batch: dict, world_size: int, rank: int) -> dict:
     return {k: v[lo:hi] for k, v in batch.items()}
 
 
+def shard_stream(n_requests: int, world_size: int, rank: int):
+    """Request stream over replicas (serving.ContinuousBatcher per GPU): round-robin, so that ragged prompt / answer
+    lengths in arrival order spread evenly.  Returns the indices rank `rank` serves."""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world_size")
+    return list(range(rank, n_requests, world_size))
+
+
+def gather_stream_results(local: dict, group=None) -> dict:
+    """{request index: token list} of every rank merged on all ranks (reporting only; off the timed path)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return dict(local)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, {int(k): [int(t) for t in v] for k, v in local.items()}, group=group)
+    out = {}
+    for part in parts:
+        assert not (set(part) & set(out)), "a request was served by two ranks"
+        out.update(part)
+    return out
+
+
 def gather_tokens(local_tokens: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
     """All-gathers the generated token ids [b_local, T] into [global_batch, T] (reporting only; off the timed path)."""
     import torch.distributed as dist
