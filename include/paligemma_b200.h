@@ -40,6 +40,7 @@ long long pg_launch_count(void);
 int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
+int pg_debug_set_gemm_bn(int bn); /* tuning sweeps: force the N tile (64 / 128 / 256) of the token-major GEMM, 0 = automatic */
 int pg_debug_set_decode_gemm_trace(long long* device_buffer); /* pg_gemm_decode: 8 stamps per launch */
 int pg_debug_decode_gemm_blocks_per_sm(int dynamic_smem_bytes); /* prints + returns cudaOccupancyMaxActiveBlocksPerMultiprocessor */
 int pg_debug_set_decode_gemm_cta_trace(long long* device_buffer); /* pg_gemm_decode: [grid][3] = smid, globaltimer in / out */

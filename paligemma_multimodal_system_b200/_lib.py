@@ -25,6 +25,7 @@ SIGNATURES = {
     "pg_launch_count": [],
     "pg_set_pdl": [i32],
     "pg_debug_set_gemm_trace": [p],
+    "pg_debug_set_gemm_bn": [i32],
     "pg_debug_set_attn_trace": [p],
     "pg_debug_topp_retries": [],
     "pg_debug_topp_trace": [p],
@@ -193,12 +194,19 @@ def gemm_residual(x, w, h, bias=None):
     T, K = x.shape
     F = w.shape[0]
     swap = 1 if T <= 128 else 0
+    kb = (K + 63) // 64
     if swap:
         tiles = (F + 127) // 128
     else:
         tiles = ((T + 127) // 128) * ((F + 255) // 256)
-    kb = (K + 63) // 64
-    if tiles >= 120 or kb < 8 or T > 512:  # (large-batch prefill keeps the deterministic, atomics-free epilogue)
+        if kb < 128:
+            # few-token prefill (latency path), short/medium K: count 128x64 tiles -- the kernel narrows its N tile before
+            # the host splits K, because every split costs a full fp32 red.add pass over the output tile (measured at
+            # T = 256: fc2 14 splits x 256 columns 34 us -> 4 splits x 64 columns 15.6 us; o_proj 6 splits 25.6 -> 1 split
+            # 15.4 us).  Long reductions (down_proj, K = 16384) keep wide tiles + splits: 64-column tiles re-read the
+            # activation tile from L2 too often.
+            tiles = ((T + 127) // 128) * ((F + 63) // 64)
+    if tiles >= 96 or kb < 8 or T > 512:  # (large-batch prefill keeps the deterministic, atomics-free epilogue)
         return gemm(x, w, h, mode=EPI_F32, bias=bias, resid=h, swap=swap)
     split = max(1, min(kb // 4, (2 * 148 if swap else 148) // tiles))
     return gemm(x, w, h, mode=EPI_ATOMIC_F32, bias=bias, swap=swap, split_k=split)

@@ -516,13 +516,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       uint32_t phase = 0;
       // The weight operand never depends on the previous kernel: with programmatic dependent launch its first
       // pipeline stages are fetched BEFORE griddepcontrol.wait, i.e. while the previous kernel is still running.
+      // (token-major kernel: the weights are operand B; only the first tile of a CTA can be prefetched this way, which is
+      //  what matters for the few-token latency path where a CTA has one tile and the launch chain is the critical path)
       int pre = 0;
-      if (SWAP && static_cast<int>(blockIdx.x) < num_tiles) {
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
         const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         pre = min(STAGES, t.kb1 - t.kb0);
         for (int s = 0; s < pre; ++s) {
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
+          if (SWAP) tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
+          else tma_load_2d(smem_base + s * STAGE_BYTES + A_TILE_BYTES, &tmapB, full_bar(s), (t.kb0 + s) * BK, t.n_blk * BN, hintB);
         }
       }
       if (tr) args.trace[1] = clock64();  // weights prefetch issued
@@ -533,14 +536,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          if (pre > 0) {  // weights of this stage are already in flight
+          const bool weights_in_flight = pre > 0;  // this stage's weight tile was requested before the dependency wait
+          if (weights_in_flight) {
             --pre;
           } else {
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
           }
-          tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
+          if (!(SWAP && weights_in_flight)) tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
+          if (!(!SWAP && weights_in_flight)) tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -724,6 +728,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_idx = 0;
 extern "C" int pg_debug_set_gemm_trace(long long* p) { g_gemm_trace = p; g_gemm_trace_idx = 0; return 0; }
+static int g_force_bn = 0;  // tuning sweeps only: 64 / 128 / 256 overrides the token-major kernel's N tile, 0 = automatic
+extern "C" int pg_debug_set_gemm_bn(int bn) {
+  if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return PG_ERR_ARG;
+  g_force_bn = bn;
+  return 0;
+}
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -831,6 +841,7 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     } else {
       BN = features > 128 ? 256 : features > 64 ? 128 : 64;
       while (BN > 64 && ntiles(BN) < 120) BN /= 2;
+      if (g_force_bn) BN = g_force_bn;
     }
     if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
