@@ -160,3 +160,33 @@ def test_batcher_input_validation():
     cb.submit(bad, px)
     with pytest.raises(ValueError):
         cb.run()
+
+
+def test_long_generation_crosses_kv_page_boundaries():
+    """140 new tokens from prompts of 258-263 tokens: the KV length passes the 64-token page boundaries at 320 and 384 in
+    generate() (teacher-forced logits against the oracle at every step, diffuse regime) and in the batcher (free-running
+    tokens against the oracle in the stable regime, slots refilled while others sit in their third page)."""
+    from oracle import paligemma_oracle as O
+    from paligemma_multimodal_system_b200.random_init import make_inputs
+    from paligemma_multimodal_system_b200.serving import ContinuousBatcher
+    T = 140
+    sd = make_state_dict(TINY_CONFIG, "R2", seed=11)
+    model = build_model(TINY_CONFIG, sd)
+    inp = make_inputs(TINY_CONFIG, batch=2, prompt_len=5, seed=31)
+    ref_t, ref_l = O.generate(sd, TINY_CONFIG, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], T, return_logits=True)
+    _, logits = model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), T,
+                               return_logits=True, forced_tokens=ref_t)
+    worst = max((stats(logits[r, t], ref_l[r, t])["rel"], r, t) for r in range(2) for t in range(T))
+    cos = min(stats(logits[r, t], ref_l[r, t])["cos"] for r in range(2) for t in range(T))
+    print(f"[long] teacher-forced R2, {T} steps: worst max-abs/absmax {worst[0]:.4f} at row {worst[1]} step {worst[2]}, min cosine {cos:.6f}")
+    assert worst[0] <= 3e-2 and cos >= 0.999
+    sd1 = make_state_dict(TINY_CONFIG, "R1", seed=11)
+    model1 = build_model(TINY_CONFIG, sd1)
+    reqs = make_requests(TINY_CONFIG, 5, 2, 7, seed=21)
+    budgets = [T, 70, T, 9, 100]
+    cb = ContinuousBatcher(model1, num_slots=2, max_prompt_len=264, max_new_tokens=T, steps_per_replay=8, stage=1)
+    rids = [cb.submit(ids, px, m) for (ids, px), m in zip(reqs, budgets)]
+    out = cb.run()
+    for r, (ids, px) in enumerate(reqs):
+        want = O.generate(sd1, TINY_CONFIG, ids[None], px[None], torch.ones(1, ids.numel(), dtype=torch.int64), budgets[r])[0].tolist()
+        assert out[rids[r]].tolist() == want, r
