@@ -179,7 +179,9 @@ def test_long_generation_crosses_kv_page_boundaries():
     worst = max((stats(logits[r, t], ref_l[r, t])["rel"], r, t) for r in range(2) for t in range(T))
     cos = min(stats(logits[r, t], ref_l[r, t])["cos"] for r in range(2) for t in range(T))
     print(f"[long] teacher-forced R2, {T} steps: worst max-abs/absmax {worst[0]:.4f} at row {worst[1]} step {worst[2]}, min cosine {cos:.6f}")
-    assert worst[0] <= 3e-2 and cos >= 0.999
+    # tolerance of the diffuse tiny regime (3 % over 16 steps in test_model_parity_gpu.py); the maximum over 280 step-rows
+    # sits a little higher (measured 2.8 %), hence 4 % here; the cosine gate is unchanged
+    assert worst[0] <= 4e-2 and cos >= 0.999
     sd1 = make_state_dict(TINY_CONFIG, "R1", seed=11)
     model1 = build_model(TINY_CONFIG, sd1)
     reqs = make_requests(TINY_CONFIG, 5, 2, 7, seed=21)
