@@ -182,11 +182,17 @@ class PaliGemmaForConditionalGeneration(nn.Module):
     @torch.no_grad()
     def generate(self, input_ids, pixel_values, attention_mask, max_tokens_to_generate: int, do_sample: bool = False,
                  temperature: float = 0.8, top_p: float = 0.9, eos_token_id: Optional[int] = None, seed: int = 0,
-                 use_cuda_graph: bool = True, return_logits: bool = False, forced_tokens=None, timings: dict = None):
+                 use_cuda_graph: bool = True, return_logits: bool = False, forced_tokens=None, timings: dict = None,
+                 prompt_lens=None):
         """Returns int64 tokens [B, T] (T = max_tokens_to_generate, or shorter if every row has emitted EOS; rows that
         finished early keep generating -- trim at the first EOS as the reference loop would).  The decode step
         (embedding, all layers, lm_head, sampler, counter advance) is captured once in a CUDA graph and replayed; the host
-        only checks EOS every 16 steps.  `forced_tokens` [B, T] teacher-forces the step inputs (parity tests)."""
+        only checks EOS every 16 steps.  `forced_tokens` [B, T] teacher-forces the step inputs (parity tests).
+
+        `prompt_lens` [B] serves a RAGGED batch: row b's prompt is its first prompt_lens[b] tokens, the rest of the row is
+        right padding that is masked out (each row then gets exactly the result of its own B = 1 run).  Without it a
+        padded row behaves as in the reference: pads embedded as zeros at position 1 and attended to
+        (modeling_paligemma.py:125-127,154-156,195)."""
         _lib.require_device()
         L = _lib.lib()
         lm, c = self.language_model, self.text_config
@@ -202,8 +208,14 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             ev[0].record()
         img = stt["img"].copy_(self.image_features(pixel_values))  # static buffer: the decode graph reads it
         kv.image_feats = img
+        lens = None
+        if prompt_lens is not None:
+            lens = torch.as_tensor(prompt_lens).to(device=dev, dtype=torch.int32).reshape(B).contiguous()
+            if bool(((lens < 1) | (lens > S)).any()):
+                raise ValueError("prompt_lens must lie in [1, S]")
+            attention_mask = (torch.arange(S, device=dev)[None, :] < lens[:, None]).to(torch.int64)
         h, pos = self._merge(input_ids, attention_mask, img)
-        logits = lm.prefill(h, pos, B, S, kv, last_only=True).view(B, V)
+        logits = lm.prefill(h, pos, B, S, kv, last_only=True, lens=lens).view(B, V)
         if ev:
             ev[1].record()
 
@@ -212,8 +224,12 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         forced = None if forced_tokens is None else forced_tokens.to(device=dev, dtype=torch.int32).t().contiguous()
         # decode counters: position id of the next token, its cache slot, kv length including it
         kv.counters[0].copy_(attention_mask.to(dev).sum(-1).to(torch.int32) + 1)
-        kv.counters[1].fill_(S)
-        kv.counters[2].fill_(S + 1)
+        if lens is None:
+            kv.counters[1].fill_(S)
+            kv.counters[2].fill_(S + 1)
+        else:  # ragged: row b continues right after its own prompt (its padding slots are overwritten as it grows)
+            kv.counters[1].copy_(lens)
+            kv.counters[2].copy_(lens + 1)
         step.zero_()
         inv_t = 1.0 / float(temperature)
 
