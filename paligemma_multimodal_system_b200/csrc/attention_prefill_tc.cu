@@ -11,10 +11,14 @@
 //   warp 1      tcgen05.mma issuer:  S_j = Q K_j^T  (M=128, N=BN, K=dh; both operands K-major, 128B swizzle)
 //                                    O  += P_j V_j  (M=128, N=dh, K=BN; P K-major from shared memory, V MN-major: the
 //                                                    [keys, dh] tile exactly as TMA delivers it)
-//   warps 2..5  softmax: thread = query row; S is read from TMEM (tcgen05.ld), P = exp2(s - m) goes to shared memory as
+//   warps 2..   softmax: thread = query row; S is read from TMEM (tcgen05.ld), P = exp2(s - m) goes to shared memory as
 //               bf16 in the swizzled A-operand layout, the row sum stays in registers.  The running maximum is only
 //               advanced when it grew by more than 2^8 (the O accumulator in TMEM then gets rescaled in place), which
-//               keeps the accumulator round trip off the common path.
+//               keeps the accumulator round trip off the common path.  SW = 1: four warps (one per TMEM lane quadrant),
+//               a thread owns all BN columns of its row.  SW = 2: eight warps, two per quadrant, each thread owns half of
+//               the columns of its row (the two halves exchange their tile maxima through shared memory and one 64-thread
+//               named barrier per tile): the softmax is bound by instruction issue of ONE warp per SM sub-partition
+//               (~6 instructions per score), and the second set of warps doubles the issue slots it gets.
 // S is double buffered in TMEM, so S_{j+1} is computed while the softmax of tile j runs, and P_j V_j runs while the
 // softmax of tile j+1 runs: the tensor pipe only idles when the softmax (MUFU exp2) is the longer stage (dh = 72).
 // Zero padding comes from TMA: columns beyond dh (72 -> 80) and key / query rows beyond the sequence are out-of-bounds
@@ -24,6 +28,10 @@
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"
+
+#ifndef PG_ATTN_PP_DEFAULT
+#define PG_ATTN_PP_DEFAULT 0
+#endif
 
 namespace pg {
 namespace ap {
@@ -55,7 +63,8 @@ struct Cfg {
   static constexpr int OFF_V = OFF_K + KST * KV_BYTES;
   static constexpr int OFF_P = OFF_V + VST * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int OFF_X = OFF_BAR + 256;          // float [2 S buffers][2 halves][128 rows]: tile maxima / row sums (SW = 2)
+  static constexpr int SMEM = OFF_X + 2048;
   static constexpr int TMEM_COLS = 512;
   static constexpr int COL_S = 0, COL_O = 2 * BN;
   static_assert(2 * BN + DHP <= 512, "TMEM budget");
@@ -108,8 +117,26 @@ PG_DEVINL float exp2_mufu(float x) {
   return y;
 }
 
-template <int DH>
-__global__ void __launch_bounds__(192, 1)
+// 2^x on the FMA / ALU pipes only (no MUFU, no F2I -- both live on the XU pipe, which is what saturates at dh <= 128:
+// ncu shows sm__inst_executed_pipe_xu_realtime at 100 % with the tensor pipe at 24 %).  Round-to-nearest range reduction by
+// the 1.5*2^23 trick (the integer part lands in the low mantissa bits), degree-4 polynomial of 2^f on [-0.5, 0.5]
+// (relative error 4e-5, far below the bf16 rounding the result goes through), 2^n by an exponent-field add.
+PG_DEVINL float exp2_fma(float x) {
+  const float xc = fmaxf(x, -125.0f);
+  const float t = xc + 12582912.0f;
+  const float f = xc - (t - 12582912.0f);
+  float p = 0.00961813f;
+  p = fmaf(p, f, 0.05550411f);
+  p = fmaf(p, f, 0.24022651f);
+  p = fmaf(p, f, 0.69314718f);
+  p = fmaf(p, f, 1.0f);
+  const float r = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+  return x < -125.0f ? 0.f : r;  // masked keys carry -inf and must weigh exactly nothing
+}
+
+// PP = how many of the four score pairs of every 8-key chunk take the FMA-pipe exponential (0 = all on the MUFU)
+template <int DH, int SW, int PP>
+__global__ void __launch_bounds__(64 + 128 * SW, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
   using C = Cfg<DH>;
@@ -147,8 +174,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
-      mbar_init(p_full(s), 4);
+      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4 * SW);
+      mbar_init(p_full(s), 4 * SW);
     }
     mbar_init(o_done, 1);
     mbar_fence_init();
@@ -227,21 +254,25 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
   } else {
     // ============================== softmax / epilogue ========================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // row inside the tile == TMEM lane
+    constexpr int HB = BN / SW;         // score columns of a tile owned by one thread
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which part of the columns (always 0 when SW == 1)
+    const int r = q * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int row = m_blk * BM + r;
+    float* xch = reinterpret_cast<float*>(smem_ap + C::OFF_X);  // [2][2][128]
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };  // the two warps of a quadrant
     float m_used = -INFINITY, l_run = 0.f;
     const uint32_t p_row = sbase + C::OFF_P + r * 128;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
       mbar_wait(s_full(sb), (j >> 1) & 1);
       tc_fence_after();
-      float s[BN];
+      float s[HB];
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = 0; c0 < HB; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(lane_addr + C::COL_S + sb * BN + c0, v);
+        tmem_ld16(lane_addr + C::COL_S + sb * BN + half * HB + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) s[c0 + i] = __uint_as_float(v[i]) * p.sl2;
@@ -249,12 +280,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(sb));  // the S buffer may be overwritten by S_{j+2}
-      const int nvalid = n_keys - j * BN;       // keys of this tile that exist
+      const int nvalid = n_keys - j * BN - half * HB;  // columns of this thread that are real keys
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < BN; ++i) {
+      for (int i = 0; i < HB; ++i) {
         if (i >= nvalid) s[i] = -INFINITY;
         mx = fmaxf(mx, s[i]);
+      }
+      if constexpr (SW == 2) {  // row maximum over both halves (buffer sb is rewritten two tiles later, one barrier apart)
+        xch[(sb * 2 + half) * 128 + r] = mx;
+        pair_sync();
+        mx = fmaxf(mx, xch[(sb * 2 + (half ^ 1)) * 128 + r]);
       }
       // lazy running maximum: only move it when it grew by more than 8 (log2 units); probabilities stay <= 2^8
       const bool need = mx > m_used + 8.0f;
@@ -264,26 +300,28 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float sum = 0.f;
       const uint32_t pdst = p_row + sb * C::P_BYTES;
 #pragma unroll
-      for (int c = 0; c < BN / 8; ++c) {  // 16-byte chunks of 8 keys
+      for (int cc = 0; cc < HB / 8; ++cc) {  // 16-byte chunks of 8 keys
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          // (measured: moving every other exponential to the FMA pipe with a degree-4 polynomial + exponent-field add makes
-          //  the dh = 72 kernel 40 % SLOWER: the softmax warps are bound by instruction issue, not by the MUFU rate)
-          const float p0 = exp2_mufu(s[c * 8 + 2 * e] - m_new), p1 = exp2_mufu(s[c * 8 + 2 * e + 1] - m_new);
+          // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
+          //  as well, so it added XU work instead of removing it)
+          const float x0 = s[cc * 8 + 2 * e] - m_new, x1 = s[cc * 8 + 2 * e + 1] - m_new;
+          const float p0 = e < PP ? exp2_fma(x0) : exp2_mufu(x0), p1 = e < PP ? exp2_fma(x1) : exp2_mufu(x1);
           sum += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
         }
+        const int c = half * (HB / 8) + cc;  // chunk index inside the whole tile row
         const uint32_t addr = pdst + (c >> 3) * C::P_BOX + (((c & 7) ^ (r & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       }
-      l_run = l_run * alpha + sum;
+      l_run = l_run * alpha + sum;  // (SW == 2: the sum over this thread's columns only; the halves are added at the end)
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need)) {  // (both warps of a quadrant see the same maxima, hence the same decision)
           tc_fence_after();
 #pragma unroll 1
-          for (int c0 = 0; c0 < DHP; c0 += 16) {
+          for (int c0 = half * 16; c0 < DHP; c0 += 16 * SW) {  // the halves take alternate 16-column slices of O
             uint32_t v[16];
             tmem_ld16(lane_addr + C::COL_O + c0, v);
             tmem_ld_wait();
@@ -300,6 +338,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (lane == 0) mbar_arrive(p_full(sb));
     }
     // ---- epilogue: O / l -> bf16 ----
+    if constexpr (SW == 2) {  // total row sum = sum over both halves
+      pair_sync();            // the partner has read the last tile's maximum: the exchange area is free
+      xch[half * 128 + r] = l_run;
+      pair_sync();
+      l_run += xch[(half ^ 1) * 128 + r];
+    }
     mbar_wait(o_done, (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l_run;
@@ -307,7 +351,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     bf16* orow = p.o + b * p.o_bs + h * p.o_head_off + static_cast<long long>(row / p.group) * p.o_ts +
                  static_cast<long long>(row % p.group) * p.o_hs;
 #pragma unroll 1
-    for (int c0 = 0; c0 < DHP; c0 += 16) {
+    for (int c0 = half * 16; c0 < DHP; c0 += 16 * SW) {
       uint32_t v[16];
       tmem_ld16(lane_addr + C::COL_O + c0, v);
       tmem_ld_wait();
@@ -353,19 +397,19 @@ static int make_tmap_nd(CUtensorMap* m, const void* ptr, int rank, const long lo
   return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
 }
 
-template <int DH>
+template <int DH, int SW, int PP>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int B, int H, cudaStream_t st) {
   using C = Cfg<DH>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
       cudaGetLastError();
       return PG_ERR_CUDA;
     }
     configured = true;
   }
   dim3 grid((p.rows + C::BM - 1) / C::BM, H, B);
-  attn_prefill_tc_kernel<DH><<<grid, 192, C::SMEM, st>>>(tq, tk, tv, p);
+  attn_prefill_tc_kernel<DH, SW, PP><<<grid, 64 + 128 * SW, C::SMEM, st>>>(tq, tk, tv, p);
   pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
@@ -411,9 +455,20 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   p.sl2 = scale * 1.4426950408889634f;
   p.key_lens = key_lens;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // softmax warps per TMEM lane quadrant and FMA-pipe exponentials per four score pairs (PG_ATTN_SW / PG_ATTN_PP: A/B runs)
+  static const int sw_env = getenv("PG_ATTN_SW") ? atoi(getenv("PG_ATTN_SW")) : 0;
+  static const int pp_env = getenv("PG_ATTN_PP") ? atoi(getenv("PG_ATTN_PP")) : -1;
+  const int sw = sw_env == 1 || sw_env == 2 ? sw_env : (dh > 128 ? 1 : 2);
+  const int pp = sw == 2 && pp_env >= 0 && pp_env <= 2 ? pp_env : (sw == 2 ? PG_ATTN_PP_DEFAULT : 0);
+#define PG_AP_LAUNCH(DHV)                                                          \
+  if (sw == 1) return ap::launch<DHV, 1, 0>(tq, tk, tv, p, B, H, st);              \
+  if (pp == 0) return ap::launch<DHV, 2, 0>(tq, tk, tv, p, B, H, st);              \
+  if (pp == 1) return ap::launch<DHV, 2, 1>(tq, tk, tv, p, B, H, st);              \
+  return ap::launch<DHV, 2, 2>(tq, tk, tv, p, B, H, st);
   switch (dh) {
-    case 64: return ap::launch<64>(tq, tk, tv, p, B, H, st);
-    case 72: return ap::launch<72>(tq, tk, tv, p, B, H, st);
-    default: return ap::launch<256>(tq, tk, tv, p, B, H, st);
+    case 64: PG_AP_LAUNCH(64)
+    case 72: PG_AP_LAUNCH(72)
+    default: PG_AP_LAUNCH(256)
   }
+#undef PG_AP_LAUNCH
 }
