@@ -46,28 +46,31 @@ struct Params {
   const int* key_lens;  // optional [B]: problem b only attends to its first key_lens[b] keys (ragged prompts); else nullptr
 };
 
-template <int DH>
+template <int DH, int QT>
 struct Cfg {
   static constexpr int BM = 128;
-  static constexpr int BN = DH > 128 ? 64 : 128;       // keys per tile
+  static constexpr int BN = (DH > 128 || QT == 2) ? 64 : 128;  // keys per tile
   static constexpr int DHP = (DH + 15) / 16 * 16;       // UMMA K (QK^T) / N (PV) extent: 72 -> 80
   static constexpr int NKB = (DH + 63) / 64;            // 64-column (128 B) boxes along dh
   static constexpr int Q_BOX = BM * 128;                // bytes of one Q box
   static constexpr int KV_BOX = BN * 128;               // bytes of one K / V box
-  static constexpr int Q_BYTES = NKB * Q_BOX;
+  static constexpr int Q_BYTES = NKB * Q_BOX;           // one query tile
   static constexpr int KV_BYTES = NKB * KV_BOX;
   static constexpr int P_BOX = BM * 128;                // [128 rows x 64 keys]
   static constexpr int P_BYTES = (BN / 64) * P_BOX;
-  static constexpr int KST = 2, VST = 2;                // ring depths
-  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int KST = QT == 2 ? 3 : 2, VST = KST;  // ring depths
+  static constexpr int OFF_K = QT * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KST * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + VST * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_P = OFF_V + VST * KV_BYTES;  // [QT][2 buffers][P_BYTES]
+  static constexpr int OFF_BAR = OFF_P + QT * 2 * P_BYTES;
   static constexpr int OFF_X = OFF_BAR + 256;          // float [2 S buffers][2 halves][128 rows]: tile maxima / row sums (SW = 2)
   static constexpr int SMEM = OFF_X + 2048;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int COL_S = 0, COL_O = 2 * BN;
-  static_assert(2 * BN + DHP <= 512, "TMEM budget");
+  static constexpr int COL_S = 0, COL_O = 2 * QT * BN;  // S: [QT][2 buffers][BN] columns, then O: [QT] accumulators
+  static constexpr int O_STRIDE = QT == 2 ? 128 : DHP;  // (two accumulators: each starts on a 128-column boundary)
+  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 7 * QT;
+  static_assert(2 * QT * BN + (QT - 1) * O_STRIDE + DHP <= 512, "TMEM budget");
+  static_assert(8 * NBAR + 8 <= 256, "barrier area");
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -134,31 +137,37 @@ PG_DEVINL float exp2_fma(float x) {
   return x < -125.0f ? 0.f : r;  // masked keys carry -inf and must weigh exactly nothing
 }
 
-// PP = how many of the four score pairs of every 8-key chunk take the FMA-pipe exponential (0 = all on the MUFU)
-template <int DH, int SW, int PP>
-__global__ void __launch_bounds__(64 + 128 * SW, 1)
+// PP = how many of the four score pairs of every 8-key chunk take the FMA-pipe exponential (0 = all on the MUFU).
+// QT = query tiles (128 rows each) per CTA.  QT = 2 (dh <= 128): both tiles run against the SAME K / V tiles in shared
+// memory -- the kernel is bound by K/V delivery through the crossbar (profiles/r01d_prefill_attn72_ncu_full.csv), and two
+// query tiles halve the K/V bytes per FLOP; softmax warps 2-5 own tile 0, warps 6-9 tile 1 (no exchange between them).
+template <int DH, int SW, int PP, int QT>
+__global__ void __launch_bounds__(64 + 128 * SW * QT, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
-  using C = Cfg<DH>;
-  constexpr int BM = C::BM, BN = C::BN, DHP = C::DHP, NKB = C::NKB;
+  static_assert(SW * QT <= 2, "eight softmax warps at most");
+  using C = Cfg<DH, QT>;
+  constexpr int BM = C::BM, BN = C::BN, DHP = C::DHP, NKB = C::NKB, KST = C::KST, VST = C::VST;
   constexpr uint32_t IDESC_S = make_idesc_bf16(BM, BN);
   constexpr uint32_t IDESC_O = make_idesc_bf16(BM, DHP, 0, 1);  // B (= V) is MN-major
   extern __shared__ __align__(1024) uint8_t smem_ap[];
   const uint32_t sbase = smem_u32(smem_ap);
   if ((sbase & 1023u) != 0) __trap();
   const uint32_t bar0 = sbase + C::OFF_BAR;
-  // barriers: q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full[2], o_done
+  // barriers: q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], then per query tile s_full[2], s_empty[2],
+  // p_full[2] and o_done
+  constexpr int S0 = 1 + 2 * KST + 2 * VST;
   const uint32_t q_full = bar0;
   auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
-  auto s_full = [&](int s) { return bar0 + 8u * (9 + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (11 + s); };
-  auto p_full = [&](int s) { return bar0 + 8u * (13 + s); };
-  const uint32_t o_done = bar0 + 8u * 15;
-  const uint32_t tmem_slot = bar0 + 8u * 16;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_ap + C::OFF_BAR + 8 * 16);
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + KST + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * KST + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 2 * KST + VST + s); };
+  auto s_full = [&](int qt, int s) { return bar0 + 8u * (S0 + qt * 2 + s); };
+  auto s_empty = [&](int qt, int s) { return bar0 + 8u * (S0 + 2 * QT + qt * 2 + s); };
+  auto p_full = [&](int qt, int s) { return bar0 + 8u * (S0 + 4 * QT + qt * 2 + s); };
+  auto o_done = [&](int qt) { return bar0 + 8u * (S0 + 6 * QT + qt); };
+  const uint32_t tmem_slot = bar0 + 8u * C::NBAR;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_ap + C::OFF_BAR + 8 * C::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -171,13 +180,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
-      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4 * SW);
-      mbar_init(p_full(s), 4 * SW);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    for (int qt = 0; qt < QT; ++qt) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(s_full(qt, s), 1); mbar_init(s_empty(qt, s), 4 * SW);
+        mbar_init(p_full(qt, s), 4 * SW);
+      }
+      mbar_init(o_done(qt), 1);
     }
-    mbar_init(o_done, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -192,18 +203,22 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      const int t0 = (m_blk * BM) / p.group;  // first token of this row tile (128 % group == 0)
-      mbar_expect_tx(q_full, C::Q_BYTES);
+      mbar_expect_tx(q_full, QT * C::Q_BYTES);
 #pragma unroll
-      for (int kb = 0; kb < NKB; ++kb) tma_load_5d(sbase + kb * C::Q_BOX, &tmQ, q_full, kb * 64, 0, t0, h, b);
+      for (int qt = 0; qt < QT; ++qt) {
+        const int t0 = ((m_blk * QT + qt) * BM) / p.group;  // first token of this row tile (128 % group == 0)
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb)
+          tma_load_5d(sbase + qt * C::Q_BYTES + kb * C::Q_BOX, &tmQ, q_full, kb * 64, 0, t0, h, b);
+      }
       for (int j = 0; j < n_tiles; ++j) {
-        const int ks = j % C::KST, vs = j % C::VST;
-        mbar_wait(k_empty(ks), ((j / C::KST) & 1) ^ 1);
+        const int ks = j % KST, vs = j % VST;
+        mbar_wait(k_empty(ks), ((j / KST) & 1) ^ 1);
         mbar_expect_tx(k_full(ks), C::KV_BYTES);
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb)
           tma_load_4d(sbase + C::OFF_K + ks * C::KV_BYTES + kb * C::KV_BOX, &tmK, k_full(ks), kb * 64, j * BN, h, b);
-        mbar_wait(v_empty(vs), ((j / C::VST) & 1) ^ 1);
+        mbar_wait(v_empty(vs), ((j / VST) & 1) ^ 1);
         mbar_expect_tx(v_full(vs), C::KV_BYTES);
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb)
@@ -214,41 +229,47 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
     if (lane == 0) {
-      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j % 2
-        const int ks = j % C::KST, sb = j & 1;
-        mbar_wait(k_full(ks), (j / C::KST) & 1);
-        mbar_wait(s_empty(sb), ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + C::COL_S + sb * BN;
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T of every query tile into its S buffer j % 2
+        const int ks = j % KST, sb = j & 1;
+        mbar_wait(k_full(ks), (j / KST) & 1);
         const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t adesc = make_sdesc_k_sw128(sbase + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
-          const uint64_t bdesc = make_sdesc_k_sw128(kaddr + (k >> 2) * C::KV_BOX) + 2 * (k & 3);
-          umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
+        for (int qt = 0; qt < QT; ++qt) {
+          mbar_wait(s_empty(qt, sb), ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + C::COL_S + (qt * 2 + sb) * BN;
+#pragma unroll
+          for (int k = 0; k < DHP / 16; ++k) {
+            const uint64_t adesc = make_sdesc_k_sw128(sbase + qt * C::Q_BYTES + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
+            const uint64_t bdesc = make_sdesc_k_sw128(kaddr + (k >> 2) * C::KV_BOX) + 2 * (k & 3);
+            umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(qt, sb));
         }
         umma_commit(k_empty(ks));
-        umma_commit(s_full(sb));
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_s(j + 1);
-        const int vs = j % C::VST, pb = j & 1;
-        mbar_wait(v_full(vs), (j / C::VST) & 1);
-        mbar_wait(p_full(pb), (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + C::COL_O;
-        const uint32_t paddr = sbase + C::OFF_P + pb * C::P_BYTES;
+        const int vs = j % VST, pb = j & 1;
+        mbar_wait(v_full(vs), (j / VST) & 1);
         const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
-          const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);  // 16 keys = two 8-row groups
-          umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
+        for (int qt = 0; qt < QT; ++qt) {
+          mbar_wait(p_full(qt, pb), (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + C::COL_O + qt * C::O_STRIDE;
+          const uint32_t paddr = sbase + C::OFF_P + (qt * 2 + pb) * C::P_BYTES;
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) {
+            const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
+            const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);  // 16 keys = two 8-row groups
+            umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(o_done(qt));
         }
         umma_commit(v_empty(vs));
-        umma_commit(o_done);
       }
     }
     __syncwarp();
@@ -256,37 +277,46 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ============================== softmax / epilogue ========================
     constexpr int HB = BN / SW;         // score columns of a tile owned by one thread
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // which part of the columns (always 0 when SW == 1)
+    const int grp = (warp - 2) >> 2;    // second set of four warps: the other column half (SW = 2) or query tile 1 (QT = 2)
+    const int half = SW == 2 ? grp : 0;
+    const int qt = QT == 2 ? grp : 0;
     const int r = q * 32 + lane;        // row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int row = m_blk * BM + r;
+    const int row = (m_blk * QT + qt) * BM + r;
+    const uint32_t col_s = C::COL_S + qt * 2 * BN, col_o = C::COL_O + qt * C::O_STRIDE;
     float* xch = reinterpret_cast<float*>(smem_ap + C::OFF_X);  // [2][2][128]
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };  // the two warps of a quadrant
     float m_used = -INFINITY, l_run = 0.f;
-    const uint32_t p_row = sbase + C::OFF_P + r * 128;
+    const uint32_t p_row = sbase + C::OFF_P + qt * 2 * C::P_BYTES + r * 128;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
-      mbar_wait(s_full(sb), (j >> 1) & 1);
+      mbar_wait(s_full(qt, sb), (j >> 1) & 1);
       tc_fence_after();
       float s[HB];
 #pragma unroll
       for (int c0 = 0; c0 < HB; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(lane_addr + C::COL_S + sb * BN + half * HB + c0, v);
+        tmem_ld16(lane_addr + col_s + sb * BN + half * HB + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s[c0 + i] = __uint_as_float(v[i]) * p.sl2;
+        for (int i = 0; i < 16; ++i) s[c0 + i] = __uint_as_float(v[i]);  // raw scores: the scale rides on the FFMA below
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(sb));  // the S buffer may be overwritten by S_{j+2}
+      if (lane == 0) mbar_arrive(s_empty(qt, sb));  // the S buffer may be overwritten by S_{j+2}
+      // The softmax warps are bound by instruction issue (ncu: ~9 instructions per score, XU pipe 39 %, tensor pipe 24 %), so
+      // the per-score work is kept to FMNMX, FFMA, MUFU, FADD and half an F2FP: keys are only masked in the one tile that
+      // has padding, and the softmax scale is folded into the exponent's FFMA (scale > 0: max commutes with it).
       const int nvalid = n_keys - j * BN - half * HB;  // columns of this thread that are real keys
+      if (nvalid < HB) {
+#pragma unroll
+        for (int i = 0; i < HB; ++i)
+          if (i >= nvalid) s[i] = -INFINITY;
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < HB; ++i) {
-        if (i >= nvalid) s[i] = -INFINITY;
-        mx = fmaxf(mx, s[i]);
-      }
+      for (int i = 0; i < HB; ++i) mx = fmaxf(mx, s[i]);
+      mx *= p.sl2;
       if constexpr (SW == 2) {  // row maximum over both halves (buffer sb is rewritten two tiles later, one barrier apart)
         xch[(sb * 2 + half) * 128 + r] = mx;
         pair_sync();
@@ -306,7 +336,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int e = 0; e < 4; ++e) {
           // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
           //  as well, so it added XU work instead of removing it)
-          const float x0 = s[cc * 8 + 2 * e] - m_new, x1 = s[cc * 8 + 2 * e + 1] - m_new;
+          const float x0 = fmaf(s[cc * 8 + 2 * e], p.sl2, -m_new), x1 = fmaf(s[cc * 8 + 2 * e + 1], p.sl2, -m_new);
           const float p0 = e < PP ? exp2_fma(x0) : exp2_mufu(x0), p1 = e < PP ? exp2_fma(x1) : exp2_mufu(x1);
           sum += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
@@ -317,17 +347,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       l_run = l_run * alpha + sum;  // (SW == 2: the sum over this thread's columns only; the halves are added at the end)
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
+        mbar_wait(o_done(qt), (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
         if (__any_sync(0xffffffffu, need)) {  // (both warps of a quadrant see the same maxima, hence the same decision)
           tc_fence_after();
 #pragma unroll 1
           for (int c0 = half * 16; c0 < DHP; c0 += 16 * SW) {  // the halves take alternate 16-column slices of O
             uint32_t v[16];
-            tmem_ld16(lane_addr + C::COL_O + c0, v);
+            tmem_ld16(lane_addr + col_o + c0, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st16(lane_addr + C::COL_O + c0, v);
+            tmem_st16(lane_addr + col_o + c0, v);
           }
           tmem_st_wait();
         }
@@ -335,7 +365,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(sb));
+      if (lane == 0) mbar_arrive(p_full(qt, sb));
     }
     // ---- epilogue: O / l -> bf16 ----
     if constexpr (SW == 2) {  // total row sum = sum over both halves
@@ -344,7 +374,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       pair_sync();
       l_run += xch[(half ^ 1) * 128 + r];
     }
-    mbar_wait(o_done, (n_tiles - 1) & 1);
+    mbar_wait(o_done(qt), (n_tiles - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const bool row_ok = row < p.rows;
@@ -353,7 +383,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll 1
     for (int c0 = half * 16; c0 < DHP; c0 += 16 * SW) {
       uint32_t v[16];
-      tmem_ld16(lane_addr + C::COL_O + c0, v);
+      tmem_ld16(lane_addr + col_o + c0, v);
       tmem_ld_wait();
       if (row_ok) {
         uint32_t pk[8];
@@ -397,19 +427,19 @@ static int make_tmap_nd(CUtensorMap* m, const void* ptr, int rank, const long lo
   return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
 }
 
-template <int DH, int SW, int PP>
+template <int DH, int SW, int PP, int QT>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int B, int H, cudaStream_t st) {
-  using C = Cfg<DH>;
+  using C = Cfg<DH, QT>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, PP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
       cudaGetLastError();
       return PG_ERR_CUDA;
     }
     configured = true;
   }
-  dim3 grid((p.rows + C::BM - 1) / C::BM, H, B);
-  attn_prefill_tc_kernel<DH, SW, PP><<<grid, 64 + 128 * SW, C::SMEM, st>>>(tq, tk, tv, p);
+  dim3 grid((p.rows + C::BM * QT - 1) / (C::BM * QT), H, B);
+  attn_prefill_tc_kernel<DH, SW, PP, QT><<<grid, 64 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
   pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
@@ -425,6 +455,7 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
                             long long o_head_off, float scale, const int* key_lens, void* stream) {
   using namespace pg;
   if (dh != 64 && dh != 72 && dh != 256) return 1;
+  if (!(scale > 0.f)) return 1;  // the kernel takes row maxima before scaling
   if (group <= 0 || (128 % group) != 0 || (rows % group) != 0) return 1;
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   auto ok8 = [](long long s) { return s > 0 && (s % 8) == 0; };
@@ -440,7 +471,12 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
     const int box[5] = {64, group, 128 / group, 1, 1};
     if ((rc = ap::make_tmap_nd(&tq, q, 5, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
   }
-  const int BN = dh > 128 ? 64 : 128;
+  // query tiles per CTA (PG_ATTN_QT=1|2 overrides: A/B runs).  Two tiles (64-key steps) win while a head has few key tiles
+  // -- fewer, fuller CTAs: SigLIP 224 px 0.107 -> 0.088 ms, 448 px 0.389 -> 0.366 ms per layer -- and lose slightly at 4096 keys
+  // (1.158 vs 1.190 ms), where the 128-key steps of the one-tile variant amortise the per-step barrier traffic better.
+  static const int qt_env = getenv("PG_ATTN_QT") ? atoi(getenv("PG_ATTN_QT")) : 0;
+  const int qt = dh > 128 ? 1 : (qt_env == 1 || qt_env == 2 ? qt_env : (rows > 128 && keys <= 2048 ? 2 : 1));
+  const int BN = (dh > 128 || qt == 2) ? 64 : 128;
   {
     const long long dims[4] = {dh, keys, H, B};
     const long long strides[4] = {1, kv_ts, kv_head_off, kv_bs};
@@ -455,20 +491,27 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   p.sl2 = scale * 1.4426950408889634f;
   p.key_lens = key_lens;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // softmax warps per TMEM lane quadrant and FMA-pipe exponentials per four score pairs (PG_ATTN_SW / PG_ATTN_PP: A/B runs)
+  // softmax warps per TMEM lane quadrant (one query tile per CTA only) and FMA-pipe exponentials per four score pairs
+  // (PG_ATTN_SW / PG_ATTN_PP: A/B runs)
   static const int sw_env = getenv("PG_ATTN_SW") ? atoi(getenv("PG_ATTN_SW")) : 0;
   static const int pp_env = getenv("PG_ATTN_PP") ? atoi(getenv("PG_ATTN_PP")) : -1;
-  const int sw = sw_env == 1 || sw_env == 2 ? sw_env : (dh > 128 ? 1 : 2);
-  const int pp = sw == 2 && pp_env >= 0 && pp_env <= 2 ? pp_env : (sw == 2 ? PG_ATTN_PP_DEFAULT : 0);
-#define PG_AP_LAUNCH(DHV)                                                          \
-  if (sw == 1) return ap::launch<DHV, 1, 0>(tq, tk, tv, p, B, H, st);              \
-  if (pp == 0) return ap::launch<DHV, 2, 0>(tq, tk, tv, p, B, H, st);              \
-  if (pp == 1) return ap::launch<DHV, 2, 1>(tq, tk, tv, p, B, H, st);              \
-  return ap::launch<DHV, 2, 2>(tq, tk, tv, p, B, H, st);
-  switch (dh) {
-    case 64: PG_AP_LAUNCH(64)
-    case 72: PG_AP_LAUNCH(72)
-    default: PG_AP_LAUNCH(256)
+  const int sw = qt == 2 ? 1 : (sw_env == 1 || sw_env == 2 ? sw_env : (dh > 128 ? 1 : 2));
+  const int pp = pp_env >= 0 && pp_env <= 2 && (sw == 2 || qt == 2) ? pp_env : 0;
+#define PG_AP_LAUNCH1(DHV)                                                           \
+  if (sw == 1) return ap::launch<DHV, 1, 0, 1>(tq, tk, tv, p, B, H, st);             \
+  if (pp == 0) return ap::launch<DHV, 2, 0, 1>(tq, tk, tv, p, B, H, st);             \
+  if (pp == 1) return ap::launch<DHV, 2, 1, 1>(tq, tk, tv, p, B, H, st);             \
+  return ap::launch<DHV, 2, 2, 1>(tq, tk, tv, p, B, H, st);
+#define PG_AP_LAUNCH2(DHV)                                                           \
+  if (qt == 2) {                                                                     \
+    if (pp == 0) return ap::launch<DHV, 1, 0, 2>(tq, tk, tv, p, B, H, st);           \
+    return ap::launch<DHV, 1, 1, 2>(tq, tk, tv, p, B, H, st);                        \
   }
-#undef PG_AP_LAUNCH
+  switch (dh) {
+    case 64: PG_AP_LAUNCH2(64) PG_AP_LAUNCH1(64)
+    case 72: PG_AP_LAUNCH2(72) PG_AP_LAUNCH1(72)
+    default: PG_AP_LAUNCH1(256)
+  }
+#undef PG_AP_LAUNCH1
+#undef PG_AP_LAUNCH2
 }
