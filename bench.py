@@ -221,7 +221,8 @@ def measure_serving(model, cfg, n_requests=256, slots=64, stage=32, min_admit=16
     assert sum(len(v) for v in out.values()) == useful
     st = cb.stats
     res.update({"useful_tokens_per_s": useful / dt, "requests_per_s": n_requests / dt, "prefill_groups": st["prefill_groups"],
-                "decode_steps": st["decode_steps"], "slot_occupancy": useful / max(1, st["decode_steps"] * slots)})
+                "decode_steps": st["decode_steps"], "slot_occupancy": useful / max(1, st["decode_steps"] * slots),
+                "host_ms": {k[2:-2]: round(1e3 * v, 1) for k, v in st.items() if k.startswith("t_")}})
     return res
 
 

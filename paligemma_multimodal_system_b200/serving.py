@@ -168,7 +168,8 @@ class ContinuousBatcher:
         self.reset_stats()
 
     def reset_stats(self):
-        self.stats = dict(prefill_groups=0, prefill_rows=0, decode_replays=0, decode_steps=0, tokens=0, wall_s=0.0)
+        self.stats = dict(prefill_groups=0, prefill_rows=0, decode_replays=0, decode_steps=0, tokens=0, wall_s=0.0,
+                          t_prefill_s=0.0, t_prefill_prep_s=0.0, t_arm_s=0.0, t_decode_s=0.0, t_retire_s=0.0)  # host wall time per phase
 
     # -- host API --------------------------------------------------------------------------------------------------
     def submit(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, max_new_tokens: Optional[int] = None) -> int:
@@ -187,15 +188,22 @@ class ContinuousBatcher:
     def run(self) -> Dict[int, torch.Tensor]:
         """Serves every submitted request; returns {request id: int64 tokens} (EOS included when it was emitted)."""
         t0 = time.perf_counter()
+        clk, st = time.perf_counter, self.stats
         while not self.sched.idle():
+            ta = clk()
             reqs = self.sched.plan_prefill()
             if reqs:
-                self._prefill(reqs)
+                self._prefill(reqs)  # (ends with the D2H read of the first tokens: device time of the prefill included)
+            tb = clk()
             pairs = self.sched.plan_arming()
             if pairs:
                 self._arm(pairs)
+            tc = clk()
             if self.sched.active:
                 self._decode_group()
+            st["t_prefill_s"] += tb - ta
+            st["t_arm_s"] += tc - tb
+            st["t_decode_s"] += clk() - tc
         torch.cuda.synchronize()
         self.stats["wall_s"] += time.perf_counter() - t0
         out = {rid: torch.tensor(t, dtype=torch.int64) for rid, t in self.sched.finished.items()}
@@ -226,6 +234,7 @@ class ContinuousBatcher:
     def _prefill(self, reqs: List[Request]):
         """One ragged prefill: keys/values of request i land in its page set, its first token is sampled."""
         model, c = self.model, self.c
+        t_prep = time.perf_counter()
         g = len(reqs)
         lens = [int(r.input_ids.numel()) for r in reqs]
         S = max(lens)
@@ -238,6 +247,7 @@ class ContinuousBatcher:
         px = torch.stack([r.pixel_values for r in reqs]).to("cuda", non_blocking=True)
         sets_t = torch.tensor([r.page_set for r in reqs], device="cuda", dtype=torch.int64)
         lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+        self.stats["t_prefill_prep_s"] += time.perf_counter() - t_prep  # host batching + H2D of the pixels
         img = model.image_features(px)
         self.img_sets.index_copy_(0, sets_t, img[:, 0].contiguous())
         h, pos = model._merge(ids.cuda(), mask.cuda(), img)
@@ -304,7 +314,10 @@ class ContinuousBatcher:
             for _ in range(self.GK):
                 self._step()
         ring = self.ring.cpu()  # [GK, B]; the one host sync per group
+        t0 = time.perf_counter()
         self.stats["decode_replays"] += 1
         self.stats["decode_steps"] += self.GK
-        done = [slot for slot in list(self.sched.active) if self._consume(slot, ring[:, slot].tolist())]
+        cols = ring.t().tolist()
+        done = [slot for slot in list(self.sched.active) if self._consume(slot, cols[slot])]
         self._set_idle(done)
+        self.stats["t_retire_s"] += time.perf_counter() - t0
