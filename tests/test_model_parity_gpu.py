@@ -120,6 +120,32 @@ def test_generate_greedy_identical_to_reference(regime):
     assert toks2[0].tolist() == G[f"{regime}_greedy_tokens"].tolist()
 
 
+def test_graphed_prefill_of_the_latency_path_follows_its_inputs():
+    """From the second generate() call of a geometry the whole prefill replays as one CUDA graph over static input buffers:
+    different requests through the same graph must give what the eager path gives, errors included."""
+    sd = make_state_dict(TINY_CONFIG, "R1", seed=11)
+    model = build_model(TINY_CONFIG, sd)
+    a = make_inputs(TINY_CONFIG, batch=2, prompt_len=4, seed=5)
+    b = make_inputs(TINY_CONFIG, batch=2, prompt_len=4, seed=77)
+    b["input_ids"][:, -1] = torch.tensor([300, 417])  # R1 echoes the last prompt token: make the answers differ
+    run = lambda inp, **kw: model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), 8, **kw)
+    eager_a, eager_b = run(a, use_cuda_graph=False), run(b, use_cuda_graph=False)
+    assert eager_a[0].tolist() == G["R1_greedy_tokens"][:8].tolist() and eager_a.tolist() != eager_b.tolist()
+    first = run(a)            # eager warm-up of the graphed path
+    second = run(b)           # capture + replay
+    third = run(a)            # replay with other inputs
+    assert model._graphs and any(st.get("prefill", {}).get("graph") is not None for st in model._graphs.values())
+    assert first.tolist() == eager_a.tolist() and second.tolist() == eager_b.tolist() and third.tolist() == eager_a.tolist()
+    _, lg = run(b, return_logits=True)
+    _, le = run(b, return_logits=True, use_cuda_graph=False)
+    assert stats(lg[:, 0], le[:, 0])["rel"] < 1e-3  # prefill logits: same kernels, split-K order aside
+    bad = {k: v.clone() for k, v in a.items()}
+    bad["input_ids"][1, 3] = 5  # 255 image tokens in row 1
+    with pytest.raises(ValueError):
+        run(bad)
+    assert run(a).tolist() == eager_a.tolist()  # the graph is still usable after a rejected request
+
+
 def test_batched_generate_rows_equal_single_row_runs():
     """B > 1 (not runnable in the reference): every row must reproduce its own B = 1 run, oracle as the judge."""
     sd = make_state_dict(TINY_CONFIG, "R2", seed=3)
