@@ -149,6 +149,29 @@ def test_graphed_prefill_of_the_latency_path_follows_its_inputs():
     assert run(a).tolist() == eager_a.tolist()  # the graph is still usable after a rejected request
 
 
+@pytest.mark.parametrize("image_size,batch", [(448, 2), (896, 1)])
+def test_long_image_sequences_1024_and_4096_image_tokens(image_size, batch):
+    """BASELINE configs[3] / [4] geometry (1024 / 4096 image tokens, position table, merge, many key tiles in both prefill
+    attentions, a KV cache of 17 / 65 pages) on the tiny widths, so that the CPU oracle stays cheap: prefill + teacher-forced
+    decode logits and free-running greedy tokens against the oracle."""
+    import copy
+    cfg = copy.deepcopy(TINY_CONFIG)
+    cfg["vision_config"]["image_size"] = image_size
+    sd = make_state_dict(cfg, "R1", seed=13)
+    model = build_model(cfg, sd)
+    inp = make_inputs(cfg, batch=batch, prompt_len=5, seed=3)
+    inp["input_ids"][:, -1] = torch.arange(batch) + 200  # R1 echoes the last prompt token: rows differ
+    T = 6
+    ref_t, ref_l = O.generate(sd, cfg, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], T, return_logits=True)
+    toks, logits = model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), T,
+                                  return_logits=True, forced_tokens=ref_t)
+    for r in range(batch):
+        _check(logits[r], ref_l[r], "R1", f"{image_size}px teacher-forced logits row {r}")
+    free = model.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), T)
+    assert free.cpu().tolist() == ref_t.tolist()
+    assert model._graphs[next(iter(model._graphs))]["kv"].page_table.shape[1] >= (image_size // 14) ** 2 // 64 + 1
+
+
 def test_batched_generate_rows_equal_single_row_runs():
     """B > 1 (not runnable in the reference): every row must reproduce its own B = 1 run, oracle as the judge."""
     sd = make_state_dict(TINY_CONFIG, "R2", seed=3)
