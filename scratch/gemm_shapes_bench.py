@@ -27,7 +27,10 @@ for name, T, F, K, kind in shapes:
         fn = lambda: _lib.gemm(x, w, out, mode=_lib.EPI_GEGLU, swap=0)
     else:
         out = torch.randn(T, F, device="cuda")
-        fn = lambda: _lib.gemm(x, w, out, mode=_lib.EPI_F32, bias=bias if "siglip" in name else None, resid=out if kind == "f32r" else None, swap=0)
+        if kind == "f32r":
+            fn = lambda: _lib.gemm_residual(x, w, out, bias=bias if "siglip" in name else None)
+        else:
+            fn = lambda: _lib.gemm(x, w, out, mode=_lib.EPI_F32, swap=0)
     ms = t(fn)
     fl = 2.0 * T * F * K
     y = torch.empty(T, F, device="cuda", dtype=torch.bfloat16)
