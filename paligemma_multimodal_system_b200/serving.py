@@ -179,6 +179,16 @@ class ContinuousBatcher:
             raise ValueError(f"prompt of {ids.numel()} tokens does not fit max_prompt_len = {self.max_prompt_len}")
         if not 1 <= m <= self.max_new_tokens:
             raise ValueError(f"max_new_tokens must lie in [1, {self.max_new_tokens}]")
+        # a bad request is refused HERE, never in the middle of a prefill group that carries other requests
+        if bool(((ids < 0) | (ids >= self.c.vocab_size)).any()):
+            raise IndexError("input_ids out of range for the embedding table")
+        n_img = int((ids == self.model.dummy_image_token_id).sum())
+        if n_img != self.c.num_image_tokens:
+            raise ValueError(f"a request must hold exactly {self.c.num_image_tokens} image tokens (id "
+                             f"{self.model.dummy_image_token_id}), got {n_img}")
+        vc = self.model.vision_config
+        if tuple(pixel_values.shape) != (vc.num_channels, vc.image_size, vc.image_size):
+            raise ValueError(f"pixel_values must be [{vc.num_channels}, {vc.image_size}, {vc.image_size}], got {tuple(pixel_values.shape)}")
         rid = self._next_rid
         self._next_rid += 1
         self.sched.submit(Request(rid, ids, pixel_values, m))

@@ -176,10 +176,17 @@ def test_batcher_input_validation():
     with pytest.raises(ValueError):
         cb.submit(ids[:258], px, 5)  # budget above the batcher's
     bad = ids[:258].clone()
-    bad[3] = 5  # 255 image tokens: the merge kernel's check (the reference mis-scatters silently)
-    cb.submit(bad, px)
+    bad[3] = 5  # 255 image tokens (the reference mis-scatters silently): refused at submit, not inside a prefill group
     with pytest.raises(ValueError):
-        cb.run()
+        cb.submit(bad, px)
+    with pytest.raises(ValueError):
+        cb.submit(ids[:258], px[:, :100])
+    oob = ids[:258].clone()
+    oob[-1] = 5000
+    with pytest.raises(IndexError):
+        cb.submit(oob, px)
+    rid = cb.submit(ids[:258], px)
+    assert list(cb.run()) == [rid]  # the batcher is untouched by the refused requests
 
 
 def test_long_generation_crosses_kv_page_boundaries():
