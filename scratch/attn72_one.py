@@ -3,7 +3,8 @@ import sys, torch
 sys.path.insert(0, '.')
 from paligemma_multimodal_system_b200 import _lib
 L = _lib.lib()
-B, N, H, dh = 8, 4096, 16, 72
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+B, H, dh = 32768 // N, 16, 72
 D = H * dh
 qkv = (torch.randn(B * N, 3 * D, device="cuda") * 0.7).bfloat16()
 out = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
