@@ -33,6 +33,8 @@ extern "C" {
 /* Library / device info.  Returns the ABI version (>0) or PG_ERR_ARCH when the current device is not sm_100. */
 int pg_abi_version(void);
 int pg_check_device(void);
+/* Streaming multiprocessors of the current device (the host side sizes split-K factors and persistent grids with it). */
+int pg_num_sms(void);
 /* Number of kernel launches this library has issued in the calling process (host-side counter). */
 long long pg_launch_count(void);
 /* Programmatic dependent launch for the decode-step kernels (default on): the next kernel's prologue and weight
@@ -41,10 +43,6 @@ int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
 int pg_debug_set_gemm_bn(int bn); /* tuning sweeps: force the N tile (64 / 128 / 256) of the token-major GEMM, 0 = automatic */
-int pg_debug_set_decode_gemm_trace(long long* device_buffer); /* pg_gemm_decode: 8 stamps per launch */
-int pg_debug_decode_gemm_blocks_per_sm(int dynamic_smem_bytes); /* prints + returns cudaOccupancyMaxActiveBlocksPerMultiprocessor */
-int pg_debug_set_decode_gemm_cta_trace(long long* device_buffer); /* pg_gemm_decode: [grid][3] = smid, globaltimer in / out */
-int pg_debug_decode_gemm_max_clusters(int cluster_k); /* cudaOccupancyMaxActiveClusters of the 64-token decode GEMM */
 int pg_debug_set_topp_bracket(int half_width_bins); /* > 0 overrides the estimated-bracket half width of pg_sample_top_p */
 int pg_debug_topp_trace(long long* host_out16); /* clock64 stamps of CTA 0 after each phase of the last pg_sample_top_p */
 int pg_debug_topp_retries(void); /* rows whose estimated top-p bracket failed verification (second full pass), cumulative */
@@ -61,35 +59,41 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
                  const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
                  int act_gelu, float scale, int swap, int split_k, void* stream);
 
-/* Same, with the RMSNorm factor of the PRODUCER of x applied in the epilogue (swap kernels only): acc[t,f] is multiplied
- * by rsqrt(ss_in[t] / norm_dim + eps) before bias / activation / GEGLU.  x then holds bf16(h * (1 + w)) and ss_in[t] the
- * sum of squares of the fp32 h row (GemmaRMSNorm, modeling_gemma.py:172-181, folded into the consumer GEMM). */
-int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
-                         const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
-                         int act_gelu, float scale, int swap, int split_k, const float* ss_in, int norm_dim, float eps,
-                         void* stream);
-
 /*
- * Decode-step GEMM (tokens <= 128) with the split-K reduction done inside a thread-block cluster through distributed
- * shared memory (no global atomics): cluster_k in {1,2,4,8,16} CTAs share one 128-row output tile.  Replaces q/k/v_proj,
- * o_proj and down_proj at q_len == 1 (modeling_gemma.py:274-278,356,210-218) and the GemmaRMSNorm that follows the
- * residual add (modeling_gemma.py:172-181,393-417).
- *   PG_DEC_F32:        out[t,f] = acc * rsqrt(ss_in[t]/norm_dim + eps) + bias[f]     (ss_in, bias optional)
- *   PG_DEC_RESID_NORM: out[t,f] += acc  (fp32 residual stream, in place);  hb[t,f] = bf16(out[t,f] * (1 + norm_w[f]));
- *                      ss_out[t] += sum_f out[t,f]^2  (ss_out must be zero before the launch)
+ * pg_gemm_bf16 with the decode-step fusions of the swap-AB (tokens <= 128) kernels; `fusion` may be NULL (= pg_gemm_bf16).
+ *
+ *  - x_f32 != NULL: the activation operand is built IN the kernel from fp32 rows (the residual stream), x is ignored:
+ *        X[t,k] = bf16(x_f32[t,k] * (1 + norm_w[k]))
+ *    i.e. GemmaRMSNorm (modeling_gemma.py:172-181) without its per-token factor r[t] = rsqrt(mean_k x_f32[t,k]^2 + eps), which
+ *    is linear in the GEMM.  apply_rstd = 1 (split_k must be 1): the epilogue multiplies the accumulator by r[t] before bias /
+ *    activation / GEGLU, so out = Linear(GemmaRMSNorm(x_f32)) exactly as modeling_gemma.py:395-396,412-413 chain them.
+ *    apply_rstd = 0: the CONSUMER applies r[t] (split-K q/k/v projection -> pg_attention_decode_fused, which computes r[t]
+ *    from the same rows).  Replaces the standalone RMSNorm launch and its bf16 round trip.
+ *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; used to reset the
+ *    split-K accumulator that a later kernel of the chain red.adds into.
+ *  - pf_*: L2 prefetch (cp.async.bulk.prefetch.L2) of the K and V pages [0, ceil(pf_kv_len[b] / 64)) of every sequence b,
+ *    pages located through pf_page_table [pf_B, pf_max_pages]; pf_page_bytes = 64 * Hkv * dh * 2.  Issued before the
+ *    dependency wait, so the attention kernel that follows finds its cache rows in L2 (KVCache reads of
+ *    modeling_gemma.py:49-57 / 307-339 overlapped with the projection that precedes them).
  */
-#define PG_DEC_F32 0
-#define PG_DEC_RESID_NORM 1
-int pg_gemm_decode(const void* x, long long ldx, const void* w, long long ldw, int tokens, int features, int K, int mode,
-                   int cluster_k, float* out, long long ldo, const float* bias, const float* ss_in, int norm_dim,
-                   float eps, void* hb, long long ldh, const float* norm_w, float* ss_out, void* stream);
-
-/* Head of a decode step: optionally gathers the token embeddings (same rules as pg_embed_tokens; tokens == NULL keeps the
- * fp32 rows already in h), then hb[b,:] = bf16(h[b,:] * (1 + norm_w)), ss[b] = sum h[b,:]^2 and zero-fills
- * zero_buf[0 .. zero_count) (the per-layer sum-of-squares accumulators of the step). */
-int pg_decode_prologue(const int* tokens, const void* embed, const float* img, float* h, void* hb, float* ss,
-                       const float* norm_w, float* zero_buf, long long zero_count, int B, int D, int N, float text_scale,
-                       float img_scale, long long pad_token, long long image_token, void* stream);
+typedef struct PgGemmFusion {
+  const float* x_f32;
+  long long ldx_f32;
+  const float* norm_w;
+  int apply_rstd;
+  float eps;
+  float* zero_buf;
+  long long zero_count;
+  const void* pf_k_pages;
+  const void* pf_v_pages;
+  const int* pf_page_table;
+  const int* pf_kv_len;
+  int pf_B, pf_max_pages;
+  long long pf_page_bytes;
+} PgGemmFusion;
+int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                       const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
+                       int act_gelu, float scale, int swap, int split_k, const PgGemmFusion* fusion, void* stream);
 
 /* Packs gate_proj / up_proj [F,K] bf16 into the [64 gate | 64 up] row-interleaved [2F,K] layout PG_EPI_GEGLU expects.
  * (modeling_gemma.py:205-206 weights; F % 64 == 0) */
@@ -102,16 +106,9 @@ int pg_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, int rows, int D,
                  float eps, void* stream);
 
-/* GemmaRMSNorm (modeling_gemma.py:157-182): y = x * rsqrt(mean(x^2) + eps) * (1 + w); x fp32 -> y bf16.
- * Optionally zero-fills `zero_buf` (zero_count floats) for a following split-K atomic GEMM, and optionally issues an L2
- * prefetch (cp.async.bulk.prefetch.L2) of `prefetch_bytes` at `prefetch_ptr` (upcoming weights), spread over the CTAs. */
-int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
-               long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream);
-
-/* Warms L2 with `bytes` of immutable data at `ptr` (128 B aligned; upcoming weights).  Plain launch (no programmatic
- * dependency): meant for a side stream that runs beside the latency-bound attention half of a decode layer.
- * mode 0 = prefetch.global.L2, 1 = cp.async.bulk.prefetch.L2, 2 = ld.global.cg + discard; `ctas` blocks of 256 threads. */
-int pg_prefetch_l2(const void* ptr, long long bytes, int mode, int ctas, void* stream);
+/* GemmaRMSNorm (modeling_gemma.py:157-182): y = x * rsqrt(mean(x^2) + eps) * (1 + w); x fp32 -> y bf16.  (Prefill, and the
+ * final norm of a decode step; the per-layer norms of a decode step are folded into pg_gemm_bf16_fused.) */
+int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, void* stream);
 
 /*
  * Image path of PaliGemmaProcessor (processing_paligemma.py:13-73) on the GPU, bit-exact with the reference's CPU path:
@@ -171,26 +168,20 @@ int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos, void* q_o
                       const float* inv_freq, void* stream);
 
 /*
- * Decode attention (modeling_gemma.py:307-339 with q_len == 1): one query token per sequence, the Hq/Hkv query heads
- * of a group share one KV head read from the paged bf16 cache (page_size must be 64), split over the KV length
- * (partials in the fp32 workspace) and combined by a second kernel.  kv_len[b] is read on the device (CUDA-graph
- * friendly).  q bf16 [B, Hq*dh] (post-RoPE); pages bf16 [num_pages, 64, Hkv*dh]; out bf16 [B, Hq*dh].
- */
-int pg_attention_decode(const void* q, const void* k_pages, const void* v_pages, const int* page_table,
-                        const int* kv_len, void* out, float* workspace, int B, int Hq, int Hkv, int dh, int page_size,
-                        int max_pages, int num_splits, float scale, void* stream);
-long long pg_attention_decode_workspace_floats(int B, int Hq, int dh, int num_splits);
-
-/*
  * Decode-step attention in ONE launch (modeling_gemma.py:285-339 at q_len == 1 + KVCache.update :18-57): rotates q and
  * the new k (fp32 qkv [B, (Hq+2Hkv)*dh] straight from the split-K QKV GEMM), appends k/v to the paged cache at slot
  * kv_len[b]-1 and attends over kv_len[b] keys.  One thread-block cluster per (sequence, kv head): each rank streams a
  * contiguous range of 64-key pages (TMA tensor loads into 128B-swizzled shared memory) and the ranks merge through
  * distributed shared memory.  num_pages = pages in the pool (k_pages / v_pages are [num_pages, 64, Hkv*dh] bf16).
+ * GQA group Hq/Hkv <= 8, dh in {64, 256}.
+ * h_norm != NULL: qkv holds the projections of the UN-normalised rows (pg_gemm_bf16_fused with apply_rstd = 0); the kernel
+ * computes r[b] = rsqrt(mean(h_norm[b, 0:norm_dim]^2) + eps) (fp32 rows, pitch norm_dim) and scales q, k and v by it before
+ * RoPE / append -- the input_layernorm factor of modeling_gemma.py:395, applied where it is cheapest.
  */
 int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
                               void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh,
-                              int page_size, int num_pages, int max_pages, float scale, void* stream);
+                              int page_size, int num_pages, int max_pages, float scale, const float* h_norm, int norm_dim,
+                              float eps, void* stream);
 
 /* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
  * views, modeling_gemma.py:8-64). */
@@ -236,52 +227,6 @@ int pg_advance_decode(const int* next, int* tok_hist, int* cur_tok, int* counter
  * idle) is frozen until the host re-arms it; step += 1. */
 int pg_advance_decode_slots(const int* next, int* tok_ring, int ring, int* cur_tok, int* counters, const int* kv_limit,
                             int* step, int B, void* stream);
-
-/*
- * A whole Gemma decode step (token embedding, L x [RMSNorm, QKV, RoPE + KV append + attention, O, RMSNorm, gate||up GEGLU,
- * down], final RMSNorm, lm_head) in ONE persistent kernel: one CTA per SM, the ops above are phases separated by grid
- * barriers (modeling_gemma.py:385-418,453-472,501-533 at q_len == 1; B <= 64 sequences).  Cooperative launch.
- * Buffers are the same as for the per-op entry points; `tensor_maps` is a DEVICE array of (4*L + 4) CUtensorMap filled by
- * pg_decode_step_encode_maps (host) and copied once; `barrier_state` is an array of 256 zero-initialised uint32 in device
- * memory (one epoch flag per CTA, persists across launches).
- */
-typedef struct PgDecodeStepArgs {
-  const void* tensor_maps;
-  int L, B, D, F, Hq, Hkv, dh, V;
-  int split_qkv, split_o, split_down;
-  const int* cur_tok;          /* [B] token ids to embed */
-  const void* embed;           /* bf16 [V, D] */
-  const float* img;            /* fp32 [B, n_img, D] projected image features (may be NULL) */
-  int n_img;
-  float text_scale, img_scale;
-  long long pad_token, image_token;
-  float* h;                    /* fp32 [B, D] residual stream (written) */
-  void* hn;                    /* bf16 [B, D] */
-  float* qkv;                  /* fp32 [B, (Hq+2Hkv)*dh] */
-  void* att;                   /* bf16 [B, Hq*dh] */
-  void* mid;                   /* bf16 [B, F] */
-  float* logits;               /* fp32 [B, V] (lm_head output incl. bias) */
-  const float* ln1;            /* fp32 [L, D] input_layernorm weights */
-  const float* ln2;            /* fp32 [L, D] post_attention_layernorm weights */
-  const float* norm_w;         /* fp32 [D] */
-  const float* head_b;         /* fp32 [V] */
-  float eps;
-  void* k_pages;               /* bf16 [L][pages][64][Hkv*dh] */
-  void* v_pages;
-  long long layer_stride;      /* elements between layers */
-  const int* page_table;       /* [B, max_pages] */
-  const int* pos;              /* [B] position id of the token */
-  const int* kv_len;           /* [B] cache length including the token */
-  const float* inv_freq;       /* [dh/2] */
-  int max_pages, page_size;
-  float scale;                 /* 1/sqrt(dh) */
-  unsigned int* barrier_state; /* [256] */
-  unsigned long long* trace;   /* optional [1024 + 3*(7*L+3)]: per-phase %globaltimer / clock64 of CTA trace_cta (profiling) */
-  int trace_cta;
-} PgDecodeStepArgs;
-int pg_decode_step(const PgDecodeStepArgs* args, void* stream);
-int pg_decode_step_encode_maps(void* out_maps_host, const void* const* weights, const void* hn, const void* att,
-                               const void* mid, int L, int B, int D, int F, int Hq, int Hkv, int dh, int V);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ p, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulongl
 SIGNATURES = {
     "pg_abi_version": [],
     "pg_check_device": [],
+    "pg_num_sms": [],
     "pg_launch_count": [],
     "pg_set_pdl": [i32],
     "pg_debug_set_gemm_trace": [p],
@@ -30,19 +31,12 @@ SIGNATURES = {
     "pg_debug_topp_retries": [],
     "pg_debug_topp_trace": [p],
     "pg_debug_set_topp_bracket": [i32],
-    "pg_debug_set_decode_gemm_cta_trace": [p],
-    "pg_debug_decode_gemm_blocks_per_sm": [i32],
-    "pg_debug_decode_gemm_max_clusters": [i32],
-    "pg_debug_set_decode_gemm_trace": [p],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
-    "pg_gemm_bf16_colnorm": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p, i32, f32, p],
-    "pg_gemm_decode": [p, i64, p, i64, i32, i32, i32, i32, i32, p, i64, p, p, i32, f32, p, i64, p, p, p],
-    "pg_decode_prologue": [p, p, p, p, p, p, p, p, i64, i32, i32, i32, f32, f32, i64, i64, p],
+    "pg_gemm_bf16_fused": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
     "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],
-    "pg_rmsnorm": [p, p, p, i32, i32, f32, p, i64, p, i64, p],
-    "pg_prefetch_l2": [p, i64, i32, i32, p],
+    "pg_rmsnorm": [p, p, p, i32, i32, f32, p],
     "pg_resample_h_u8": [p, p, i32, i32, i32, p, p, i32, p],
     "pg_resample_v_u8_norm": [p, p, i32, i32, i32, p, p, i32, p, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
@@ -50,9 +44,7 @@ SIGNATURES = {
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_attention_prefill_varlen": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
-    "pg_attention_decode": [p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
-    "pg_attention_decode_workspace_floats": [i32, i32, i32, i32],
-    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
+    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p, i32, f32, p],
     "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
@@ -60,25 +52,18 @@ SIGNATURES = {
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
     "pg_advance_decode_slots": [p, p, i32, p, p, p, p, i32, p],
-    "pg_decode_step": [p, p],
-    "pg_decode_step_encode_maps": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32],
 }
-_RESTYPE = {"pg_attention_decode_workspace_floats": i64, "pg_launch_count": i64}
+_RESTYPE = {"pg_launch_count": i64}
 
 
 
-class DecodeStepArgs(C.Structure):
-    """Mirror of PgDecodeStepArgs (include/paligemma_b200.h)."""
+class GemmFusion(C.Structure):
+    """Mirror of PgGemmFusion (include/paligemma_b200.h)."""
     _fields_ = [
-        ("tensor_maps", p),
-        ("L", i32), ("B", i32), ("D", i32), ("F", i32), ("Hq", i32), ("Hkv", i32), ("dh", i32), ("V", i32),
-        ("split_qkv", i32), ("split_o", i32), ("split_down", i32),
-        ("cur_tok", p), ("embed", p), ("img", p), ("n_img", i32), ("text_scale", f32), ("img_scale", f32),
-        ("pad_token", i64), ("image_token", i64),
-        ("h", p), ("hn", p), ("qkv", p), ("att", p), ("mid", p), ("logits", p),
-        ("ln1", p), ("ln2", p), ("norm_w", p), ("head_b", p), ("eps", f32),
-        ("k_pages", p), ("v_pages", p), ("layer_stride", i64), ("page_table", p), ("pos", p), ("kv_len", p), ("inv_freq", p),
-        ("max_pages", i32), ("page_size", i32), ("scale", f32), ("barrier_state", p), ("trace", p), ("trace_cta", i32),
+        ("x_f32", p), ("ldx_f32", i64), ("norm_w", p), ("apply_rstd", i32), ("eps", f32),
+        ("zero_buf", p), ("zero_count", i64),
+        ("pf_k_pages", p), ("pf_v_pages", p), ("pf_page_table", p), ("pf_kv_len", p), ("pf_B", i32), ("pf_max_pages", i32),
+        ("pf_page_bytes", i64),
     ]
 
 
@@ -117,6 +102,10 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def num_sms():
+    return int(lib().pg_num_sms())
+
+
 def require_device():
     """The product path needs an sm_100 GPU and the compiled kernels; anything else is an error, not a fallback."""
     if not torch.cuda.is_available():
@@ -143,32 +132,36 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
     return out
 
 
-DEC_F32, DEC_RESID_NORM = 0, 1
-
-
-def gemm_colnorm(x, w, out, *, mode, ss_in, norm_dim, eps=1e-6, bias=None, swap=1):
-    """Swap-AB (decode) GEMM whose epilogue applies the producer's RMSNorm factor rsqrt(ss_in[t]/norm_dim + eps) per token."""
-    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
-    assert ss_in.dtype == torch.float32 and ss_in.numel() >= x.shape[0]
-    T, K = x.shape
-    check(lib().pg_gemm_bf16_colnorm(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
-                                     0, 0, T, w.shape[0], K, mode, 0, 1.0, swap, 1, ss_in.data_ptr(), int(norm_dim), float(eps),
-                                     stream()), "pg_gemm_bf16_colnorm")
-    return out
-
-
-def gemm_decode(x, w, out, *, mode, cluster_k, bias=None, ss_in=None, norm_dim=0, eps=1e-6, hb=None, norm_w=None, ss_out=None):
-    """Cluster split-K decode GEMM (csrc/gemm_decode.cu): DEC_F32 writes out fp32; DEC_RESID_NORM adds into the fp32 residual
-    stream `out` and emits hb = bf16(out * (1 + norm_w)) and ss_out += sum(out^2) for the next fused RMSNorm."""
-    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
-    assert out.dtype == torch.float32 and out.stride(1) == 1
-    T, K = x.shape
+def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=False, eps=1e-6, zero_buf=None, kv_prefetch=None,
+               bias=None, split_k=1):
+    """Decode-step (swap-AB, tokens <= 128) GEMM with the fusions of pg_gemm_bf16_fused:
+      x_f32 / norm_w   activation operand built in the kernel from the fp32 residual rows, bf16(x * (1 + norm_w)) -- the
+                       GemmaRMSNorm that precedes the projection, minus its per-token factor (apply_rstd: applied in the
+                       epilogue; otherwise the consumer applies it);
+      zero_buf         fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
+      kv_prefetch      (k_pages_layer, v_pages_layer, page_table, kv_len) whose live pages are pulled into L2."""
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+    fu = GemmFusion()
+    if x_f32 is not None:
+        assert x is None and x_f32.dtype == torch.float32 and x_f32.stride(1) == 1 and norm_w.dtype == torch.float32
+        T, K = x_f32.shape
+        fu.x_f32, fu.ldx_f32, fu.norm_w, fu.apply_rstd, fu.eps = x_f32.data_ptr(), x_f32.stride(0), norm_w.data_ptr(), int(apply_rstd), float(eps)
+        xp, ldx = 0, 0
+    else:
+        assert x.dtype == torch.bfloat16 and x.stride(1) == 1
+        T, K = x.shape
+        xp, ldx = x.data_ptr(), x.stride(0)
     assert w.shape[1] == K
-    if mode == DEC_RESID_NORM:
-        assert hb.dtype == torch.bfloat16 and norm_w.dtype == torch.float32 and ss_out.dtype == torch.float32
-    check(lib().pg_gemm_decode(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), T, w.shape[0], K, mode, int(cluster_k),
-                               out.data_ptr(), out.stride(0), ptr(bias), ptr(ss_in), int(norm_dim), float(eps), ptr(hb),
-                               0 if hb is None else hb.stride(0), ptr(norm_w), ptr(ss_out), stream()), "pg_gemm_decode")
+    if zero_buf is not None:
+        assert zero_buf.dtype == torch.float32 and zero_buf.is_contiguous()
+        fu.zero_buf, fu.zero_count = zero_buf.data_ptr(), zero_buf.numel()
+    if kv_prefetch is not None:
+        kp, vp, table, kv_len = kv_prefetch
+        fu.pf_k_pages, fu.pf_v_pages, fu.pf_page_table, fu.pf_kv_len = kp.data_ptr(), vp.data_ptr(), table.data_ptr(), kv_len.data_ptr()
+        fu.pf_B, fu.pf_max_pages = table.shape
+        fu.pf_page_bytes = kp.stride(0) * kp.element_size()
+    check(lib().pg_gemm_bf16_fused(xp, ldx, w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias), 0, 0, T, w.shape[0], K,
+                                   mode, 0, 1.0, 1, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")
     return out
 
 
@@ -179,12 +172,10 @@ def layernorm(x, gamma, beta, eps, out_bf16=None, out_f32=None):
                              stream()), "pg_layernorm")
 
 
-def rmsnorm(x, w, out_bf16, eps=1e-6, zero_buf=None, prefetch=None, prefetch_bytes=None):
+def rmsnorm(x, w, out_bf16, eps=1e-6):
     rows, D = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
-    pf_bytes = 0 if prefetch is None else (prefetch.numel() * prefetch.element_size() if prefetch_bytes is None else prefetch_bytes)
-    check(lib().pg_rmsnorm(x.data_ptr(), w.data_ptr(), out_bf16.data_ptr(), rows, D, float(eps), ptr(zero_buf),
-                           0 if zero_buf is None else zero_buf.numel(), ptr(prefetch), pf_bytes, stream()), "pg_rmsnorm")
+    check(lib().pg_rmsnorm(x.data_ptr(), w.data_ptr(), out_bf16.data_ptr(), rows, D, float(eps), stream()), "pg_rmsnorm")
 
 
 def gemm_residual(x, w, h, bias=None):

@@ -430,13 +430,14 @@ static int make_tmap_nd(CUtensorMap* m, const void* ptr, int rank, const long lo
 template <int DH, int SW, int PP, int QT>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int B, int H, cudaStream_t st) {
   using C = Cfg<DH, QT>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, PP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
       cudaGetLastError();
       return PG_ERR_CUDA;
     }
-    configured = true;
+    configured[dev] = true;
   }
   dim3 grid((p.rows + C::BM * QT - 1) / (C::BM * QT), H, B);
   attn_prefill_tc_kernel<DH, SW, PP, QT><<<grid, 64 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
@@ -471,11 +472,10 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
     const int box[5] = {64, group, 128 / group, 1, 1};
     if ((rc = ap::make_tmap_nd(&tq, q, 5, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
   }
-  // query tiles per CTA (PG_ATTN_QT=1|2 overrides: A/B runs).  Two tiles (64-key steps) win while a head has few key tiles
+  // query tiles per CTA.  Two tiles (64-key steps) win while a head has few key tiles
   // -- fewer, fuller CTAs: SigLIP 224 px 0.107 -> 0.088 ms, 448 px 0.389 -> 0.366 ms per layer -- and lose slightly at 4096 keys
   // (1.158 vs 1.190 ms), where the 128-key steps of the one-tile variant amortise the per-step barrier traffic better.
-  static const int qt_env = getenv("PG_ATTN_QT") ? atoi(getenv("PG_ATTN_QT")) : 0;
-  const int qt = dh > 128 ? 1 : (qt_env == 1 || qt_env == 2 ? qt_env : (rows > 128 && keys <= 2048 ? 2 : 1));
+  const int qt = dh > 128 ? 1 : (rows > 128 && keys <= 2048 ? 2 : 1);
   const int BN = (dh > 128 || qt == 2) ? 64 : 128;
   {
     const long long dims[4] = {dh, keys, H, B};
@@ -491,22 +491,13 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   p.sl2 = scale * 1.4426950408889634f;
   p.key_lens = key_lens;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // softmax warps per TMEM lane quadrant (one query tile per CTA only) and FMA-pipe exponentials per four score pairs
-  // (PG_ATTN_SW / PG_ATTN_PP: A/B runs)
-  static const int sw_env = getenv("PG_ATTN_SW") ? atoi(getenv("PG_ATTN_SW")) : 0;
-  static const int pp_env = getenv("PG_ATTN_PP") ? atoi(getenv("PG_ATTN_PP")) : -1;
-  const int sw = qt == 2 ? 1 : (sw_env == 1 || sw_env == 2 ? sw_env : (dh > 128 ? 1 : 2));
-  const int pp = pp_env >= 0 && pp_env <= 2 && (sw == 2 || qt == 2) ? pp_env : 0;
+  // softmax warps per TMEM lane quadrant: two (column halves) for the one-tile dh <= 128 variant, else one
+  const int sw = qt == 2 ? 1 : (dh > 128 ? 1 : 2);
 #define PG_AP_LAUNCH1(DHV)                                                           \
   if (sw == 1) return ap::launch<DHV, 1, 0, 1>(tq, tk, tv, p, B, H, st);             \
-  if (pp == 0) return ap::launch<DHV, 2, 0, 1>(tq, tk, tv, p, B, H, st);             \
-  if (pp == 1) return ap::launch<DHV, 2, 1, 1>(tq, tk, tv, p, B, H, st);             \
-  return ap::launch<DHV, 2, 2, 1>(tq, tk, tv, p, B, H, st);
+  return ap::launch<DHV, 2, 0, 1>(tq, tk, tv, p, B, H, st);
 #define PG_AP_LAUNCH2(DHV)                                                           \
-  if (qt == 2) {                                                                     \
-    if (pp == 0) return ap::launch<DHV, 1, 0, 2>(tq, tk, tv, p, B, H, st);           \
-    return ap::launch<DHV, 1, 1, 2>(tq, tk, tv, p, B, H, st);                        \
-  }
+  if (qt == 2) return ap::launch<DHV, 1, 0, 2>(tq, tk, tv, p, B, H, st);
   switch (dh) {
     case 64: PG_AP_LAUNCH2(64) PG_AP_LAUNCH1(64)
     case 72: PG_AP_LAUNCH2(72) PG_AP_LAUNCH1(72)

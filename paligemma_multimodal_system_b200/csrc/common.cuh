@@ -239,6 +239,21 @@ PG_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0
 }
 
 
+// Per-device host state: kernel attributes (cudaFuncSetAttribute) and the SM count belong to a device, not to the process
+// (one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+inline int num_sms() {
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 // Host-side launch through cudaLaunchKernelEx, optionally as a programmatic dependent launch.  Every kernel launched
 // this way executes griddepcontrol.wait before its first dependent global access.
 template <typename... KArgs, typename... Args>

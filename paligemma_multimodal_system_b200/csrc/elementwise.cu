@@ -64,28 +64,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // GemmaRMSNorm (modeling_gemma.py:172-181): fp32, x * rsqrt(mean(x^2) + eps) * (1 + w)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      bf16* __restrict__ y, int D, float eps, float* __restrict__ zero_buf,
-                                                      long long zero_count, const uint8_t* __restrict__ pf_ptr,
-                                                      long long pf_bytes) {
+                                                      bf16* __restrict__ y, int D, float eps) {
   extern __shared__ float row[];
   float* red = row + D;
   const long long r = blockIdx.x;
-  if (pf_ptr != nullptr) {
-    // Pull upcoming weights (immutable, independent of the previous kernel) into L2 while the latency-bound part of
-    // the layer runs; issued before the dependency wait.
-    constexpr long long CH = 16384;
-    const long long per = ((pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
-    const long long lo = r * per, hi = min(pf_bytes, lo + per);
-    for (long long off = lo + threadIdx.x * CH; off < hi; off += blockDim.x * CH)
-      prefetch_l2_bulk(pf_ptr + off, static_cast<uint32_t>(min(CH, hi - off) & ~15ll));
-  }
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
-  if (zero_buf != nullptr) {  // zero-fill for the split-K GEMM that follows
-    const long long per = (zero_count + gridDim.x - 1) / gridDim.x;
-    const long long lo = r * per, hi = min(zero_count, lo + per);
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) zero_buf[i] = 0.f;
-  }
   const float4* xr = reinterpret_cast<const float4*>(x + r * D);
   float ss = 0.f;
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
@@ -333,55 +317,6 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(const int* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Head of a decode step: token embedding (as embed_tokens_kernel) + the operands of the first fused RMSNorm:
-// hb = bf16(h * (1 + w)), ss = sum h^2; also zeroes the sum-of-squares accumulators of the rest of the step.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_prologue_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed,
-                                                              const float* __restrict__ img, float* __restrict__ h,
-                                                              bf16* __restrict__ hb, float* __restrict__ ss,
-                                                              const float* __restrict__ norm_w, float* __restrict__ zero_buf,
-                                                              long long zero_count, int D, int N, float text_scale,
-                                                              float img_scale, long long pad_token, long long image_token) {
-  __shared__ float red[33];
-  const int b = blockIdx.x;
-  griddep_wait();
-  if (threadIdx.x == 0) griddep_launch_dependents();
-  {
-    const long long per = (zero_count + gridDim.x - 1) / gridDim.x;
-    const long long lo = b * per, hi = min(zero_count, lo + per);
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) zero_buf[i] = 0.f;
-  }
-  float4* hrow = reinterpret_cast<float4*>(h + static_cast<long long>(b) * D);
-  uint2* hbrow = reinterpret_cast<uint2*>(hb + static_cast<long long>(b) * D);
-  const long long id = tokens != nullptr ? tokens[b] : -1;
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
-    float4 v;
-    if (tokens == nullptr) {
-      v = hrow[i];
-    } else {
-      if (id == pad_token) {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else if (id == image_token && img != nullptr) {
-        const float4 s4 = reinterpret_cast<const float4*>(img + static_cast<long long>(b) * N * D)[i];
-        v = make_float4(s4.x * img_scale, s4.y * img_scale, s4.z * img_scale, s4.w * img_scale);
-      } else {
-        const uint2 u = reinterpret_cast<const uint2*>(embed + id * D)[i];
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-        v = make_float4(a.x * text_scale, a.y * text_scale, c.x * text_scale, c.y * text_scale);
-      }
-      hrow[i] = v;
-    }
-    const float4 w4 = reinterpret_cast<const float4*>(norm_w)[i];
-    hbrow[i] = make_uint2(pack_bf16(v.x * (1.0f + w4.x), v.y * (1.0f + w4.y)), pack_bf16(v.z * (1.0f + w4.z), v.w * (1.0f + w4.w)));
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) ss[b] = tot;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // RoPE (rotate-half, modeling_gemma.py:116-151) + KVCache.update (:18-57) into pages
 // ---------------------------------------------------------------------------------------------------------
 template <bool F32IN>
@@ -486,32 +421,6 @@ __global__ void advance_decode_slots_kernel(const int* __restrict__ next, int* _
   if (threadIdx.x == 0) *step = st + 1;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// L2 warm-up of an immutable weight range, meant to run on a SIDE stream concurrently with the latency-bound part of a
-// decode layer (attention half) so that the HBM pipe never idles.  mode 0: prefetch.global.L2 (LSU path, no data
-// returned to the SM); mode 1: cp.async.bulk.prefetch.L2 (bulk-copy engine); mode 2: ld.global.cg + discard.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) l2_prefetch_kernel(const uint8_t* __restrict__ p, long long bytes, int mode) {
-  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
-  if (mode == 0) {
-    for (long long off = tid * 128; off < bytes; off += nth * 128)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off) : "memory");
-  } else if (mode == 1) {
-    constexpr long long CH = 4096;
-    for (long long off = tid * CH; off < bytes; off += nth * CH)
-      prefetch_l2_bulk(p + off, static_cast<uint32_t>(min(CH, bytes - off) & ~15ll));
-  } else {
-    uint32_t acc = 0;
-    for (long long off = tid * 16; off + 16 <= bytes; off += nth * 16) {
-      uint32_t a, b, c, d;
-      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p + off));
-      acc ^= a ^ b ^ c ^ d;
-    }
-    if (acc == 0x9e3779b9u && bytes < 0) printf("%u", acc);  // keeps the loads alive
-  }
-}
-
 }  // namespace pg
 
 using namespace pg;
@@ -527,7 +436,8 @@ int pg_pdl_enabled(void) { return g_pdl; }
 extern "C" int pg_set_pdl(int on) { g_pdl = on ? 1 : 0; return PG_OK; }
 extern "C" long long pg_launch_count(void) { return g_launches; }
 
-extern "C" int pg_abi_version(void) { return 1; }
+extern "C" int pg_abi_version(void) { return 2; }
+extern "C" int pg_num_sms(void) { return pg::num_sms(); }
 
 extern "C" int pg_check_device(void) {
   int dev = 0, major = 0;
@@ -549,24 +459,15 @@ extern "C" int pg_layernorm(const float* x, const float* gamma, const float* bet
   PG_RET();
 }
 
-extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, float* zero_buf,
-                          long long zero_count, const void* prefetch_ptr, long long prefetch_bytes, void* stream) {
+extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
-  if (prefetch_ptr != nullptr && ((reinterpret_cast<uintptr_t>(prefetch_ptr) & 15) || prefetch_bytes < 0)) return PG_ERR_ARG;
-  if (rows >= 1024 && (D % 128) == 0 && D <= 2048 && zero_buf == nullptr && prefetch_ptr == nullptr &&
+  if (rows >= 1024 && (D % 128) == 0 && D <= 2048 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y_bf16)) & 15) == 0) {
     rmsnorm_warp_kernel<16><<<(rows + 7) / 8, 256, 0, PG_ST(stream)>>>(x, w, static_cast<bf16*>(y_bf16), rows, D, eps);
     PG_RET();
   }
   return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), (D + 33) * sizeof(float), PG_ST(stream), x, w,
-                       static_cast<bf16*>(y_bf16), D, eps, zero_buf, zero_count, static_cast<const uint8_t*>(prefetch_ptr),
-                       prefetch_bytes) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
-}
-
-extern "C" int pg_prefetch_l2(const void* ptr, long long bytes, int mode, int ctas, void* stream) {
-  if (ptr == nullptr || bytes <= 0 || (reinterpret_cast<uintptr_t>(ptr) & 127) || mode < 0 || mode > 2 || ctas <= 0) return PG_ERR_ARG;
-  l2_prefetch_kernel<<<ctas, 256, 0, PG_ST(stream)>>>(static_cast<const uint8_t*>(ptr), bytes, mode);
-  PG_RET();
+                       static_cast<bf16*>(y_bf16), D, eps) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream) {
@@ -616,17 +517,6 @@ extern "C" int pg_embed_tokens(const int* tokens, const void* embed, const float
   if (B <= 0 || D <= 0 || (D % 4)) return PG_ERR_ARG;
   return launch_kernel(embed_tokens_kernel, dim3(B), dim3(256), 0, PG_ST(stream), tokens, static_cast<const bf16*>(embed), img, h,
                        D, N, text_scale, img_scale, pad_token, image_token) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
-}
-
-extern "C" int pg_decode_prologue(const int* tokens, const void* embed, const float* img, float* h, void* hb, float* ss,
-                                  const float* norm_w, float* zero_buf, long long zero_count, int B, int D, int N,
-                                  float text_scale, float img_scale, long long pad_token, long long image_token, void* stream) {
-  if (B <= 0 || D <= 0 || (D % 4) || h == nullptr || hb == nullptr || ss == nullptr || norm_w == nullptr) return PG_ERR_ARG;
-  if (tokens != nullptr && embed == nullptr) return PG_ERR_ARG;
-  if (zero_count < 0 || (zero_count > 0 && zero_buf == nullptr)) return PG_ERR_ARG;
-  return launch_kernel(decode_prologue_kernel, dim3(B), dim3(256), 0, PG_ST(stream), tokens, static_cast<const bf16*>(embed), img,
-                       h, static_cast<bf16*>(hb), ss, norm_w, zero_buf, zero_count, D, N, text_scale, img_scale, pad_token,
-                       image_token) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos, void* q_out, void* k_out, void* v_out,

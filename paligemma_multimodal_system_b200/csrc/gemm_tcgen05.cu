@@ -13,7 +13,13 @@
 //   SWAP = false (prefill, many tokens):  UMMA M = 128 tokens,   N = BN features
 //   SWAP = true  (decode, tokens <= 128): UMMA M = 128 features, N = BN tokens  (weight streaming, HBM bound),
 //                                         optional split-K with fp32 red.global.add into the output
-#include <stdlib.h>
+//   BF32 = true  (decode, SWAP only): the activation operand is the fp32 residual stream itself.  The epilogue warps
+//                                         turn each 64-column slice of it into the bf16, 128B-swizzled B tile
+//                                         (x * (1 + norm_w): GemmaRMSNorm, modeling_gemma.py:172-181, minus its
+//                                         per-token factor) while the weight tiles arrive by TMA; the factor
+//                                         rsqrt(mean(x^2) + eps) is linear in the GEMM and is applied in the epilogue
+//                                         (full-K tiles) or by the consumer (split-K qkv -> the attention kernel).
+//                                         No standalone RMSNorm launch, no bf16 activation round trip.
 
 #include "common.cuh"
 #include "paligemma_b200.h"
@@ -57,13 +63,26 @@ struct GemmArgs {
   const float* bias;
   const float* resid;
   long long ldr;
-  // optional per-token RMSNorm factor of the producer of X (SWAP kernels): acc[f, t] *= rsqrt(ss_in[t] * inv_norm_dim + eps)
-  const float* ss_in;
-  float inv_norm_dim, eps;
   int n_fast;  // tile raster order (decode_tile)
-  int debug_skip_epilogue;  // profiling: 1 = no epilogue work at all, 2 = TMEM reads only (no global stores)
   int f32_coalesced;  // token-major fp32 epilogue through the shared-memory transposition (alignment checked by the host)
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
+  // ---- BF32 kernels: B operand = bf16(xf[t, k] * (1 + norm_w[k])) built in the kernel from fp32 rows ----
+  const float* xf;
+  long long ldxf;
+  const float* norm_w;
+  int apply_rstd;  // full-K tiles: multiply the accumulator by rsqrt(sum_k xf[t,k]^2 / K + eps) in the epilogue
+  float eps;
+  // ---- decode-step chores of the SWAP kernels ----
+  float* zero_buf;  // zero-filled after the dependency wait (the split-K accumulator of a LATER kernel of the chain)
+  long long zero_count;
+  // L2 prefetch of the paged KV cache rows the attention kernel two launches ahead will stream (issued before the
+  // dependency wait: pages of earlier positions, the page table and kv_len were written before this kernel could start)
+  const uint8_t* pf_k;
+  const uint8_t* pf_v;
+  const int* pf_table;
+  const int* pf_len;
+  int pf_B, pf_max_pages;
+  long long pf_page_bytes;
 };
 
 struct TileInfo {
@@ -259,7 +278,7 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
       }
       if (collective)
         warp_store_rows_128B(stage, lane, pkc, reinterpret_cast<char*>(out_bf - static_cast<long long>(lane) * args.ldo + f0),
-                             args.ldo * 2, rows_valid, args.debug_skip_epilogue != 3);
+                             args.ldo * 2, rows_valid, true);
     } else {  // feature tail / unaligned rows: element by element
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -441,14 +460,68 @@ PG_DEVINL void geglu_swap_epilogue(const GemmArgs& args, uint32_t taddr, float* 
   geglu_swap_epilogue_group<BN>(args, taddr, xch, bar, q, lane, et, j_base, m_blk, rs_tab);
 }
 
+// BF32 kernels: the NEPI epilogue warps build the B tiles (tokens x 64 k, bf16, K-major, 128B swizzle: row = token, 16-byte
+// chunk c of a row sits at chunk position c ^ (row & 7) -- the layout TMA would have produced) of the k-blocks [kb0, kb1)
+// of one output tile from the fp32 rows xf[t, :], scaled by (1 + norm_w[k]).  Work item = (token, 16-float segment): four
+// threads share a token, so a token's sum of squares is one quad reduction away.  The loads of the next k-block are in
+// flight while the current one waits for its pipeline slot.  Returns this thread's partial sum of squares of its token
+// (items beyond the first only exist when BN * 4 > threads; their partials are folded into `ssq[j]`).
+template <int BN, int NEPI>
+struct BTileConverter {
+  static constexpr int NT = NEPI * 32;
+  static constexpr int ITEMS = BN * 4;
+  static constexpr int PER = (ITEMS + NT - 1) / NT;
+
+  PG_DEVINL static void load(const GemmArgs& args, int j_base, int kb, int et, float4 (&v)[PER][4]) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int idx = et + j * NT;
+      const int tok = j_base + (idx >> 2), k0 = kb * BK + (idx & 3) * 16;
+      const bool row_ok = idx < ITEMS && tok < args.tokens;
+      const float* src = args.xf + static_cast<long long>(tok) * args.ldxf + k0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)  // K % 8 == 0 and k0 % 16 == 0: a float4 is either fully inside the row or fully outside
+        v[j][i] = (row_ok && k0 + 4 * i < args.K) ? __ldcg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  PG_DEVINL static void store(const GemmArgs& args, uint32_t b_tile, int kb, int et, const float4 (&v)[PER][4], float (&ssq)[PER]) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int idx = et + j * NT;
+      if (idx >= ITEMS) continue;
+      const int row = idx >> 2, seg = idx & 3, k0 = kb * BK + seg * 16;
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + 4 * i < args.K) w = __ldg(reinterpret_cast<const float4*>(args.norm_w + k0) + i);
+        const float4 x = v[j][i];
+        ssq[j] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        pk[2 * i] = pack_bf16(x.x * (1.0f + w.x), x.y * (1.0f + w.y));
+        pk[2 * i + 1] = pack_bf16(x.z * (1.0f + w.z), x.w * (1.0f + w.w));
+      }
+      const uint32_t base = b_tile + row * 128;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((2 * seg) ^ (row & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
+                   "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((2 * seg + 1) ^ (row & 7)) << 4)), "r"(pk[4]), "r"(pk[5]),
+                   "r"(pk[6]), "r"(pk[7]) : "memory");
+    }
+  }
+};
+
 // SPLITK = true: swap-AB kernel specialised for the split-K red.add epilogue with EIGHT epilogue warps (two per TMEM lane
 // quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
 // red.add epilogue is compiled out, which keeps the 320-thread CTA at two per SM.
-template <int BN, bool SWAP, bool SPLITK = false>
+template <int BN, bool SWAP, bool SPLITK = false, bool BF32 = false>
 __global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
+  static_assert(!BF32 || SWAP, "the in-kernel fp32 -> bf16 operand conversion exists for the decode (swap-AB) kernels");
+  constexpr int NEPI = SPLITK ? 8 : 4;  // epilogue warps (they also build the B tiles of the BF32 kernels)
+  // bytes the TMA producer brings into one pipeline stage (BF32: the weight tile only)
+  constexpr uint32_t TMA_STAGE_BYTES = BF32 ? A_TILE_BYTES : stage_bytes(BN);
   // (token-major kernel: SPLITK = true selects the same 320-thread shape, eight epilogue warps that split the columns;
   //  it pays for the short-K SigLIP GEMMs whose epilogue outlasts the main loop, and costs registers on the long-K ones)
   constexpr int STAGES = num_stages(BN, SWAP);
@@ -488,7 +561,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), BF32 ? 1 + NEPI : 1);  // BF32: + one arrival per converter warp (the B tile is in place)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
@@ -523,7 +596,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         pre = min(STAGES, t.kb1 - t.kb0);
         for (int s = 0; s < pre; ++s) {
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), TMA_STAGE_BYTES);
           if (SWAP) tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
           else tma_load_2d(smem_base + s * STAGE_BYTES + A_TILE_BYTES, &tmapB, full_bar(s), (t.kb0 + s) * BK, t.n_blk * BN, hintB);
         }
@@ -541,10 +614,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             --pre;
           } else {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            mbar_expect_tx(full_bar(stage), TMA_STAGE_BYTES);
           }
           if (!(SWAP && weights_in_flight)) tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
-          if (!(!SWAP && weights_in_flight)) tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
+          if (!BF32 && !(!SWAP && weights_in_flight))
+            tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -584,14 +658,84 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   } else {
     // =================================== epilogue warps =================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    griddep_wait();          // outputs / residual / bias may depend on the previous kernel
+    const int et = (warp - 2) * 32 + lane;
+    if constexpr (SWAP) {
+      if (args.pf_k != nullptr) {
+        // chunks of <= 16 KB: (sequence b, page j, K|V, piece); CTAs interleave so that every SM issues a few
+        constexpr long long CH = 16384;
+        const int cpp = static_cast<int>((args.pf_page_bytes + CH - 1) / CH);
+        const long long total = static_cast<long long>(args.pf_B) * args.pf_max_pages * 2 * cpp;
+        for (long long c = blockIdx.x + static_cast<long long>(gridDim.x) * et; c < total; c += static_cast<long long>(gridDim.x) * (NEPI * 32)) {
+          const int sub = static_cast<int>(c % cpp);
+          long long r = c / cpp;
+          const int kv = static_cast<int>(r & 1);
+          r >>= 1;
+          const int j = static_cast<int>(r % args.pf_max_pages), b = static_cast<int>(r / args.pf_max_pages);
+          if (j * 64 < __ldg(args.pf_len + b)) {
+            const long long page = __ldg(args.pf_table + static_cast<long long>(b) * args.pf_max_pages + j);
+            const long long off = sub * CH;
+            const long long nbytes = min(CH, args.pf_page_bytes - off) & ~15ll;
+            if (nbytes > 0) prefetch_l2_bulk((kv ? args.pf_v : args.pf_k) + page * args.pf_page_bytes + off, static_cast<uint32_t>(nbytes));
+          }
+        }
+      }
+    }
+    griddep_wait();          // outputs / residual / bias / fp32 activations may depend on the previous kernel
+    if constexpr (SWAP) {
+      if (args.zero_buf != nullptr) {
+        const long long n4 = args.zero_count >> 2;  // (host: zero_count % 4 == 0, 16-byte aligned)
+        const long long per = (n4 + gridDim.x - 1) / gridDim.x;
+        const long long lo = blockIdx.x * per, hi = min(n4, lo + per);
+        for (long long i = lo + et; i < hi; i += NEPI * 32) reinterpret_cast<float4*>(args.zero_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cstage = 0;           // BF32: pipeline position of the converter (walks the same k-blocks as producer and issuer)
+    uint32_t cphase = 0;
     const int mode = args.mode;
     __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
     float* out_f = reinterpret_cast<float*>(args.out);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
+      const float* rs_tab = nullptr;  // per-token epilogue factors (x args.scale) in shared memory
+      if constexpr (BF32) {
+        using Conv = BTileConverter<BN, NEPI>;
+        float4 cur[Conv::PER][4], nxt[Conv::PER][4];
+        float ssq[Conv::PER];
+#pragma unroll
+        for (int j = 0; j < Conv::PER; ++j) ssq[j] = 0.f;
+        const int j_base = t.n_blk * BN;
+        Conv::load(args, j_base, t.kb0, et, cur);
+#pragma unroll 1
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          if (kb + 1 < t.kb1) Conv::load(args, j_base, kb + 1, et, nxt);
+          mbar_wait(empty_bar(cstage), cphase ^ 1);  // the MMAs that read this slot's previous tile have completed
+          Conv::store(args, smem_base + cstage * STAGE_BYTES + A_TILE_BYTES, kb, et, cur, ssq);
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(cstage));
+          if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
+#pragma unroll
+          for (int j = 0; j < Conv::PER; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
+        }
+        if (args.apply_rstd) {  // (host: split_k == 1, so this CTA has seen every column of its tokens)
+          float* tab = xch + 64 * BN;  // BN floats after the exchange area
+          named_bar_sync(3, NEPI * 32);  // the previous tile's epilogue has read the table
+#pragma unroll
+          for (int j = 0; j < Conv::PER; ++j) {
+            float v = ssq[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int idx = et + j * Conv::NT;
+            if ((idx & 3) == 0 && idx < Conv::ITEMS) tab[idx >> 2] = rsqrtf(v / static_cast<float>(args.K) + args.eps) * args.scale;
+          }
+          named_bar_sync(3, NEPI * 32);
+          rs_tab = tab;
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       if (tr && threadIdx.x == 64) args.trace[3] = clock64();  // accumulator ready (first tile)
       tc_fence_after();
@@ -606,23 +750,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         if (mode == PG_EPI_GEGLU) {
           if constexpr (BN >= 32)
             geglu_swap_epilogue_group<HALF_COLS>(args, taddr + half * HALF_COLS, xch + half * 64 * HALF_COLS, 1 + half, q, lane,
-                                                 ((warp - 2) & 3) * 32 + lane, t.n_blk * BN + half * HALF_COLS, t.m_blk, nullptr);
+                                                 ((warp - 2) & 3) * 32 + lane, t.n_blk * BN + half * HALF_COLS, t.m_blk,
+                                                 rs_tab != nullptr ? rs_tab + half * HALF_COLS : nullptr);
         } else if (half * HALF_COLS < BN) {
-          swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split, nullptr,
+          swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split, rs_tab,
                                                     half * HALF_COLS, (half + 1) * HALF_COLS);
-        }
-      } else if (args.debug_skip_epilogue == 1 || args.debug_skip_epilogue == 2) {
-        if (args.debug_skip_epilogue == 2) {
-          uint32_t sink = 0;
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sink ^= r[i];
-          }
-          if (sink == 0x12345678u) reinterpret_cast<uint32_t*>(args.out)[0] = sink;
         }
       } else if constexpr (!SWAP) {
         const int tok = t.m_blk * BM + rl;
@@ -658,7 +790,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             }
             if (al) {
               warp_store_rows_128B(wstage, lane, pk, reinterpret_cast<char*>(out_bf + static_cast<long long>(t.m_blk * BM + q * 32) * args.ldo + f0),
-                                   args.ldo * 2, rows_valid, args.debug_skip_epilogue != 3);
+                                   args.ldo * 2, rows_valid, true);
             } else if (row_ok) {
               __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
 #pragma unroll
@@ -681,19 +813,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
         const int fr = t.m_blk * BM + rl;
         const int j_base = t.n_blk * BN;
-        // per-token RMSNorm factor of the producer (x args.scale), staged once per tile in shared memory
-        const float* rs_tab = nullptr;
-        if (args.ss_in != nullptr) {
-          float* tab = xch + 64 * BN;  // BN floats after the exchange area
-          const int et = (warp - 2) * 32 + lane;
-          named_bar_sync(1, 128);      // previous tile's readers are done
-          if (et < BN) {
-            const int j = j_base + et;
-            tab[et] = j < args.tokens ? rsqrtf(__ldg(args.ss_in + j) * args.inv_norm_dim + args.eps) * args.scale : 0.f;
-          }
-          named_bar_sync(1, 128);
-          rs_tab = tab;
-        }
         if (mode == PG_EPI_GEGLU) {
           geglu_swap_epilogue<BN>(args, taddr, xch, 1, q, lane, (warp - 2) * 32 + lane, j_base, t.m_blk, rs_tab);
         } else {
@@ -734,33 +853,23 @@ extern "C" int pg_debug_set_gemm_bn(int bn) {
   g_force_bn = bn;
   return 0;
 }
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
-}
 
-template <int BN, bool SWAP, bool SPLITK = false>
+template <int BN, bool SWAP, bool SPLITK = false, bool BF32 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   constexpr int smem = smem_bytes(BN, SWAP);
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+  const int dev = current_device();
+  if (!configured[dev]) {  // function attributes are per device
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK, BF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();  // do not leave a sticky error behind
       return PG_ERR_CUDA;
     }
-    if (getenv("PG_CARVEOUT") != nullptr)
-      cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("PG_CARVEOUT")));
-    configured = true;
+    configured[dev] = true;
   }
   const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
   const int grid = num_tiles < slots ? num_tiles : slots;
-  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess ? PG_OK
-                                                                                                                         : PG_ERR_CUDA;
+  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK, BF32>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess
+             ? PG_OK : PG_ERR_CUDA;
 }
 
 }  // namespace pg
@@ -770,22 +879,23 @@ using namespace pg;
 extern "C" int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
                             const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
                             int mode, int act_gelu, float scale, int swap, int split_k, void* stream) {
-  return pg_gemm_bf16_colnorm(x, ldx, w, ldw, out, ldo, bias, resid, ldr, tokens, features, K, mode, act_gelu, scale, swap,
-                              split_k, nullptr, 0, 0.f, stream);
+  return pg_gemm_bf16_fused(x, ldx, w, ldw, out, ldo, bias, resid, ldr, tokens, features, K, mode, act_gelu, scale, swap,
+                            split_k, nullptr, stream);
 }
 
-extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
-                                    const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
-                                    int mode, int act_gelu, float scale, int swap, int split_k, const float* ss_in,
-                                    int norm_dim, float eps, void* stream) {
+extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
+                                  const float* bias, const float* resid, long long ldr, int tokens, int features, int K,
+                                  int mode, int act_gelu, float scale, int swap, int split_k, const PgGemmFusion* fu,
+                                  void* stream) {
   if (tokens <= 0 || features <= 0 || K <= 0) return PG_ERR_ARG;
-  if ((K % 8) != 0 || (ldx % 8) != 0 || (ldw % 8) != 0) return PG_ERR_ARG;  // TMA: 16 B pitch granularity
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return PG_ERR_ARG;
+  const bool bf32 = fu != nullptr && fu->x_f32 != nullptr;
+  if ((K % 8) != 0 || (ldw % 8) != 0) return PG_ERR_ARG;  // TMA: 16 B pitch granularity
+  if (reinterpret_cast<uintptr_t>(w) & 15) return PG_ERR_ARG;
+  if (!bf32 && (x == nullptr || (ldx % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15))) return PG_ERR_ARG;
   if (mode < PG_EPI_BF16 || mode > PG_EPI_GEGLU) return PG_ERR_ARG;
   if (mode == PG_EPI_GEGLU && (features % 128) != 0) return PG_ERR_ARG;
   if (swap < 0) swap = tokens <= 128 ? 1 : 0;
   if (swap && tokens > 128) return PG_ERR_ARG;
-  if (ss_in != nullptr && (!swap || norm_dim <= 0)) return PG_ERR_ARG;  // the per-token factor is a SWAP-kernel epilogue
   const int total_kb = (K + BK - 1) / BK;
   if (split_k <= 0) split_k = 1;
   if (mode != PG_EPI_ATOMIC_F32) split_k = 1;
@@ -796,10 +906,32 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-  GemmArgs a;
+  GemmArgs a = {};
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
   a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
-  a.ss_in = ss_in; a.inv_norm_dim = norm_dim > 0 ? 1.0f / static_cast<float>(norm_dim) : 0.f; a.eps = eps;
+  if (fu != nullptr) {
+    if (!swap) return PG_ERR_ARG;  // the fusions below belong to the decode (swap-AB) kernels
+    if (bf32) {
+      if (fu->norm_w == nullptr || (fu->ldx_f32 % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->x_f32) & 15) ||
+          (reinterpret_cast<uintptr_t>(fu->norm_w) & 15))
+        return PG_ERR_ARG;
+      if (fu->apply_rstd && split_k != 1) return PG_ERR_ARG;  // a split only sees a slice of the row
+      a.xf = fu->x_f32; a.ldxf = fu->ldx_f32; a.norm_w = fu->norm_w; a.apply_rstd = fu->apply_rstd ? 1 : 0; a.eps = fu->eps;
+    }
+    if (fu->zero_count > 0) {
+      if (fu->zero_buf == nullptr || (fu->zero_count % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->zero_buf) & 15)) return PG_ERR_ARG;
+      a.zero_buf = fu->zero_buf; a.zero_count = fu->zero_count;
+    }
+    if (fu->pf_k_pages != nullptr) {
+      if (fu->pf_v_pages == nullptr || fu->pf_page_table == nullptr || fu->pf_kv_len == nullptr || fu->pf_B <= 0 ||
+          fu->pf_max_pages <= 0 || fu->pf_page_bytes <= 0 || (fu->pf_page_bytes % 16) != 0 ||
+          (reinterpret_cast<uintptr_t>(fu->pf_k_pages) & 15) || (reinterpret_cast<uintptr_t>(fu->pf_v_pages) & 15))
+        return PG_ERR_ARG;
+      a.pf_k = static_cast<const uint8_t*>(fu->pf_k_pages); a.pf_v = static_cast<const uint8_t*>(fu->pf_v_pages);
+      a.pf_table = fu->pf_page_table; a.pf_len = fu->pf_kv_len; a.pf_B = fu->pf_B; a.pf_max_pages = fu->pf_max_pages;
+      a.pf_page_bytes = fu->pf_page_bytes;
+    }
+  }
   a.n_fast = 0;
   if (!swap && split_k == 1) {  // DRAM traffic estimate of the two raster orders (100 MB of the 126 MB L2 usable)
     const double l2 = 100e6, A = 2.0 * tokens * K, Bw = 2.0 * features * K;
@@ -809,7 +941,6 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     const double n_fast = A + (Bw > l2 ? Bw * ((static_cast<double>(mb) * nb256 + 147) / 148) : Bw);
     a.n_fast = n_fast < 0.8 * m_fast ? 1 : 0;
   }
-  a.debug_skip_epilogue = getenv("PG_DEBUG_SKIP_EPILOGUE") ? atoi(getenv("PG_DEBUG_SKIP_EPILOGUE")) : 0;
   a.f32_coalesced = (!swap && mode == PG_EPI_F32 && (features % 4) == 0 && (ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
                      (resid == nullptr || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0))) ? 1 : 0;
@@ -820,11 +951,21 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
   if (swap) {
     int BN = tokens <= 16 ? 16 : tokens <= 32 ? 32 : tokens <= 64 ? 64 : 128;
     if ((rc = make_tmap_2d(&ta, w, features, K, ldw, BM)) != PG_OK) return rc;
-    if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
+    if (bf32) tb = ta;  // unused by the BF32 kernels (the B tiles are built from the fp32 rows)
+    else if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
     const int tiles = ((features + BM - 1) / BM) * split_k;
-    static const bool no8 = getenv("PG_NO_SPLITK8") != nullptr;  // A/B switch
-    if ((mode == PG_EPI_ATOMIC_F32 || mode == PG_EPI_GEGLU) && ss_in == nullptr && BN == 64 && !no8)
-      return launch<64, true, true>(ta, tb, a, tiles, st);
+    // 33..64 tokens, red.add or GEGLU epilogue: the 320-thread variant with eight epilogue warps
+    const bool eight = (mode == PG_EPI_ATOMIC_F32 || mode == PG_EPI_GEGLU) && BN == 64;
+    if (bf32) {
+      if (eight) return launch<64, true, true, true>(ta, tb, a, tiles, st);
+      switch (BN) {
+        case 16: return launch<16, true, false, true>(ta, tb, a, tiles, st);
+        case 32: return launch<32, true, false, true>(ta, tb, a, tiles, st);
+        case 64: return launch<64, true, false, true>(ta, tb, a, tiles, st);
+        default: return launch<128, true, false, true>(ta, tb, a, tiles, st);
+      }
+    }
+    if (eight) return launch<64, true, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 16: return launch<16, true>(ta, tb, a, tiles, st);
       case 32: return launch<32, true>(ta, tb, a, tiles, st);
@@ -847,8 +988,7 @@ extern "C" int pg_gemm_bf16_colnorm(const void* x, long long ldx, const void* w,
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
     const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;
     // short reduction (K <= 1536: the SigLIP projections): the epilogue outlasts the main loop, so it gets eight warps
-    static const bool no8p = getenv("PG_NO_PREFILL_EPI8") != nullptr;
-    if (BN == 256 && K <= 1536 && !no8p) return launch<256, false, true>(ta, tb, a, tiles, st);
+    if (BN == 256 && K <= 1536) return launch<256, false, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 64: return launch<64, false>(ta, tb, a, tiles, st);
       case 128: return launch<128, false>(ta, tb, a, tiles, st);

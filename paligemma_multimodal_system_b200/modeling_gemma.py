@@ -8,9 +8,7 @@ Compute path per layer (all through the C ABI of include/paligemma_b200.h):
             residual stream, and split-KV attention over the paged bf16 cache.
 The residual stream is fp32 (as in the reference); GEMM operands are bf16.
 """
-import ctypes
 import math
-import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -20,6 +18,7 @@ from . import _lib
 from .modeling_siglip import _ParamsOnly, _bf16, _f32
 
 PAGE = 64  # tokens per KV page (= the decode attention key tile)
+MAX_DECODE_BATCH = 128  # rows of one decode step (the batch sits on the UMMA N axis of the weight-streaming GEMMs)
 
 
 class KVCache:
@@ -46,8 +45,12 @@ class KVCache:
         """Appends [B, Hkv, s, dh] keys/values (already rotated) for `layer_idx`, returns the full K, V of that layer."""
         _lib.require_device()
         B, Hkv, s, dh = key_states.shape
-        if self._geom is None:
-            raise RuntimeError("KVCache.update before allocation: call allocate(B, layers, Hkv, dh, capacity) first")
+        if self._geom is None:  # the reference's KVCache() is usable as constructed: its first update creates the layer
+            self.allocate(B, layer_idx + 1, Hkv, dh, s + self.reserve_tokens)
+        if self._geom[0] != B or self._geom[2:] != (Hkv, dh):
+            raise ValueError(f"KVCache holds [B, Hkv, dh] = {(self._geom[0],) + self._geom[2:]}, update got {(B, Hkv, dh)}")
+        if layer_idx >= self._geom[1]:
+            self._grow_layers(layer_idx + 1)
         while layer_idx >= len(self._layer_len):
             self._layer_len.append(0)
         start = self._layer_len[layer_idx]
@@ -104,6 +107,13 @@ class KVCache:
         self.k_pages.view(layers, B, new_pages, PAGE, Hkv * dh)[:, :, :old_pages] = old_k.view(layers, B, old_pages, PAGE, Hkv * dh)
         self.v_pages.view(layers, B, new_pages, PAGE, Hkv * dh)[:, :, :old_pages] = old_v.view(layers, B, old_pages, PAGE, Hkv * dh)
         self.page_table = torch.arange(B * new_pages, device="cuda", dtype=torch.int32).view(B, new_pages).contiguous()
+
+    def _grow_layers(self, layers):
+        B, old_layers, Hkv, dh = self._geom
+        extra = torch.zeros(layers - old_layers, *self.k_pages.shape[1:], device="cuda", dtype=torch.bfloat16)
+        self.k_pages = torch.cat([self.k_pages, extra], 0)
+        self.v_pages = torch.cat([self.v_pages, torch.zeros_like(extra)], 0)
+        self._geom = (B, layers, Hkv, dh)
 
     def _dense(self, pages, layer):
         B, _, Hkv, dh = self._geom
@@ -190,18 +200,7 @@ class GemmaModel(_ParamsOnly):
         self.norm = GemmaRMSNorm(config.hidden_size, **fk)
 
 
-def _pick_cluster(tiles_m, total_kb, env=None, sms=148):
-    """Cluster size (split-K ranks per output tile) for the decode GEMMs: enough CTAs to keep every SM streaming weights,
-    a power of two <= 16, at least two k-blocks per rank."""
-    if env and os.environ.get(env):
-        return int(os.environ[env])
-    s = 1
-    while s < 16 and tiles_m * s < sms - 20 and total_kb // (2 * s) >= 2:
-        s *= 2
-    return s
-
-
-def _pick_split(tiles_mn, total_kb, sms=148):
+def _pick_split(tiles_mn, total_kb, sms):
     """split-K so that roughly one wave of CTAs streams the weight matrix (decode GEMMs with few output tiles)."""
     if tiles_mn >= sms:
         return 1
@@ -223,8 +222,6 @@ class GemmaForCausalLM(nn.Module):
         self.model = GemmaModel(config, **fk)
         self._packed = None
         self._ws = {}
-        self._step_maps = {}
-        self._barrier_state = None
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
@@ -263,19 +260,9 @@ class GemmaForCausalLM(nn.Module):
                 qkv_w=torch.cat([_bf16(a.q_proj.weight), _bf16(a.k_proj.weight), _bf16(a.v_proj.weight)], 0).contiguous(),
                 o_w=_bf16(a.o_proj.weight), gu_w=gu, down_w=_bf16(l.mlp.down_proj.weight)))
             del gate, up
-        pk["ln1_all"] = torch.stack([lw["ln1"] for lw in pk["layers"]]).contiguous()
-        pk["ln2_all"] = torch.stack([lw["ln2"] for lw in pk["layers"]]).contiguous()
         torch.cuda.synchronize()
         self._packed = pk
-        self._step_maps = {}
         return pk
-
-    def _buf(self, name, shape, dtype):
-        t = self._ws.get(name)
-        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(*shape, device="cuda", dtype=dtype)
-            self._ws[name] = t
-        return t
 
     # -- prefill ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -360,40 +347,43 @@ class GemmaForCausalLM(nn.Module):
     def decode_buffers(self, B, private: bool = False):
         """Activation buffers of one decode step.  Cached per batch size: captured CUDA graphs (generate(), serving.py) hold
         these addresses, so a buffer must never be replaced once handed out; `private` returns a fresh set owned by the
-        caller."""
+        caller.  `qkv` is the split-K accumulator of the q/k/v projection: zero on entry of decode_layers and zero again
+        on exit (each layer's o_proj launch resets it once the attention kernel has consumed it)."""
         c = self.text_config
+        if B > MAX_DECODE_BATCH:
+            raise ValueError(f"decode batch {B} > {MAX_DECODE_BATCH}: the weight-streaming decode GEMMs put the batch on the "
+                             f"UMMA N axis (<= {MAX_DECODE_BATCH} rows per step); shard the requests over more GPUs / batchers")
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        shapes = dict(h=((B, D), torch.float32), hn=((B, D), torch.bfloat16), hb=((B, D), torch.bfloat16),
-                      ss=((2 * c.num_hidden_layers + 1, B), torch.float32), qkv=((B, (Hq + 2 * Hkv) * dh), torch.float32),
+        shapes = dict(h=((B, D), torch.float32), hn=((B, D), torch.bfloat16), qkv=((B, (Hq + 2 * Hkv) * dh), torch.float32),
                       att=((B, Hq * dh), torch.bfloat16), mid=((B, F), torch.bfloat16), logits=((B, V), torch.float32))
-        if private:
-            return {k: torch.empty(*shp, device="cuda", dtype=dt) for k, (shp, dt) in shapes.items()}
-        return {k: self._buf(f"d_{k}_{B}", shp, dt) for k, (shp, dt) in shapes.items()}
 
-    @torch.no_grad()
-    def decode_prologue(self, bufs, B, tokens_i32=None, img=None, img_scale=1.0, pad_token=-1, image_token=-1):
-        """Token embedding (or the fp32 rows already in bufs['h'] when tokens_i32 is None) -> operands of the first fused
-        RMSNorm (hb = bf16(h * (1 + ln1_0)), ss[0] = sum h^2); zeroes the remaining sum-of-squares accumulators."""
-        c = self.text_config
-        pk = self._packed or self.pack()
-        D = c.hidden_size
-        ss = bufs["ss"]
-        _lib.check(_lib.lib().pg_decode_prologue(
-            _lib.ptr(tokens_i32), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), bufs["hb"].data_ptr(),
-            ss[0].data_ptr(), pk["layers"][0]["ln1"].data_ptr(), ss[1].data_ptr(), ss.numel() - ss.shape[1], B, D,
-            0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token if pad_token is not None else -1, image_token,
-            _lib.stream()), "pg_decode_prologue")
+        def make(shp, dt, name):
+            return (torch.zeros if name == "qkv" else torch.empty)(*shp, device="cuda", dtype=dt)
+
+        if private:
+            return {k: make(shp, dt, k) for k, (shp, dt) in shapes.items()}
+        out = {}
+        for k, (shp, dt) in shapes.items():
+            t = self._ws.get(f"d_{k}_{B}")
+            if t is None or t.shape != tuple(shp) or t.dtype != dt:
+                t = make(shp, dt, k)
+                self._ws[f"d_{k}_{B}"] = t
+            out[k] = t
+        return out
 
     @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B):
-        """One decode step over all layers; reads bufs['h'] (fp32 embeddings), leaves fp32 logits in bufs['logits'].
-        Seven launches per layer: RMSNorm, QKV GEMM, fused RoPE + KV append + attention, O GEMM, RMSNorm, gate||up GEGLU
-        GEMM, down GEMM; the three small-output GEMMs split K over CTAs and red.add their fp32 partials straight into the
-        residual stream / the pre-zeroed qkv buffer.  Every launch reads its sizes from device counters, so the sequence
-        can be captured in a CUDA graph.  (PG_DECODE_CLUSTER=1 selects the variant whose split-K reduction runs inside
-        thread-block clusters and folds the RMSNorms into the GEMM epilogues: measured slower on B200)"""
-        if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
-            return self.decode_layers_cluster(bufs, kv_cache, B)
+        """One decode step over all layers (modeling_gemma.py:385-418 at q_len == 1); reads bufs['h'] (fp32 embeddings),
+        leaves fp32 logits in bufs['logits'].  FIVE launches per layer:
+          1. q/k/v projection, split-K red.add into the zeroed fp32 `qkv`; its activation operand is built in the kernel
+             from the fp32 residual stream (input_layernorm without the per-token factor) and it pulls this layer's live
+             KV pages into L2 while it streams its weights;
+          2. RoPE + KV append + attention (applies the input_layernorm factor to q, k, v);
+          3. o_proj, split-K red.add into the residual stream; re-zeroes `qkv`;
+          4. gate||up with GeGLU epilogue; operand from the residual stream (post_attention_layernorm), the per-token
+             factor computed in the kernel and applied in the epilogue;
+          5. down_proj, split-K red.add into the residual stream.
+        Every launch reads its sizes from device counters, so the sequence can be captured in a CUDA graph."""
         c = self.text_config
         pk = self._packed or self.pack()
         L, st = _lib.lib(), _lib.stream()
@@ -402,124 +392,40 @@ class GemmaForCausalLM(nn.Module):
         pos, kvl = kv_cache.counters[0], kv_cache.counters[2]
         max_pages = kv_cache.page_table.shape[1]
         scale = 1.0 / math.sqrt(dh)
+        eps = c.rms_norm_eps if c.rms_norm_eps is not None else 1e-6
         W = (Hq + 2 * Hkv) * dh
-        sp_qkv = _pick_split((W + 127) // 128, D // 64)
-        sp_o = _pick_split((D + 127) // 128, D // 64)
-        sp_down = _pick_split((D + 127) // 128, F // 64, sms=296)
+        sms = _lib.num_sms()
+        sp_qkv = _pick_split((W + 127) // 128, D // 64, sms)
+        sp_o = _pick_split((D + 127) // 128, D // 64, sms)
+        sp_down = _pick_split((D + 127) // 128, F // 64, 2 * sms)
         if getattr(self, "deterministic_decode", False):
             # one CTA per output tile: the fp32 red.add has a single writer per element, so the step is bitwise
             # reproducible run to run (the split-K partials otherwise arrive in a different order every launch)
             sp_qkv = sp_o = sp_down = 1
         for li, lw in enumerate(pk["layers"]):
-            _lib.rmsnorm(h, lw["ln1"], hn, zero_buf=qkv)
-            _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
-            # RoPE + KV append + split-KV attention + combine: one launch
+            _lib.gemm_fused(lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=lw["ln1"], split_k=sp_qkv,
+                            kv_prefetch=(kv_cache.k_pages[li], kv_cache.v_pages[li], kv_cache.page_table, kvl))
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
-                kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
-            _lib.gemm(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_o)
-            _lib.rmsnorm(h, lw["ln2"], hn)
-            _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
+                kv_cache.k_pages.shape[1], max_pages, scale, h.data_ptr(), D, eps, st), "pg_attention_decode_fused")
+            _lib.gemm_fused(lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, x=att, split_k=sp_o, zero_buf=qkv)
+            _lib.gemm_fused(lw["gu_w"], mid, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=lw["ln2"], apply_rstd=True, eps=eps)
             _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
-        _lib.rmsnorm(h, pk["norm_w"], hn)
+        _lib.rmsnorm(h, pk["norm_w"], hn, eps=eps)
         _lib.gemm(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], swap=1)
         return bufs["logits"]
 
     @torch.no_grad()
-    def decode_layers_cluster(self, bufs, kv_cache: KVCache, B):
-        """Variant of decode_layers with five launches per layer: QKV GEMM (cluster split-K, input RMSNorm applied as a
-        per-token factor), attention, O GEMM (+residual, emits the post-attention norm operands), gate||up GEGLU GEMM, down
-        GEMM (+residual, emits the next layer's norm operands).  Needs decode_prologue() to have filled hb / ss[0]."""
-        c = self.text_config
-        pk = self._packed or self.pack()
-        L, st = _lib.lib(), _lib.stream()
-        D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        h, hb, ss, qkv, att, mid = bufs["h"], bufs["hb"], bufs["ss"], bufs["qkv"], bufs["att"], bufs["mid"]
-        pos, kvl = kv_cache.counters[0], kv_cache.counters[2]
-        max_pages = kv_cache.page_table.shape[1]
-        scale = 1.0 / math.sqrt(dh)
-        W = (Hq + 2 * Hkv) * dh
-        eps = 1e-6
-        s_qkv = _pick_cluster((W + 127) // 128, D // 64, "PG_S_QKV")
-        s_o = _pick_cluster((D + 127) // 128, D // 64, "PG_S_O")
-        s_down = _pick_cluster((D + 127) // 128, F // 64, "PG_S_DOWN")
-        n_layers = len(pk["layers"])
-        for li, lw in enumerate(pk["layers"]):
-            _lib.gemm_decode(hb, lw["qkv_w"], qkv, mode=_lib.DEC_F32, cluster_k=s_qkv, ss_in=ss[2 * li], norm_dim=D, eps=eps)
-            _lib.check(L.pg_attention_decode_fused(
-                qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
-                kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
-                kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
-            _lib.gemm_decode(att, lw["o_w"], h, mode=_lib.DEC_RESID_NORM, cluster_k=s_o, hb=hb, norm_w=lw["ln2"], ss_out=ss[2 * li + 1])
-            _lib.gemm_colnorm(hb, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, ss_in=ss[2 * li + 1], norm_dim=D, eps=eps)
-            next_w = pk["layers"][li + 1]["ln1"] if li + 1 < n_layers else pk["norm_w"]
-            _lib.gemm_decode(mid, lw["down_w"], h, mode=_lib.DEC_RESID_NORM, cluster_k=s_down, hb=hb, norm_w=next_w, ss_out=ss[2 * li + 2])
-        _lib.gemm_colnorm(hb, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], ss_in=ss[2 * n_layers], norm_dim=D, eps=eps)
-        return bufs["logits"]
-
-    # -- one-kernel decode step ------------------------------------------------------------------------------------------
-    def megakernel_ok(self, B):
-        c = self.text_config
-        # opt-in: measured slower than the PDL-chained per-op kernels (2.19 vs 1.74 ms / step at 3B, 64 sequences): a grid
-        # barrier costs ~2.3 us, about the same as a programmatic-dependent-launch kernel boundary (DESIGN.md 4)
-        return (os.environ.get("PG_MEGAKERNEL", "0") == "1" and B * c.num_key_value_heads <= 148 and B <= 64
-                and c.head_dim in (64, 256) and c.num_attention_heads // c.num_key_value_heads <= 8)
-
-    @torch.no_grad()
     def decode_step(self, bufs, kv_cache: KVCache, B, tokens_i32, img, img_scale, pad_token, image_token):
-        """Embeds `tokens_i32` [B] and runs every layer + final norm + lm_head; fp32 logits land in bufs['logits'].
-        B <= 64: ONE persistent cooperative kernel (csrc/decode_step.cu); otherwise the per-op kernels."""
+        """Embeds `tokens_i32` [B] and runs every layer + final norm + lm_head; fp32 logits land in bufs['logits']."""
         c = self.text_config
         pk = self._packed or self.pack()
-        L = _lib.lib()
-        D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
-        if not self.megakernel_ok(B):
-            if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
-                self.decode_prologue(bufs, B, tokens_i32, img, img_scale, pad_token, image_token)
-            else:
-                _lib.check(L.pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
-                                             0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
-                                             _lib.stream()), "pg_embed_tokens")
-            return self.decode_layers(bufs, kv_cache, B)
-        key = (B, bufs["hn"].data_ptr(), bufs["att"].data_ptr(), bufs["mid"].data_ptr())
-        maps = self._step_maps.get(key)
-        if maps is None:
-            n = 4 * c.num_hidden_layers + 4
-            host = ctypes.create_string_buffer(n * 128)
-            wl = []
-            for lw in pk["layers"]:
-                wl += [lw["qkv_w"].data_ptr(), lw["o_w"].data_ptr(), lw["gu_w"].data_ptr(), lw["down_w"].data_ptr()]
-            wl.append(pk["head_w"].data_ptr())
-            warr = (ctypes.c_void_p * len(wl))(*wl)
-            _lib.check(L.pg_decode_step_encode_maps(ctypes.addressof(host), ctypes.addressof(warr), bufs["hn"].data_ptr(),
-                                                    bufs["att"].data_ptr(), bufs["mid"].data_ptr(), c.num_hidden_layers, B, D, F,
-                                                    Hq, Hkv, dh, V), "pg_decode_step_encode_maps")
-            maps = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).cuda()
-            self._step_maps = {key: maps}
-        if self._barrier_state is None:
-            self._barrier_state = torch.zeros(256, device="cuda", dtype=torch.int32)
-        W = (Hq + 2 * Hkv) * dh
-        a = _lib.DecodeStepArgs()
-        a.tensor_maps = maps.data_ptr()
-        a.L, a.B, a.D, a.F, a.Hq, a.Hkv, a.dh, a.V = c.num_hidden_layers, B, D, F, Hq, Hkv, dh, V
-        a.split_qkv = _pick_split((W + 127) // 128, D // 64)
-        a.split_o = _pick_split((D + 127) // 128, D // 64)
-        a.split_down = _pick_split((D + 127) // 128, F // 64)
-        a.cur_tok, a.embed, a.img = tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img)
-        a.n_img = 0 if img is None else img.shape[1]
-        a.text_scale, a.img_scale, a.pad_token, a.image_token = D ** 0.5, img_scale, pad_token, image_token
-        a.h, a.hn, a.qkv, a.att, a.mid, a.logits = (bufs[k].data_ptr() for k in ("h", "hn", "qkv", "att", "mid", "logits"))
-        a.ln1, a.ln2, a.norm_w, a.head_b, a.eps = pk["ln1_all"].data_ptr(), pk["ln2_all"].data_ptr(), pk["norm_w"].data_ptr(), pk["head_b"].data_ptr(), 1e-6
-        a.k_pages, a.v_pages = kv_cache.k_pages.data_ptr(), kv_cache.v_pages.data_ptr()
-        a.layer_stride = kv_cache.k_pages.stride(0)
-        a.page_table, a.pos, a.kv_len = kv_cache.page_table.data_ptr(), kv_cache.counters[0].data_ptr(), kv_cache.counters[2].data_ptr()
-        a.inv_freq, a.max_pages, a.page_size, a.scale = pk["inv_freq"].data_ptr(), kv_cache.page_table.shape[1], PAGE, 1.0 / math.sqrt(dh)
-        a.barrier_state = self._barrier_state.data_ptr()
-        a.trace = _lib.ptr(getattr(self, "_trace", None))
-        a.trace_cta = getattr(self, "_trace_cta", 0)
-        _lib.check(L.pg_decode_step(ctypes.byref(a), _lib.stream()), "pg_decode_step")
-        return bufs["logits"]
+        D = c.hidden_size
+        _lib.check(_lib.lib().pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
+                                              0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
+                                              _lib.stream()), "pg_embed_tokens")
+        return self.decode_layers(bufs, kv_cache, B)
 
     def forward(self, input_embeds=None, position_ids=None, attention_mask=None, kv_cache=None):
         """Reference signature (modeling_gemma.py:501-533): input_embeds [B,S,D] UNSCALED (the sqrt(D) normaliser is
@@ -538,8 +444,6 @@ class GemmaForCausalLM(nn.Module):
             kv_cache.counters[2].fill_(n + 1)
             bufs = self.decode_buffers(B)
             bufs["h"].copy_(h)
-            if os.environ.get("PG_DECODE_CLUSTER", "0") == "1":
-                self.decode_prologue(bufs, B)
             logits = self.decode_layers(bufs, kv_cache, B).clone().view(B, 1, -1)
             kv_cache._set_len(n + 1, self.text_config.num_hidden_layers)
         else:

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .modeling_gemma import GemmaConfig, GemmaForCausalLM, KVCache
+from .modeling_gemma import MAX_DECODE_BATCH, GemmaConfig, GemmaForCausalLM, KVCache
 from .modeling_siglip import SiglipVisionConfig, SiglipVisionModel, _ParamsOnly, _bf16
 
 
@@ -58,10 +58,20 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         self.pad_token_id = config.pad_token_id if config.pad_token_id is not None else -1
         self.dummy_image_token_id = config.image_token_index
         self._proj_w = None
+        self._proj_b = None  # fp32 projector bias of real checkpoints (utils.load_hf_model); the reference has none
         self._graphs = {}
 
     def tie_weights(self):
+        # captured graphs hold raw pointers into the packed weights, which are rebuilt after this
+        self._graphs = {}
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
         return self.language_model.tie_weights()
+
+    def set_projector_bias(self, bias):
+        """multi_modal_projector.linear.bias of a Hugging Face checkpoint (absent from the reference's module tree,
+        modeling_paligemma.py:57): added in the projector GEMM epilogue."""
+        self._proj_b = None if bias is None else bias.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        self._graphs = {}
 
     def _apply(self, fn, *a, **k):
         self._proj_w = None
@@ -80,6 +90,8 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         self.vision_tower.pack()
         self.language_model.pack()
         self._proj_w = _bf16(self.multi_modal_projector.linear.weight)
+        self._graphs = {}
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
         return self
 
     # -- pieces ------------------------------------------------------------------------------------------------------
@@ -91,7 +103,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         B = pixel_values.shape[0]
         feats = self.vision_tower.forward_features(pixel_values, out_bf16=True)
         out = torch.empty(feats.shape[0], self.config.projection_dim, device=feats.device, dtype=torch.float32)
-        _lib.gemm(feats, self._proj_w, out, mode=_lib.EPI_F32, swap=0 if feats.shape[0] > 128 else 1)
+        _lib.gemm(feats, self._proj_w, out, mode=_lib.EPI_F32, bias=self._proj_b, swap=0 if feats.shape[0] > 128 else 1)
         return out.view(B, -1, self.config.projection_dim)
 
     @torch.no_grad()
@@ -240,6 +252,9 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         L = _lib.lib()
         lm, c = self.language_model, self.text_config
         B, S = input_ids.shape
+        if B > MAX_DECODE_BATCH:
+            raise ValueError(f"generate() serves at most {MAX_DECODE_BATCH} rows per call (decode batch of the weight-streaming "
+                             "GEMMs); split the batch or shard it over GPUs (sharding.py)")
         T = int(max_tokens_to_generate)
         V = c.vocab_size
         dev = torch.device("cuda")

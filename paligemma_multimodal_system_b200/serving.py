@@ -134,8 +134,10 @@ class ContinuousBatcher:
         self.lm, self.c = model.language_model, model.text_config
         c = self.c
         self.B = int(num_slots)
-        if self.B > 1024:
-            raise ValueError("at most 1024 slots")
+        from .modeling_gemma import MAX_DECODE_BATCH
+        if self.B > MAX_DECODE_BATCH:
+            raise ValueError(f"at most {MAX_DECODE_BATCH} slots per batcher (one decode step = one <= {MAX_DECODE_BATCH}-row "
+                             "weight-streaming GEMM batch); run several batchers / GPUs for more concurrent requests")
         self.max_prompt_len, self.max_new_tokens = int(max_prompt_len), int(max_new_tokens)
         self.do_sample, self.inv_t, self.top_p, self.seed = bool(do_sample), 1.0 / float(temperature), float(top_p), int(seed)
         self.GK = max(1, int(steps_per_replay))
@@ -163,6 +165,7 @@ class ContinuousBatcher:
         self._set_idle(list(range(self.B)))
         self.bufs = self.lm.decode_buffers(self.B, private=True)  # the captured graph owns these addresses
         self.graph = None
+        self._graph_weights_version = 0
         self.admit_logits = {} if keep_admit_logits else None  # request id -> fp32 logits of its first token (tests)
         self._next_rid = 0
         self.reset_stats()
@@ -316,8 +319,12 @@ class ContinuousBatcher:
         return g
 
     def _decode_group(self):
+        ver = getattr(self.model, "_weights_version", 0)
+        if self.graph is not None and ver != self._graph_weights_version:
+            self.graph = None  # the model re-packed its weights (tie_weights / pack): the captured pointers are stale
         if self.use_cuda_graph and self.graph is None and self.stats["decode_replays"] > 0:
             self.graph = self._capture()  # the first group ran eagerly: lazy kernel attributes / entry points are warm
+            self._graph_weights_version = ver
         if self.graph is not None:
             self.graph.replay()
         else:

@@ -1,0 +1,134 @@
+"""Steady-state timing of the decode-layer kernel chain (3B shapes), 18 layers' weights in rotation (cold L2), every chain
+captured in one CUDA graph (no host launch overhead).  A/B of the 7-launch chain (standalone RMSNorms, bf16 operands by TMA)
+against the 5-launch chain (norms folded into the GEMMs, KV pages prefetched into L2 by the q/k/v projection).
+
+    python profiles/tools/decode_microbench.py            # MB_B=64 MB_KV=324 by default
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from paligemma_multimodal_system_b200 import _lib  # noqa: E402
+
+L = _lib.lib()
+B, D, F, Hq, Hkv, dh, V, NL = int(os.environ.get("MB_B", 64)), 2048, 16384, 8, 1, 256, 257216, 18
+kvlen = int(os.environ.get("MB_KV", 324))
+W = (Hq + 2 * Hkv) * dh
+dev = "cuda"
+PEAK = 6550.7e3  # bytes / us
+
+
+def rnd(*s):
+    return (torch.randn(*s, device=dev) * 0.02).bfloat16()
+
+
+qkv_w = [rnd(W, D) for _ in range(NL)]
+o_w = [rnd(D, D) for _ in range(NL)]
+gu_w = [rnd(2 * F, D) for _ in range(NL)]
+down_w = [rnd(D, F) for _ in range(NL)]
+head_w = rnd(V, D)
+head_b = torch.randn(V, device=dev)
+hn = rnd(B, D)
+att = rnd(B, Hq * dh)
+mid = rnd(B, F)
+h = torch.randn(B, D, device=dev)
+qkv = torch.zeros(B, W, device=dev)
+midout = torch.empty(B, F, device=dev, dtype=torch.bfloat16)
+logits = torch.empty(B, V, device=dev)
+ln_w = torch.zeros(D, device=dev)
+hn_out = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+PAGE = 64
+max_pages = (kvlen + PAGE - 1) // PAGE + 1
+k_pages = [rnd(B * max_pages, PAGE, dh) for _ in range(NL)]
+v_pages = [rnd(B * max_pages, PAGE, dh) for _ in range(NL)]
+table = torch.arange(B * max_pages, device=dev, dtype=torch.int32).view(B, max_pages).contiguous()
+kvl = torch.full((B,), kvlen, device=dev, dtype=torch.int32)
+posd = torch.full((B,), kvlen, device=dev, dtype=torch.int32)
+inv_freq = (1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).to(dev)
+attout = torch.empty(B, Hq * dh, device=dev, dtype=torch.bfloat16)
+sms = _lib.num_sms()
+SQ, SO, SD = max(1, sms // 20), max(1, sms // 16), max(1, 2 * sms // 16)
+
+
+def graph_time(name, fn, bytes_per_launch, reps=5):
+    for i in range(NL):
+        fn(i)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for i in range(NL):
+                fn(i)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * NL)
+    print(f"{name:52s} {us:8.2f} us   {bytes_per_launch / us / 1e3:8.1f} GB/s  ideal {bytes_per_launch / PEAK:6.2f} us", flush=True)
+    return us
+
+
+def attn(i, norm=False):
+    _lib.check(L.pg_attention_decode_fused(qkv.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(),
+                                           v_pages[i].data_ptr(), table.data_ptr(), attout.data_ptr(), B, Hq, Hkv, dh, PAGE, B * max_pages,
+                                           max_pages, 1.0 / 16, h.data_ptr() if norm else 0, D, 1e-6, _lib.stream()), "attn")
+
+
+def old_layer(i):
+    _lib.rmsnorm(h, ln_w, hn_out)
+    _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ)
+    attn(i)
+    _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=attout, split_k=SO, zero_buf=qkv)
+    _lib.rmsnorm(h, ln_w, hn_out)
+    _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+    _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD)
+
+
+def make_new_layer(prefetch=True, fold_qkv=True, fold_gu=True):
+    def f(i):
+        pf = (k_pages[i], v_pages[i], table, kvl) if prefetch else None
+        if fold_qkv:
+            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ, kv_prefetch=pf)
+        else:
+            _lib.rmsnorm(h, ln_w, hn_out)
+            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ, kv_prefetch=pf)
+        attn(i, norm=fold_qkv)
+        _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=attout, split_k=SO, zero_buf=qkv)
+        if fold_gu:
+            _lib.gemm_fused(gu_w[i], midout, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=ln_w, apply_rstd=True)
+        else:
+            _lib.rmsnorm(h, ln_w, hn_out)
+            _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
+        _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD)
+    return f
+
+
+layer_bytes = (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4
+print(f"==== B={B} kv={kvlen} splits qkv {SQ} o {SO} down {SD}")
+graph_time("qkv  bf16 operand (TMA)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn, split_k=SQ), W * D * 2)
+graph_time("qkv  fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ), W * D * 2)
+graph_time("qkv  fp32 operand + KV prefetch", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ,
+                                                                        kv_prefetch=(k_pages[i], v_pages[i], table, kvl)), W * D * 2)
+graph_time("o    split-K", lambda i: _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=att, split_k=SO), D * D * 2)
+graph_time("gate-up geglu, bf16 operand (TMA)", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
+graph_time("gate-up geglu, fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(gu_w[i], midout, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=ln_w, apply_rstd=True), 2 * F * D * 2)
+graph_time("down split-K", lambda i: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD), D * F * 2)
+graph_time("rmsnorm", lambda i: _lib.rmsnorm(h, ln_w, hn_out), B * D * 6)
+graph_time("attention (cold KV)", lambda i: attn(i), B * kvlen * dh * 4)
+graph_time("attention (cold KV, + norm factor)", lambda i: attn(i, True), B * kvlen * dh * 4)
+graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
+graph_time("LAYER 7 launches (round-1 chain)", old_layer, layer_bytes)
+graph_time("LAYER 5 launches (norms folded, KV prefetch)", make_new_layer(), layer_bytes)
+graph_time("LAYER 5 launches, no KV prefetch", make_new_layer(prefetch=False), layer_bytes)
+graph_time("LAYER 6 launches: only qkv norm folded", make_new_layer(fold_gu=False), layer_bytes)
+graph_time("LAYER 6 launches: only gate-up norm folded", make_new_layer(fold_qkv=False), layer_bytes)
+graph_time("LAYER 7 launches + KV prefetch", make_new_layer(fold_qkv=False, fold_gu=False), layer_bytes)

@@ -54,51 +54,12 @@ def test_gemma_prefill_attention(B, S, Hq, dh):
     _close(out, ref, 1.5e-2, "gemma prefill attention")
 
 
-@pytest.mark.parametrize("B,Hq,dh,lens,splits", [
-    (4, 8, 256, [261, 300, 64, 1], 4), (2, 4, 64, [17, 130], 2), (64, 8, 256, None, 4), (1, 8, 256, [700], 8),
-    (3, 8, 256, [128, 129, 127], 1)])
-def test_decode_attention_paged(B, Hq, dh, lens, splits):
-    from paligemma_multimodal_system_b200 import _lib
-    if lens is None:
-        lens = [260 + (i % 7) for i in range(B)]
-    page = 64
-    max_pages = (max(lens) + page - 1) // page + 1
-    num_pages = B * max_pages + 3
-    g = torch.Generator(device="cuda").manual_seed(0)
-    k_pages = (torch.randn(num_pages, page, dh, device="cuda", generator=g) * 0.5).bfloat16()
-    v_pages = (torch.randn(num_pages, page, dh, device="cuda", generator=g) * 0.5).bfloat16()
-    perm = torch.randperm(num_pages, device="cuda", generator=g)[: B * max_pages].int().view(B, max_pages).contiguous()
-    q = (torch.randn(B, Hq * dh, device="cuda", generator=g) * 0.5).bfloat16()
-    kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32)
-    out = torch.full((B, Hq * dh), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ws = torch.empty(_lib.lib().pg_attention_decode_workspace_floats(B, Hq, dh, splits), device="cuda")
-    scale = 1.0 / math.sqrt(dh)
-    rc = _lib.lib().pg_attention_decode(q.data_ptr(), k_pages.data_ptr(), v_pages.data_ptr(), perm.data_ptr(), kv_len.data_ptr(),
-                                        out.data_ptr(), ws.data_ptr(), B, Hq, 1, dh, page, max_pages, splits, scale, _lib.stream())
-    _lib.check(rc, "decode attn")
-    torch.cuda.synchronize()
-    for b in range(B):
-        L = lens[b]
-        idx = perm[b].long()
-        K = k_pages[idx].reshape(-1, dh)[:L].float()
-        V = v_pages[idx].reshape(-1, dh)[:L].float()
-        qb = q[b].float().view(Hq, dh)
-        ref = torch.softmax(qb @ K.t() * scale, -1) @ V
-        _close(out[b].view(Hq, dh), ref, 1.5e-2, f"decode attention row {b}")
-
-    # gather view
-    dense = torch.empty(B, 1, min(lens), dh, device="cuda", dtype=torch.bfloat16)
-    rc = _lib.lib().pg_kv_gather(k_pages.data_ptr(), perm.data_ptr(), dense.data_ptr(), B, min(lens), 1, dh, page, max_pages, _lib.stream())
-    _lib.check(rc, "gather")
-    torch.cuda.synchronize()
-    for b in range(B):
-        assert torch.equal(dense[b, 0], k_pages[perm[b].long()].reshape(-1, dh)[: min(lens)])
-
-
+@pytest.mark.parametrize("with_norm", [False, True])
 @pytest.mark.parametrize("B,Hq,dh,lens", [(4, 8, 256, [261, 300, 64, 1]), (2, 4, 64, [17, 130]), (64, 8, 256, None), (3, 8, 256, [128, 129, 65]),
                                           (1, 8, 256, [4100]), (40, 8, 256, None), (160, 8, 256, None)])
-def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
-    """pg_attention_decode_fused == RoPE(q,k_new) + cache append + softmax(QK^T/sqrt(dh))V over the whole cache."""
+def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens, with_norm):
+    """pg_attention_decode_fused == RoPE(q,k_new) + cache append + softmax(QK^T/sqrt(dh))V over the whole cache; with
+    `h_norm` the raw projections are first scaled by the row's RMSNorm factor rsqrt(mean(h^2) + eps)."""
     from paligemma_multimodal_system_b200 import _lib
     if lens is None:
         lens = [260 + (i % 70) for i in range(B)]
@@ -116,15 +77,20 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
     out = torch.full((B, Hq * dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     k_before, v_before = k_pages.clone(), v_pages.clone()
     scale = 1.0 / math.sqrt(dh)
+    D, eps = 520, 1e-6
+    hres = torch.randn(B, D, device="cuda", generator=g) * torch.linspace(0.3, 3.0, B, device="cuda")[:, None]
     for rep in range(2):
         k_pages.copy_(k_before); v_pages.copy_(v_before)
         rc = _lib.lib().pg_attention_decode_fused(qkv.data_ptr(), pos.data_ptr(), kv_len.data_ptr(), inv_freq.data_ptr(),
                                                   k_pages.data_ptr(), v_pages.data_ptr(), table.data_ptr(), out.data_ptr(),
-                                                  B, Hq, 1, dh, page, num_pages, max_pages, scale, _lib.stream())
+                                                  B, Hq, 1, dh, page, num_pages, max_pages, scale,
+                                                  hres.data_ptr() if with_norm else 0, D, eps, _lib.stream())
         _lib.check(rc, "fused decode attn")
         torch.cuda.synchronize()
     half = dh // 2
     rot = lambda t: torch.cat([-t[..., half:], t[..., :half]], -1)
+    if with_norm:  # the kernel's inputs are the projections of the un-normalised rows
+        qkv = qkv * torch.rsqrt(hres.pow(2).mean(-1, keepdim=True) + eps)
     for b in range(B):
         L = lens[b]
         ang = pos[b].float() * inv_freq
@@ -144,7 +110,7 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
         # the append landed in the right page slot, nothing else in the cache changed
         pg_, off = table[b, (L - 1) // page].item(), (L - 1) % page
         assert (k_pages[pg_, off].float() - kr.float()).abs().max() <= 2 ** -7 * kr.float().abs().max()
-        assert torch.equal(v_pages[pg_, off], vn.bfloat16())
+        assert (v_pages[pg_, off].float() - vn).abs().max() <= 2 ** -7 * vn.abs().max()
     changed = (k_pages != k_before).any(-1).sum().item()
     assert changed <= B
 
@@ -175,3 +141,32 @@ def test_prefill_attention_tcgen05_long_and_ragged(B, H, N, dh, group):
     ref = torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf   # [B,H,G,N,dh]
     ref = ref.permute(0, 3, 1, 2, 4)
     _close(out, ref, 2e-2, "tcgen05 prefill attention")
+
+
+def test_kv_gather_dense_view():
+    from paligemma_multimodal_system_b200 import _lib
+    B, dh, page, max_pages, n = 3, 256, 64, 4, 150
+    g = torch.Generator(device="cuda").manual_seed(1)
+    k_pages = (torch.randn(B * max_pages + 2, page, dh, device="cuda", generator=g)).bfloat16()
+    perm = torch.randperm(B * max_pages + 2, device="cuda", generator=g)[: B * max_pages].int().view(B, max_pages).contiguous()
+    dense = torch.empty(B, 1, n, dh, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().pg_kv_gather(k_pages.data_ptr(), perm.data_ptr(), dense.data_ptr(), B, n, 1, dh, page, max_pages, _lib.stream()), "gather")
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert torch.equal(dense[b, 0], k_pages[perm[b].long()].reshape(-1, dh)[:n])
+
+
+def test_attention_shapes_without_a_kernel_are_errors():
+    """One kernel per entry point: what it cannot express is PG_ERR_ARG, never a silent second implementation."""
+    from paligemma_multimodal_system_b200 import _lib
+    x = torch.zeros(4096, device="cuda", dtype=torch.bfloat16)
+    # dh = 48 has no tcgen05 instantiation; a GQA group of 3 does not tile 128 query rows
+    assert _lib.lib().pg_attention_prefill(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 1, 8, 8, 48, 1, 384, 48, 0, 48,
+                                           384, 48, 48, 384, 48, 0, 48, 0.1, _lib.stream()) == -1
+    assert _lib.lib().pg_attention_prefill(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 1, 6, 2, 64, 3, 384, 192, 64, 0,
+                                           128, 64, 0, 384, 192, 64, 0, 0.1, _lib.stream()) == -1
+    f = torch.zeros(4096, device="cuda")
+    i = torch.ones(4, device="cuda", dtype=torch.int32)
+    # GQA group 16 > 8: no decode kernel
+    assert _lib.lib().pg_attention_decode_fused(f.data_ptr(), i.data_ptr(), i.data_ptr(), f.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                                i.data_ptr(), x.data_ptr(), 1, 16, 1, 64, 64, 1, 1, 0.1, 0, 0, 0.0, _lib.stream()) == -1
