@@ -75,6 +75,11 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
  *    pages located through pf_page_table [pf_B, pf_max_pages]; pf_page_bytes = 64 * Hkv * dh * 2.  Issued before the
  *    dependency wait, so the attention kernel that follows finds its cache rows in L2 (KVCache reads of
  *    modeling_gemma.py:49-57 / 307-339 overlapped with the projection that precedes them).
+ *  - stats (PG_EPI_F32 only, no resid / x_f32 / split-K): the lm_head of a decode step (modeling_gemma.py:523-525) also emits,
+ *    for every token t and every 32-row vocabulary segment g (g = f / 32), stats[t * stats_ld + g] = (m, s) with
+ *    m = max logit of the segment and s = sum exp2((logit - m) * stat_c), stat_c = inv_temperature * log2(e) -- temperature
+ *    scaling and the max / partition-function passes of softmax + top-p (inference.py:63-66,90-106) folded into the GEMM
+ *    epilogue; consumed by pg_sample_top_p_stats / pg_argmax_stats.  stats_ld >= 4 * ceil(features / 128) (float2 units).
  */
 typedef struct PgGemmFusion {
   const float* x_f32;
@@ -90,6 +95,9 @@ typedef struct PgGemmFusion {
   const int* pf_kv_len;
   int pf_B, pf_max_pages;
   long long pf_page_bytes;
+  void* stats;
+  long long stats_ld;
+  float stat_c;
 } PgGemmFusion;
 int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
                        const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
@@ -215,6 +223,21 @@ int pg_argmax(const float* logits, long long ld, int* out, int B, int V, void* s
  */
 int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count, int B, int V, float inv_temperature,
                     float top_p, unsigned long long seed, const int* step_ptr, void* stream);
+
+/*
+ * The same two samplers fed by the segment statistics the lm_head epilogue emits (PgGemmFusion.stats: per 32-token vocabulary
+ * segment, max logit and sum exp2((x - max) * inv_temperature * log2 e)): row maximum, partition function and the segment
+ * masses of the inverse-CDF draw come from 8 bytes per segment instead of passes over the fp32 row; only the top-p
+ * verification pass (mass of strictly more probable tokens <= top_p, inference.py:96-100) still reads the logits.
+ * stats: float2 [B, stats_ld], stats_ld >= ceil(V / 32); the statistics must have been produced with the SAME
+ * inv_temperature.  seed_ptr (device, optional) overrides `seed`, so that a captured CUDA graph serves every seed.
+ * A row whose 64 candidates are all rejected (top_p far below the largest probability) yields its most probable token.
+ */
+int pg_argmax_stats(const float* logits, long long ld, const void* stats, long long stats_ld, int* out, int B, int V,
+                    void* stream);
+int pg_sample_top_p_stats(const float* logits, long long ld, const void* stats, long long stats_ld, int* out, int B, int V,
+                          float inv_temperature, float top_p, unsigned long long seed, const unsigned long long* seed_ptr,
+                          const int* step_ptr, void* stream);
 
 /* After sampling (device-side loop state, CUDA-graph friendly): tok_hist[step*B + b] = next[b]; cur_tok[b] = next[b];
  * counters[c*B + b] += 1 for c < n_counters (position ids, KV write slots, KV lengths); step += 1.  B <= 1024. */

@@ -50,6 +50,8 @@ SIGNATURES = {
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
     "pg_argmax": [p, i64, p, i32, i32, p],
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
+    "pg_argmax_stats": [p, i64, p, i64, p, i32, i32, p],
+    "pg_sample_top_p_stats": [p, i64, p, i64, p, i32, i32, f32, f32, u64, p, p, p],
     "pg_advance_decode": [p, p, p, p, i32, p, i32, p],
     "pg_advance_decode_slots": [p, p, i32, p, p, p, p, i32, p],
 }
@@ -64,6 +66,7 @@ class GemmFusion(C.Structure):
         ("zero_buf", p), ("zero_count", i64),
         ("pf_k_pages", p), ("pf_v_pages", p), ("pf_page_table", p), ("pf_kv_len", p), ("pf_B", i32), ("pf_max_pages", i32),
         ("pf_page_bytes", i64),
+        ("stats", p), ("stats_ld", i64), ("stat_c", f32),
     ]
 
 
@@ -132,14 +135,19 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
     return out
 
 
+LOG2E = 1.4426950408889634
+
+
 def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=False, eps=1e-6, zero_buf=None, kv_prefetch=None,
-               bias=None, split_k=1):
+               bias=None, split_k=1, stats=None, inv_temperature=1.0):
     """Decode-step (swap-AB, tokens <= 128) GEMM with the fusions of pg_gemm_bf16_fused:
       x_f32 / norm_w   activation operand built in the kernel from the fp32 residual rows, bf16(x * (1 + norm_w)) -- the
                        GemmaRMSNorm that precedes the projection, minus its per-token factor (apply_rstd: applied in the
                        epilogue; otherwise the consumer applies it);
       zero_buf         fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
-      kv_prefetch      (k_pages_layer, v_pages_layer, page_table, kv_len) whose live pages are pulled into L2."""
+      kv_prefetch      (k_pages_layer, v_pages_layer, page_table, kv_len) whose live pages are pulled into L2;
+      stats            fp32 [T, nseg, 2] (nseg >= 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
+                       `inv_temperature`, for pg_sample_top_p_stats / pg_argmax_stats (mode EPI_F32 only)."""
     assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
     fu = GemmFusion()
     if x_f32 is not None:
@@ -160,6 +168,9 @@ def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=Fals
         fu.pf_k_pages, fu.pf_v_pages, fu.pf_page_table, fu.pf_kv_len = kp.data_ptr(), vp.data_ptr(), table.data_ptr(), kv_len.data_ptr()
         fu.pf_B, fu.pf_max_pages = table.shape
         fu.pf_page_bytes = kp.stride(0) * kp.element_size()
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[2] == 2 and stats.is_contiguous()
+        fu.stats, fu.stats_ld, fu.stat_c = stats.data_ptr(), stats.shape[1], float(inv_temperature) * LOG2E
     check(lib().pg_gemm_bf16_fused(xp, ldx, w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias), 0, 0, T, w.shape[0], K,
                                    mode, 0, 1.0, 1, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")
     return out

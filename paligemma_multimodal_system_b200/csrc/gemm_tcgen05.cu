@@ -83,6 +83,10 @@ struct GemmArgs {
   const int* pf_len;
   int pf_B, pf_max_pages;
   long long pf_page_bytes;
+  // lm_head (PG_EPI_F32, swap): softmax statistics of every 32-row vocabulary segment, for the sampler that follows
+  float2* stats;       // [tokens][stats_ld]: (max logit of the segment, sum exp2((x - max) * stat_c))
+  long long stats_ld;  // segments per token row (>= 4 * ceil(features / 128))
+  float stat_c;        // inv_temperature * log2(e)
 };
 
 struct TileInfo {
@@ -162,6 +166,43 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
       dst += step;
       if (MODE == PG_EPI_F32) res += rstep;
     }
+  }
+}
+
+// lm_head epilogue (swap-AB, fp32 logits + bias) that also emits, per token column, the softmax statistics of the 32
+// vocabulary rows this warp holds: (m, s) = (max_r x_r, sum_r exp2((x_r - m) * c)), c = inv_temperature * log2(e).  The
+// sampler (sampler.cu) turns them into the row maximum, the partition function and the segment masses of its inverse-CDF
+// draw without touching the 1 MB logit row: temperature scaling + the first two passes of softmax/top-p
+// (inference.py:63-66,90-106) folded into the GEMM that produces the logits (modeling_gemma.py:523-525).
+// Rows past `features` (vocabulary tail) count as -inf; all 32 lanes take part in the shuffles.
+template <int BN>
+PG_DEVINL void swap_tile_epilogue_f32_stats(const GemmArgs& args, uint32_t taddr, int fr, int j_base, int seg, int lane) {
+  const bool f_ok = fr < args.features;
+  const int nvalid = min(BN, args.tokens - j_base);
+  const float scale = args.scale, c = args.stat_c;
+  const float bias_s = (args.bias != nullptr && f_ok) ? __ldg(args.bias + fr) * scale : 0.f;
+  float* dst = reinterpret_cast<float*>(args.out) + static_cast<long long>(j_base) * args.ldo + fr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (c0 >= nvalid) break;  // warp-uniform
+    uint32_t r[16];
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+    const int n = min(16, nvalid - c0);
+    float keep_m = -INFINITY, keep_s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = f_ok ? fmaf(__uint_as_float(r[i]), scale, bias_s) : -INFINITY;
+      if (i < n && f_ok) dst[static_cast<long long>(c0 + i) * args.ldo] = x;
+      float m = x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float e = x == -INFINITY ? 0.f : exp2f((x - m) * c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      if (lane == i) { keep_m = m; keep_s = e; }
+    }
+    if (lane < n) args.stats[static_cast<long long>(j_base + c0 + lane) * args.stats_ld + seg] = make_float2(keep_m, keep_s);
   }
 }
 
@@ -818,6 +859,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         } else {
           // (measured: 16-byte REDG.F32x4 after a lane-quad transpose is ~2x SLOWER here than 4-byte coalesced reds)
           if (mode == PG_EPI_ATOMIC_F32) swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, fr, j_base, first_split, rs_tab);
+          else if (mode == PG_EPI_F32 && args.stats != nullptr) swap_tile_epilogue_f32_stats<BN>(args, taddr, fr, j_base, t.m_blk * 4 + q, lane);
           else if (mode == PG_EPI_F32) swap_tile_epilogue<BN, PG_EPI_F32>(args, taddr, fr, j_base, first_split, rs_tab);
           else swap_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, fr, j_base, first_split, rs_tab);
         }
@@ -930,6 +972,13 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
       a.pf_k = static_cast<const uint8_t*>(fu->pf_k_pages); a.pf_v = static_cast<const uint8_t*>(fu->pf_v_pages);
       a.pf_table = fu->pf_page_table; a.pf_len = fu->pf_kv_len; a.pf_B = fu->pf_B; a.pf_max_pages = fu->pf_max_pages;
       a.pf_page_bytes = fu->pf_page_bytes;
+    }
+    if (fu->stats != nullptr) {
+      // plain fp32 logits + bias only (no residual, no in-kernel norm factor), one CTA per output tile
+      if (mode != PG_EPI_F32 || resid != nullptr || bf32 || split_k != 1 || fu->stats_ld < 4ll * ((features + BM - 1) / BM) ||
+          (reinterpret_cast<uintptr_t>(fu->stats) & 7) || !(fu->stat_c > 0.f))
+        return PG_ERR_ARG;
+      a.stats = static_cast<float2*>(fu->stats); a.stats_ld = fu->stats_ld; a.stat_c = fu->stat_c;
     }
   }
   a.n_fast = 0;

@@ -5,7 +5,6 @@
 // whose bins accumulate probability MASS); the token is then drawn by inverse CDF over the kept set in vocabulary order
 // with a counter-based RNG.  One CTA per row; the row (1 MB at V = 257 216) stays L2 resident across the passes.
 #include <cooperative_groups.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "paligemma_b200.h"
@@ -621,7 +620,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_rej_kernel(const float* __r
   const int step = step_ptr ? *step_ptr : 0;
   const uint64_t base_rnd = splitmix64(seed ^ splitmix64((static_cast<uint64_t>(step) << 32) | static_cast<uint32_t>(row_idx)));
 
-  for (int round = 0; round < 64; ++round) {
+  for (int round = 0; round < 16; ++round) {
     // ---- draw four candidates from the full distribution (inverse CDF over the segment masses, same in every rank) ----
     if (tid < 4) {
       const uint64_t rnd = splitmix64(base_rnd + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(4 * round + tid + 1));
@@ -721,8 +720,281 @@ __global__ void __launch_bounds__(1024) sample_top_p_rej_kernel(const float* __r
     cluster.sync();  // every rank has read the published masses / candidates before the next round overwrites them
     if (acc_k >= 0) {
       if (tid == 0 && rank == 0) out[row_idx] = S.cand_i[acc_k];
-      break;
+      return;
     }
+  }
+  // ---- every candidate of every round rejected (tiny top_p on a flat row): emit the most probable token, which is always
+  //      in the kept set (nothing lies above it); lowest index among exact ties ----
+  int first = 0x7fffffff;
+  for_each_in_segment(row, seg_lo, seg_hi, vec, lane, [&](float x, int i) { if (x == mx) first = min(first, i); });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  if (tid == 0) S.accepted = 0x7fffffff;
+  __syncthreads();
+  if (lane == 0) atomicMin(&S.accepted, first);
+  cluster.sync();
+  if (tid == 0 && rank == 0) {
+    int best = 0x7fffffff;
+    for (int r = 0; r < R; ++r) best = min(best, *remote(&S.accepted, r));
+    out[row_idx] = best == 0x7fffffff ? 0 : best;
+  }
+  cluster.sync();  // no rank leaves while its shared memory may still be read
+}
+
+
+// -------------------------------------------------------------------------------------------------------------------
+// Samplers fed by the lm_head epilogue's segment statistics (gemm_tcgen05.cu: swap_tile_epilogue_f32_stats): for every
+// 32-token vocabulary segment g of a row, stats[g] = (m_g, s_g) = (max logit, sum exp2((x - m_g) * c)), c = inv_temp * log2 e.
+// Row maximum M = max m_g, segment mass w_g = s_g * exp2((m_g - M) * c), partition function Z = sum w_g: the first two of
+// the three passes of the rejection sampler above now read 64 KB of statistics instead of the 1 MB logit row; only the
+// verification pass (mass of strictly more probable tokens, inference.py:96-100) still walks the row.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int kStatMaxPer = 8;  // segments per thread (host: nseg <= kStatMaxPer * R * 1024)
+
+struct StatShared {
+  BlockRed red;
+  float wmass[32];      // this CTA's per-warp masses (read remotely)
+  float all_w[256];     // every warp of the row (cluster), vocabulary order
+  float cta_max;        // published
+  float cand_x[4];      // candidate logits (written by the owning warp into EVERY rank)
+  int cand_i[4];
+  float mass[4];        // this CTA's mass strictly above each candidate (published)
+  float target[4], toff[4];
+  int twarp[4];
+  float z;
+  int accepted;
+  int max_seg;          // lowest segment holding the row maximum (fallback: the most probable token is always kept)
+};
+
+__global__ void __launch_bounds__(1024) sample_top_p_stats_kernel(const float* __restrict__ logits, long long ld,
+                                                                  const float2* __restrict__ stats, long long stats_ld, int nseg,
+                                                                  int* __restrict__ out, int V, float inv_temp, float top_p,
+                                                                  unsigned long long seed, const unsigned long long* __restrict__ seed_ptr,
+                                                                  const int* __restrict__ step_ptr) {
+  __shared__ StatShared S;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int R = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int row_idx = blockIdx.x / R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ row = logits + row_idx * ld;
+  const float2* __restrict__ st = stats + row_idx * stats_ld;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  auto remote = [&](auto* ptr, int r) { return cluster.map_shared_rank(ptr, r); };
+  const float c = inv_temp * 1.4426950408889634f;
+
+  // ---- this thread's contiguous run of segments (threads in cluster order = vocabulary order) ----
+  const int gt = rank * 1024 + tid;
+  const int per = (nseg + R * 1024 - 1) / (R * 1024);
+  const int s_lo = min(nseg, gt * per), s_hi = min(nseg, s_lo + per);
+  float2 my[kStatMaxPer];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kStatMaxPer; ++k) {
+    my[k] = (k < per && s_lo + k < s_hi) ? __ldcg(st + s_lo + k) : make_float2(-INFINITY, 0.f);
+    if (my[k].y > 0.f) mx = fmaxf(mx, my[k].x);
+  }
+  if (tid == 0) { S.accepted = -1; S.max_seg = 0x7fffffff; }
+  {
+    const float t = block_reduce_max(mx, S.red);
+    if (tid == 0) S.cta_max = t;
+    cluster.sync();
+    float acc = -INFINITY;
+    for (int r = 0; r < R; ++r) acc = fmaxf(acc, *remote(&S.cta_max, r));
+    mx = acc;
+  }
+  const float cm = mx * c;
+  auto w_of = [&](float x) { return exp2f(fmaf(x, c, -cm)); };  // ONE expression for every element-level weight
+  float wk[kStatMaxPer];
+  float tm = 0.f;
+#pragma unroll
+  for (int k = 0; k < kStatMaxPer; ++k) {
+    wk[k] = my[k].y > 0.f ? my[k].y * exp2f((my[k].x - mx) * c) : 0.f;
+    tm += wk[k];
+    if (my[k].y > 0.f && my[k].x == mx) atomicMin(&S.max_seg, s_lo + k);
+  }
+  {
+    float m = tm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0) S.wmass[warp] = m;
+  }
+  cluster.sync();
+  const int nwarp = R * 32;
+  if (tid < nwarp) S.all_w[tid] = remote(S.wmass, tid >> 5)[tid & 31];
+  __syncthreads();
+  if (tid == 0) {
+    float z = 0.f;
+    for (int w = 0; w < nwarp; ++w) z += S.all_w[w];
+    S.z = z;
+  }
+  __syncthreads();
+  const float Z = S.z;
+  const int step = step_ptr ? *step_ptr : 0;
+  const unsigned long long sd = seed_ptr ? *seed_ptr : seed;
+  const uint64_t base_rnd = splitmix64(sd ^ splitmix64((static_cast<uint64_t>(step) << 32) | static_cast<uint32_t>(row_idx)));
+
+  // the verification pass walks the row in per-warp element ranges (same split as the rejection kernel above)
+  const bool vec = ((V & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int seg_len = ((V + nwarp - 1) / nwarp + 127) / 128 * 128;
+  const int e_lo = min(V, (rank * 32 + warp) * seg_len), e_hi = min(V, e_lo + seg_len);
+
+  int acc_k = -1;
+  for (int round = 0; round < 16 && acc_k < 0; ++round) {
+    // ---- four candidates from the full distribution: warp by inverse CDF over the warp masses (same in every rank) ----
+    if (tid < 4) {
+      const uint64_t rnd = splitmix64(base_rnd + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(4 * round + tid + 1));
+      const float u01 = (static_cast<float>(rnd >> 40) + 0.5f) * (1.0f / 16777216.0f);
+      const float target = u01 * Z;
+      int tw = -1, last_nonempty = -1;
+      float toff = 0.f, last_off = 0.f, acc = 0.f;
+      for (int w = 0; w < nwarp; ++w) {
+        const float v = S.all_w[w];
+        if (v > 0.f) { last_nonempty = w; last_off = acc; }
+        if (tw < 0 && v > 0.f && target < acc + v) { tw = w; toff = acc; }
+        acc += v;
+      }
+      if (tw < 0) { tw = last_nonempty; toff = last_off; }
+      S.twarp[tid] = tw;
+      S.toff[tid] = toff;
+      S.target[tid] = target;
+    }
+    __syncthreads();
+    // ---- the owning warp: lane by prefix of the thread masses, segment inside the lane's run, token inside the segment ----
+    for (int k = 0; k < 4; ++k) {
+      if (S.twarp[k] != rank * 32 + warp) continue;  // warp-uniform
+      const float target = S.target[k];
+      float inc = tm;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const float before = S.toff[k] + inc - tm;
+      const uint32_t hits = __ballot_sync(0xffffffffu, tm > 0.f && target < before + tm);
+      const uint32_t has = __ballot_sync(0xffffffffu, tm > 0.f);
+      const int hl = hits ? __ffs(hits) - 1 : (has ? 31 - __clz(has) : 0);
+      int sseg = s_lo;
+      float soff = before;
+      if (lane == hl) {
+        float a = before;
+        int pick = -1, lastk = 0;
+        float lastoff = before;
+#pragma unroll
+        for (int kk = 0; kk < kStatMaxPer; ++kk) {
+          if (wk[kk] > 0.f) {
+            lastk = kk; lastoff = a;
+            if (pick < 0 && target < a + wk[kk]) { pick = kk; soff = a; }
+            a += wk[kk];
+          }
+        }
+        if (pick < 0) { pick = lastk; soff = lastoff; }
+        sseg = s_lo + pick;
+      }
+      sseg = __shfl_sync(0xffffffffu, sseg, hl);
+      soff = __shfl_sync(0xffffffffu, soff, hl);
+      const int idx = sseg * 32 + lane;
+      const bool ok = idx < V;
+      const float x = ok ? __ldcg(row + idx) : -INFINITY;
+      const float w = ok ? w_of(x) : 0.f;
+      float winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      const uint32_t ehits = __ballot_sync(0xffffffffu, ok && w > 0.f && target < soff + winc);
+      const uint32_t ehas = __ballot_sync(0xffffffffu, ok && w > 0.f);
+      const uint32_t eany = __ballot_sync(0xffffffffu, ok);
+      const int el = ehits ? __ffs(ehits) - 1 : (ehas ? 31 - __clz(ehas) : (eany ? 31 - __clz(eany) : 0));
+      const float fx = __shfl_sync(0xffffffffu, x, el);
+      if (lane < R) {
+        *remote(&S.cand_x[k], lane) = fx;
+        *remote(&S.cand_i[k], lane) = min(V - 1, sseg * 32 + el);
+      }
+    }
+    cluster.sync();
+    // ---- mass strictly above each candidate ----
+    const float cx0 = S.cand_x[0], cx1 = S.cand_x[1], cx2 = S.cand_x[2], cx3 = S.cand_x[3];
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for_each_in_segment(row, e_lo, e_hi, vec, lane, [&](float x, int) {
+      const float w = w_of(x);
+      m0 += x > cx0 ? w : 0.f;
+      m1 += x > cx1 ? w : 0.f;
+      m2 += x > cx2 ? w : 0.f;
+      m3 += x > cx3 ? w : 0.f;
+    });
+    {
+      const float t0 = block_reduce_sum(m0, S.red), t1 = block_reduce_sum(m1, S.red);
+      const float t2 = block_reduce_sum(m2, S.red), t3 = block_reduce_sum(m3, S.red);
+      if (tid == 0) { S.mass[0] = t0; S.mass[1] = t1; S.mass[2] = t2; S.mass[3] = t3; }
+    }
+    cluster.sync();
+    if (tid == 0) {
+      int a = -1;
+      for (int k = 0; k < 4 && a < 0; ++k) {
+        float above = 0.f;
+        for (int r = 0; r < R; ++r) above += remote(S.mass, r)[k];
+        if (above <= top_p * Z) a = k;  // (the most probable token always passes: nothing lies above it)
+      }
+      S.accepted = a;
+    }
+    __syncthreads();
+    acc_k = S.accepted;
+    cluster.sync();  // every rank has read the published masses / candidates before the next round overwrites them
+  }
+  if (acc_k >= 0) {
+    if (tid == 0 && rank == 0) out[row_idx] = S.cand_i[acc_k];
+    return;
+  }
+  // ---- every candidate of every round rejected (tiny top_p on a flat row): the most probable token, which is always in
+  //      the kept set; lowest index among exact ties ----
+  int ms = 0x7fffffff;
+  for (int r = 0; r < R; ++r) ms = min(ms, *remote(&S.max_seg, r));
+  cluster.sync();  // no rank leaves while its shared memory may still be read
+  if (rank == 0 && warp == 0) {
+    const int idx = ms * 32 + lane;
+    const bool hit = ms != 0x7fffffff && idx < V && __ldcg(row + idx) == mx;
+    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) out[row_idx] = b ? ms * 32 + __ffs(b) - 1 : 0;
+  }
+}
+
+// Greedy argmax (inference.py:67-68) from the segment statistics: lowest segment holding the maximum, then the first of its
+// 32 logits equal to it (ties -> lowest index, as torch.argmax over the row).
+__global__ void __launch_bounds__(256) argmax_stats_kernel(const float* __restrict__ logits, long long ld,
+                                                           const float2* __restrict__ stats, long long stats_ld, int nseg,
+                                                           int* __restrict__ out, int V) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* __restrict__ row = logits + blockIdx.x * ld;
+  const float2* __restrict__ st = stats + blockIdx.x * stats_ld;
+  griddep_wait();
+  if (threadIdx.x == 0) griddep_launch_dependents();
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int g = threadIdx.x; g < nseg; g += 256) {
+    const float2 v = __ldcg(st + g);
+    if (v.y > 0.f && (v.x > best || (v.x == best && g < bi))) { best = v.x; bi = g; }
+  }
+  auto merge = [&](float ov, int oi) { if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; } };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) merge(__shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < 8 ? sv[lane] : -INFINITY;
+    bi = lane < 8 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) merge(__shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    best = __shfl_sync(0xffffffffu, best, 0);
+    bi = __shfl_sync(0xffffffffu, bi, 0);
+    const int idx = bi * 32 + lane;
+    const bool hit = bi != 0x7fffffff && idx < V && __ldcg(row + idx) == best;
+    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) out[blockIdx.x] = b ? bi * 32 + __ffs(b) - 1 : 0;
   }
 }
 
@@ -757,8 +1029,7 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
   // cluster of R CTAs per row: enough CTAs to cover the GPU when the batch alone cannot
   int R = 1;
   if (V >= 65536) R = 2;  // (64 regs x 1024 threads = one CTA per SM: 2 x 64 rows covers 128 of the 148 SMs)
-  static const bool force_hist = getenv("PG_TOPP_HIST") != nullptr;  // A/B switch: the histogram-select kernel
-  const bool rejection = kept_count == nullptr && !force_hist && top_p > 0.f;
+  const bool rejection = kept_count == nullptr && top_p > 0.f;  // the histogram-select kernel reports the kept-set size
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(B) * R);
   cfg.blockDim = dim3(1024);
@@ -781,4 +1052,39 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
                  cudaSuccess
              ? PG_OK
              : PG_ERR_CUDA;
+}
+
+extern "C" int pg_argmax_stats(const float* logits, long long ld, const void* stats, long long stats_ld, int* out, int B, int V,
+                               void* stream) {
+  if (B <= 0 || V <= 0 || stats == nullptr || stats_ld < (V + 31) / 32) return PG_ERR_ARG;
+  return launch_kernel(argmax_stats_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), logits, ld,
+                       static_cast<const float2*>(stats), stats_ld, (V + 31) / 32, out, V) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+}
+
+extern "C" int pg_sample_top_p_stats(const float* logits, long long ld, const void* stats, long long stats_ld, int* out, int B,
+                                     int V, float inv_temperature, float top_p, unsigned long long seed,
+                                     const unsigned long long* seed_ptr, const int* step_ptr, void* stream) {
+  if (B <= 0 || V <= 0 || !(inv_temperature > 0.f) || !(top_p >= 0.f) || stats == nullptr) return PG_ERR_ARG;
+  const int nseg = (V + 31) / 32;
+  if (stats_ld < nseg) return PG_ERR_ARG;
+  int R = V >= 65536 ? 2 : 1;
+  while (nseg > kStatMaxPer * R * 1024 && R < 8) R *= 2;
+  if (nseg > kStatMaxPer * R * 1024) return PG_ERR_ARG;  // > 2 M-token vocabularies: use pg_sample_top_p
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * R);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pg_pdl_enabled() ? 2 : 1;
+  pg_count_launch(1);
+  return cudaLaunchKernelEx(&cfg, sample_top_p_stats_kernel, logits, ld, static_cast<const float2*>(stats), stats_ld, nseg, out, V,
+                            inv_temperature, top_p, seed, seed_ptr, step_ptr) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }

@@ -355,7 +355,9 @@ class GemmaForCausalLM(nn.Module):
                              f"UMMA N axis (<= {MAX_DECODE_BATCH} rows per step); shard the requests over more GPUs / batchers")
         D, F, Hq, Hkv, dh, V = c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim, c.vocab_size
         shapes = dict(h=((B, D), torch.float32), hn=((B, D), torch.bfloat16), qkv=((B, (Hq + 2 * Hkv) * dh), torch.float32),
-                      att=((B, Hq * dh), torch.bfloat16), mid=((B, F), torch.bfloat16), logits=((B, V), torch.float32))
+                      att=((B, Hq * dh), torch.bfloat16), mid=((B, F), torch.bfloat16), logits=((B, V), torch.float32),
+                      # lm_head epilogue: (max, sum exp2) of every 32-token vocabulary segment, read by the samplers
+                      stats=((B, 4 * ((V + 127) // 128), 2), torch.float32))
 
         def make(shp, dt, name):
             return (torch.zeros if name == "qkv" else torch.empty)(*shp, device="cuda", dtype=dt)
@@ -372,7 +374,7 @@ class GemmaForCausalLM(nn.Module):
         return out
 
     @torch.no_grad()
-    def decode_layers(self, bufs, kv_cache: KVCache, B):
+    def decode_layers(self, bufs, kv_cache: KVCache, B, inv_temperature: float = 1.0):
         """One decode step over all layers (modeling_gemma.py:385-418 at q_len == 1); reads bufs['h'] (fp32 embeddings),
         leaves fp32 logits in bufs['logits'].  FIVE launches per layer:
           1. q/k/v projection, split-K red.add into the zeroed fp32 `qkv`; its activation operand is built in the kernel
@@ -383,6 +385,8 @@ class GemmaForCausalLM(nn.Module):
           4. gate||up with GeGLU epilogue; operand from the residual stream (post_attention_layernorm), the per-token
              factor computed in the kernel and applied in the epilogue;
           5. down_proj, split-K red.add into the residual stream.
+        Then the final RMSNorm and the lm_head (modeling_gemma.py:523-525), whose epilogue also leaves the softmax statistics
+        of every 32-token vocabulary segment at `inv_temperature` in bufs['stats'] (pg_sample_top_p_stats / pg_argmax_stats).
         Every launch reads its sizes from device counters, so the sequence can be captured in a CUDA graph."""
         c = self.text_config
         pk = self._packed or self.pack()
@@ -413,11 +417,12 @@ class GemmaForCausalLM(nn.Module):
             _lib.gemm_fused(lw["gu_w"], mid, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=lw["ln2"], apply_rstd=True, eps=eps)
             _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
         _lib.rmsnorm(h, pk["norm_w"], hn, eps=eps)
-        _lib.gemm(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], swap=1)
+        _lib.gemm_fused(pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, x=hn, bias=pk["head_b"], stats=bufs["stats"],
+                        inv_temperature=inv_temperature)
         return bufs["logits"]
 
     @torch.no_grad()
-    def decode_step(self, bufs, kv_cache: KVCache, B, tokens_i32, img, img_scale, pad_token, image_token):
+    def decode_step(self, bufs, kv_cache: KVCache, B, tokens_i32, img, img_scale, pad_token, image_token, inv_temperature=1.0):
         """Embeds `tokens_i32` [B] and runs every layer + final norm + lm_head; fp32 logits land in bufs['logits']."""
         c = self.text_config
         pk = self._packed or self.pack()
@@ -425,7 +430,7 @@ class GemmaForCausalLM(nn.Module):
         _lib.check(_lib.lib().pg_embed_tokens(tokens_i32.data_ptr(), pk["embed"].data_ptr(), _lib.ptr(img), bufs["h"].data_ptr(), B, D,
                                               0 if img is None else img.shape[1], D ** 0.5, img_scale, pad_token, image_token,
                                               _lib.stream()), "pg_embed_tokens")
-        return self.decode_layers(bufs, kv_cache, B)
+        return self.decode_layers(bufs, kv_cache, B, inv_temperature)
 
     def forward(self, input_embeds=None, position_ids=None, attention_mask=None, kv_cache=None):
         """Reference signature (modeling_gemma.py:501-533): input_embeds [B,S,D] UNSCALED (the sqrt(D) normaliser is

@@ -137,11 +137,29 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         return h, pos
 
     @torch.no_grad()
-    def _decode_step(self, tokens_i32, kv_cache, bufs, B):
+    def _decode_step(self, tokens_i32, kv_cache, bufs, B, inv_temperature=1.0):
         D = self.text_config.hidden_size
         return self.language_model.decode_step(bufs, kv_cache, B, tokens_i32, kv_cache.image_feats,
                                                (self.config.projection_dim ** -0.5) * (D ** 0.5), self.pad_token_id,
-                                               self.dummy_image_token_id)
+                                               self.dummy_image_token_id, inv_temperature)
+
+    def _sample(self, logits, out_i32, B, do_sample, inv_t, top_p, seed, step, stats=None, seed_dev=None):
+        """Next token of every row (inference.py:63-68): greedy argmax or temperature + top-p.  `stats` = the lm_head
+        epilogue's segment statistics of these logits at the same inverse temperature (decode steps), else the samplers
+        make their own passes over the row (prefill logits)."""
+        L, V = _lib.lib(), self.text_config.vocab_size
+        if do_sample and stats is not None:
+            _lib.check(L.pg_sample_top_p_stats(logits.data_ptr(), logits.stride(0), stats.data_ptr(), stats.shape[1], out_i32.data_ptr(),
+                                               B, V, inv_t, float(top_p), int(seed), _lib.ptr(seed_dev), _lib.ptr(step), _lib.stream()),
+                       "pg_sample_top_p_stats")
+        elif do_sample:
+            _lib.check(L.pg_sample_top_p(logits.data_ptr(), logits.stride(0), out_i32.data_ptr(), 0, B, V, inv_t, float(top_p), int(seed),
+                                         _lib.ptr(step), _lib.stream()), "pg_sample_top_p")
+        elif stats is not None:
+            _lib.check(L.pg_argmax_stats(logits.data_ptr(), logits.stride(0), stats.data_ptr(), stats.shape[1], out_i32.data_ptr(), B, V,
+                                         _lib.stream()), "pg_argmax_stats")
+        else:
+            _lib.check(L.pg_argmax(logits.data_ptr(), logits.stride(0), out_i32.data_ptr(), B, V, _lib.stream()), "pg_argmax")
 
     # -- reference forward ---------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -188,6 +206,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             kv.allocate(B, c.num_hidden_layers, c.num_key_value_heads, c.head_dim, S + T + 1)
             stt = dict(kv=kv, nxt=torch.empty(B, device=dev, dtype=torch.int32), cur=torch.empty(B, device=dev, dtype=torch.int32),
                        hist=torch.zeros(T, B, device=dev, dtype=torch.int32), step=torch.zeros(1, device=dev, dtype=torch.int32),
+                       seed=torch.zeros(1, device=dev, dtype=torch.int64),
                        img=torch.empty(B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32), graph=None, graph_k=None)
             if len(self._graphs) >= 4:  # bound the number of cached geometries (each owns a KV cache)
                 self._graphs.pop(next(iter(self._graphs)))
@@ -258,7 +277,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         T = int(max_tokens_to_generate)
         V = c.vocab_size
         dev = torch.device("cuda")
-        key = (B, S, T, bool(do_sample), float(temperature), float(top_p), int(seed))
+        key = (B, S, T, bool(do_sample), float(temperature), float(top_p))  # (the seed lives in device memory)
         stt = self._gen_state(key, B, S, T, V)
         kv, nxt, cur, hist, step = stt["kv"], stt["nxt"], stt["cur"], stt["hist"], stt["step"]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timings is not None else None
@@ -297,24 +316,21 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             kv.counters[1].copy_(lens)
             kv.counters[2].copy_(lens + 1)
         step.zero_()
-        inv_t = 1.0 / float(temperature)
+        inv_t = 1.0 / float(temperature) if do_sample else 1.0
+        stt["seed"].fill_(int(seed))
 
-        def sample(lg):
-            if do_sample:
-                _lib.check(L.pg_sample_top_p(lg.data_ptr(), V, nxt.data_ptr(), 0, B, V, inv_t, float(top_p), int(seed),
-                                             step.data_ptr(), _lib.stream()), "pg_sample_top_p")
-            else:
-                _lib.check(L.pg_argmax(lg.data_ptr(), V, nxt.data_ptr(), B, V, _lib.stream()), "pg_argmax")
+        def sample(lg, stats=None):
+            self._sample(lg, nxt, B, do_sample, inv_t, top_p, seed, step, stats=stats, seed_dev=stt["seed"])
 
         def advance(n_counters):
             _lib.check(L.pg_advance_decode(nxt.data_ptr(), hist.data_ptr(), cur.data_ptr(), kv.counters.data_ptr(), n_counters,
                                            step.data_ptr(), B, _lib.stream()), "pg_advance_decode")
 
         def decode_step(t=None):
-            lg = self._decode_step(cur, kv, bufs, B)
+            lg = self._decode_step(cur, kv, bufs, B, inv_t)
             if t is not None and return_logits:
                 logit_log[t].copy_(lg)
-            sample(lg)
+            sample(lg, bufs["stats"])
             advance(3)
             if t is not None and forced is not None:
                 cur.copy_(forced[t])

@@ -236,13 +236,8 @@ class ContinuousBatcher:
         self.limit.index_copy_(0, s, one)               # kv_len == limit: frozen
         self.cur.index_fill_(0, s, 0)
 
-    def _sample(self, logits, out, rows, seed):
-        L, V = _lib.lib(), self.c.vocab_size
-        if self.do_sample:
-            _lib.check(L.pg_sample_top_p(logits.data_ptr(), V, out.data_ptr(), 0, rows, V, self.inv_t, self.top_p, seed,
-                                         self.step.data_ptr(), _lib.stream()), "pg_sample_top_p")
-        else:
-            _lib.check(L.pg_argmax(logits.data_ptr(), V, out.data_ptr(), rows, V, _lib.stream()), "pg_argmax")
+    def _sample(self, logits, out, rows, seed, stats=None):
+        self.model._sample(logits, out, rows, self.do_sample, self.inv_t, self.top_p, seed, self.step, stats=stats)
 
     def _prefill(self, reqs: List[Request]):
         """One ragged prefill: keys/values of request i land in its page set, its first token is sampled."""
@@ -301,8 +296,8 @@ class ContinuousBatcher:
         return fin
 
     def _step(self):
-        lg = self.model._decode_step(self.cur, self.kv, self.bufs, self.B)
-        self._sample(lg, self.nxt, self.B, self.seed)
+        lg = self.model._decode_step(self.cur, self.kv, self.bufs, self.B, self.inv_t if self.do_sample else 1.0)
+        self._sample(lg, self.nxt, self.B, self.seed, stats=self.bufs["stats"])
         _lib.check(_lib.lib().pg_advance_decode_slots(self.nxt.data_ptr(), self.ring.data_ptr(), self.GK, self.cur.data_ptr(),
                                                       self.kv.counters.data_ptr(), self.limit.data_ptr(), self.step.data_ptr(),
                                                       self.B, _lib.stream()), "pg_advance_decode_slots")
