@@ -71,10 +71,6 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
  *    from the same rows).  Replaces the standalone RMSNorm launch and its bf16 round trip.
  *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; used to reset the
  *    split-K accumulator that a later kernel of the chain red.adds into.
- *  - pf_*: L2 prefetch (cp.async.bulk.prefetch.L2) of the K and V pages [0, ceil(pf_kv_len[b] / 64)) of every sequence b,
- *    pages located through pf_page_table [pf_B, pf_max_pages]; pf_page_bytes = 64 * Hkv * dh * 2.  Issued before the
- *    dependency wait, so the attention kernel that follows finds its cache rows in L2 (KVCache reads of
- *    modeling_gemma.py:49-57 / 307-339 overlapped with the projection that precedes them).
  *  - stats (PG_EPI_F32 only, no resid / x_f32 / split-K): the lm_head of a decode step (modeling_gemma.py:523-525) also emits,
  *    for every token t and every 32-row vocabulary segment g (g = f / 32), stats[t * stats_ld + g] = (m, s) with
  *    m = max logit of the segment and s = sum exp2((logit - m) * stat_c), stat_c = inv_temperature * log2(e) -- temperature
@@ -89,12 +85,6 @@ typedef struct PgGemmFusion {
   float eps;
   float* zero_buf;
   long long zero_count;
-  const void* pf_k_pages;
-  const void* pf_v_pages;
-  const int* pf_page_table;
-  const int* pf_kv_len;
-  int pf_B, pf_max_pages;
-  long long pf_page_bytes;
   void* stats;
   long long stats_ld;
   float stat_c;

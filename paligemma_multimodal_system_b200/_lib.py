@@ -64,8 +64,6 @@ class GemmFusion(C.Structure):
     _fields_ = [
         ("x_f32", p), ("ldx_f32", i64), ("norm_w", p), ("apply_rstd", i32), ("eps", f32),
         ("zero_buf", p), ("zero_count", i64),
-        ("pf_k_pages", p), ("pf_v_pages", p), ("pf_page_table", p), ("pf_kv_len", p), ("pf_B", i32), ("pf_max_pages", i32),
-        ("pf_page_bytes", i64),
         ("stats", p), ("stats_ld", i64), ("stat_c", f32),
     ]
 
@@ -138,14 +136,12 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
 LOG2E = 1.4426950408889634
 
 
-def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=False, eps=1e-6, zero_buf=None, kv_prefetch=None,
-               bias=None, split_k=1, stats=None, inv_temperature=1.0):
+def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=False, eps=1e-6, zero_buf=None, bias=None, split_k=1, stats=None, inv_temperature=1.0):
     """Decode-step (swap-AB, tokens <= 128) GEMM with the fusions of pg_gemm_bf16_fused:
       x_f32 / norm_w   activation operand built in the kernel from the fp32 residual rows, bf16(x * (1 + norm_w)) -- the
                        GemmaRMSNorm that precedes the projection, minus its per-token factor (apply_rstd: applied in the
                        epilogue; otherwise the consumer applies it);
       zero_buf         fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
-      kv_prefetch      (k_pages_layer, v_pages_layer, page_table, kv_len) whose live pages are pulled into L2;
       stats            fp32 [T, nseg, 2] (nseg >= 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
                        `inv_temperature`, for pg_sample_top_p_stats / pg_argmax_stats (mode EPI_F32 only)."""
     assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
@@ -163,11 +159,6 @@ def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=Fals
     if zero_buf is not None:
         assert zero_buf.dtype == torch.float32 and zero_buf.is_contiguous()
         fu.zero_buf, fu.zero_count = zero_buf.data_ptr(), zero_buf.numel()
-    if kv_prefetch is not None:
-        kp, vp, table, kv_len = kv_prefetch
-        fu.pf_k_pages, fu.pf_v_pages, fu.pf_page_table, fu.pf_kv_len = kp.data_ptr(), vp.data_ptr(), table.data_ptr(), kv_len.data_ptr()
-        fu.pf_B, fu.pf_max_pages = table.shape
-        fu.pf_page_bytes = kp.stride(0) * kp.element_size()
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[2] == 2 and stats.is_contiguous()
         fu.stats, fu.stats_ld, fu.stat_c = stats.data_ptr(), stats.shape[1], float(inv_temperature) * LOG2E

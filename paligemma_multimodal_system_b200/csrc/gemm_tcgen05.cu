@@ -75,14 +75,6 @@ struct GemmArgs {
   // ---- decode-step chores of the SWAP kernels ----
   float* zero_buf;  // zero-filled after the dependency wait (the split-K accumulator of a LATER kernel of the chain)
   long long zero_count;
-  // L2 prefetch of the paged KV cache rows the attention kernel two launches ahead will stream (issued before the
-  // dependency wait: pages of earlier positions, the page table and kv_len were written before this kernel could start)
-  const uint8_t* pf_k;
-  const uint8_t* pf_v;
-  const int* pf_table;
-  const int* pf_len;
-  int pf_B, pf_max_pages;
-  long long pf_page_bytes;
   // lm_head (PG_EPI_F32, swap): softmax statistics of every 32-row vocabulary segment, for the sampler that follows
   float2* stats;       // [tokens][stats_ld]: (max logit of the segment, sum exp2((x - max) * stat_c))
   long long stats_ld;  // segments per token row (>= 4 * ceil(features / 128))
@@ -512,6 +504,10 @@ struct BTileConverter {
   static constexpr int NT = NEPI * 32;
   static constexpr int ITEMS = BN * 4;
   static constexpr int PER = (ITEMS + NT - 1) / NT;
+  // k-blocks whose loads are in flight per thread (16 registers each per item): one L2 round trip (~1 us under load) has
+  // to cover DEPTH k-blocks, or the converters, not the weight stream, pace the main loop (measured with DEPTH = 1:
+  // gate||up 22 -> 48 us, qkv 5.5 -> 9.0 us)
+  static constexpr int DEPTH = PER >= 4 ? 1 : 4 / PER;
 
   PG_DEVINL static void load(const GemmArgs& args, int j_base, int kb, int et, float4 (&v)[PER][4]) {
 #pragma unroll
@@ -556,7 +552,7 @@ struct BTileConverter {
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
 // red.add epilogue is compiled out, which keeps the 320-thread CTA at two per SM.
 template <int BN, bool SWAP, bool SPLITK = false, bool BF32 = false>
-__global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
+__global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, (two_per_sm(BN, SWAP) && !BF32) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
   static_assert(!BF32 || SWAP, "the in-kernel fp32 -> bf16 operand conversion exists for the decode (swap-AB) kernels");
@@ -700,27 +696,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     // =================================== epilogue warps =================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - 2) * 32 + lane;
-    if constexpr (SWAP) {
-      if (args.pf_k != nullptr) {
-        // chunks of <= 16 KB: (sequence b, page j, K|V, piece); CTAs interleave so that every SM issues a few
-        constexpr long long CH = 16384;
-        const int cpp = static_cast<int>((args.pf_page_bytes + CH - 1) / CH);
-        const long long total = static_cast<long long>(args.pf_B) * args.pf_max_pages * 2 * cpp;
-        for (long long c = blockIdx.x + static_cast<long long>(gridDim.x) * et; c < total; c += static_cast<long long>(gridDim.x) * (NEPI * 32)) {
-          const int sub = static_cast<int>(c % cpp);
-          long long r = c / cpp;
-          const int kv = static_cast<int>(r & 1);
-          r >>= 1;
-          const int j = static_cast<int>(r % args.pf_max_pages), b = static_cast<int>(r / args.pf_max_pages);
-          if (j * 64 < __ldg(args.pf_len + b)) {
-            const long long page = __ldg(args.pf_table + static_cast<long long>(b) * args.pf_max_pages + j);
-            const long long off = sub * CH;
-            const long long nbytes = min(CH, args.pf_page_bytes - off) & ~15ll;
-            if (nbytes > 0) prefetch_l2_bulk((kv ? args.pf_v : args.pf_k) + page * args.pf_page_bytes + off, static_cast<uint32_t>(nbytes));
-          }
-        }
-      }
-    }
     griddep_wait();          // outputs / residual / bias / fp32 activations may depend on the previous kernel
     if constexpr (SWAP) {
       if (args.zero_buf != nullptr) {
@@ -742,25 +717,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const float* rs_tab = nullptr;  // per-token epilogue factors (x args.scale) in shared memory
       if constexpr (BF32) {
         using Conv = BTileConverter<BN, NEPI>;
-        float4 cur[Conv::PER][4], nxt[Conv::PER][4];
+        constexpr int DEPTH = Conv::DEPTH;
+        float4 ring[DEPTH][Conv::PER][4];  // register ring: the loads of DEPTH k-blocks are in flight
         float ssq[Conv::PER];
 #pragma unroll
         for (int j = 0; j < Conv::PER; ++j) ssq[j] = 0.f;
         const int j_base = t.n_blk * BN;
-        Conv::load(args, j_base, t.kb0, et, cur);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+          if (t.kb0 + d < t.kb1) Conv::load(args, j_base, t.kb0 + d, et, ring[d]);
 #pragma unroll 1
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          if (kb + 1 < t.kb1) Conv::load(args, j_base, kb + 1, et, nxt);
-          mbar_wait(empty_bar(cstage), cphase ^ 1);  // the MMAs that read this slot's previous tile have completed
-          Conv::store(args, smem_base + cstage * STAGE_BYTES + A_TILE_BYTES, kb, et, cur, ssq);
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar(cstage));
-          if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
+        for (int kb = t.kb0; kb < t.kb1; kb += DEPTH) {
 #pragma unroll
-          for (int j = 0; j < Conv::PER; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
+          for (int d = 0; d < DEPTH; ++d) {
+            if (kb + d < t.kb1) {  // warp-uniform
+              mbar_wait(empty_bar(cstage), cphase ^ 1);  // the MMAs that read this slot's previous tile have completed
+              Conv::store(args, smem_base + cstage * STAGE_BYTES + A_TILE_BYTES, kb + d, et, ring[d], ssq);
+              fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+              __syncwarp();
+              if (lane == 0) mbar_arrive(full_bar(cstage));
+              if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
+              if (kb + d + DEPTH < t.kb1) Conv::load(args, j_base, kb + d + DEPTH, et, ring[d]);
+            }
+          }
         }
         if (args.apply_rstd) {  // (host: split_k == 1, so this CTA has seen every column of its tokens)
           float* tab = xch + 64 * BN;  // BN floats after the exchange area
@@ -963,15 +942,6 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
     if (fu->zero_count > 0) {
       if (fu->zero_buf == nullptr || (fu->zero_count % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->zero_buf) & 15)) return PG_ERR_ARG;
       a.zero_buf = fu->zero_buf; a.zero_count = fu->zero_count;
-    }
-    if (fu->pf_k_pages != nullptr) {
-      if (fu->pf_v_pages == nullptr || fu->pf_page_table == nullptr || fu->pf_kv_len == nullptr || fu->pf_B <= 0 ||
-          fu->pf_max_pages <= 0 || fu->pf_page_bytes <= 0 || (fu->pf_page_bytes % 16) != 0 ||
-          (reinterpret_cast<uintptr_t>(fu->pf_k_pages) & 15) || (reinterpret_cast<uintptr_t>(fu->pf_v_pages) & 15))
-        return PG_ERR_ARG;
-      a.pf_k = static_cast<const uint8_t*>(fu->pf_k_pages); a.pf_v = static_cast<const uint8_t*>(fu->pf_v_pages);
-      a.pf_table = fu->pf_page_table; a.pf_len = fu->pf_kv_len; a.pf_B = fu->pf_B; a.pf_max_pages = fu->pf_max_pages;
-      a.pf_page_bytes = fu->pf_page_bytes;
     }
     if (fu->stats != nullptr) {
       // plain fp32 logits + bias only (no residual, no in-kernel norm factor), one CTA per output tile

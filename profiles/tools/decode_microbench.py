@@ -1,6 +1,6 @@
 """Steady-state timing of the decode-layer kernel chain (3B shapes), 18 layers' weights in rotation (cold L2), every chain
 captured in one CUDA graph (no host launch overhead).  A/B of the 7-launch chain (standalone RMSNorms, bf16 operands by TMA)
-against the 5-launch chain (norms folded into the GEMMs, KV pages prefetched into L2 by the q/k/v projection).
+against the chains with the norms folded into the q/k/v and / or gate||up GEMMs.
 
     python profiles/tools/decode_microbench.py            # MB_B=64 MB_KV=324 by default
 """
@@ -93,14 +93,13 @@ def old_layer(i):
     _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD)
 
 
-def make_new_layer(prefetch=True, fold_qkv=True, fold_gu=True):
+def make_new_layer(fold_qkv=True, fold_gu=True):
     def f(i):
-        pf = (k_pages[i], v_pages[i], table, kvl) if prefetch else None
         if fold_qkv:
-            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ, kv_prefetch=pf)
+            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ)
         else:
             _lib.rmsnorm(h, ln_w, hn_out)
-            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ, kv_prefetch=pf)
+            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ)
         attn(i, norm=fold_qkv)
         _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=attout, split_k=SO, zero_buf=qkv)
         if fold_gu:
@@ -116,8 +115,6 @@ layer_bytes = (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4
 print(f"==== B={B} kv={kvlen} splits qkv {SQ} o {SO} down {SD}")
 graph_time("qkv  bf16 operand (TMA)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn, split_k=SQ), W * D * 2)
 graph_time("qkv  fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ), W * D * 2)
-graph_time("qkv  fp32 operand + KV prefetch", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ,
-                                                                        kv_prefetch=(k_pages[i], v_pages[i], table, kvl)), W * D * 2)
 graph_time("o    split-K", lambda i: _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=att, split_k=SO), D * D * 2)
 graph_time("gate-up geglu, bf16 operand (TMA)", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
 graph_time("gate-up geglu, fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(gu_w[i], midout, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=ln_w, apply_rstd=True), 2 * F * D * 2)
@@ -127,8 +124,5 @@ graph_time("attention (cold KV)", lambda i: attn(i), B * kvlen * dh * 4)
 graph_time("attention (cold KV, + norm factor)", lambda i: attn(i, True), B * kvlen * dh * 4)
 graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
 graph_time("LAYER 7 launches (round-1 chain)", old_layer, layer_bytes)
-graph_time("LAYER 5 launches (norms folded, KV prefetch)", make_new_layer(), layer_bytes)
-graph_time("LAYER 5 launches, no KV prefetch", make_new_layer(prefetch=False), layer_bytes)
-graph_time("LAYER 6 launches: only qkv norm folded", make_new_layer(fold_gu=False), layer_bytes)
-graph_time("LAYER 6 launches: only gate-up norm folded", make_new_layer(fold_qkv=False), layer_bytes)
-graph_time("LAYER 7 launches + KV prefetch", make_new_layer(fold_qkv=False, fold_gu=False), layer_bytes)
+graph_time("LAYER 6 launches: qkv norm folded (default)", make_new_layer(fold_gu=False), layer_bytes)
+graph_time("LAYER 5 launches: both norms folded", make_new_layer(), layer_bytes)

@@ -1,6 +1,6 @@
 """Decode-step GEMM fusions (pg_gemm_bf16_fused): the activation operand built in the kernel from the fp32 residual stream
 (GemmaRMSNorm folded into the projection, modeling_gemma.py:172-181,395-396,412-413), the zero-fill of a later split-K
-accumulator and the KV-page L2 prefetch -- against plain PyTorch fp32 of the same math, through the C ABI."""
+accumulator -- against plain PyTorch fp32 of the same math, through the C ABI."""
 import pytest
 import torch
 
@@ -87,9 +87,8 @@ def test_fused_rmsnorm_f32_and_bf16_epilogues(T):
     _close(outb, ref, 1e-2, "fused rmsnorm, bf16 epilogue")
 
 
-def test_zero_fill_and_kv_prefetch_ride_along():
-    """o_proj of a decode step: split-K red.add into the residual stream from a bf16 operand, re-zeroing the q/k/v accumulator;
-    the q/k/v projection additionally prefetches live KV pages (a hint: only its harmlessness can be asserted)."""
+def test_zero_fill_rides_along():
+    """o_proj of a decode step: split-K red.add into the residual stream from a bf16 operand, re-zeroing the q/k/v accumulator."""
     from paligemma_multimodal_system_b200 import _lib
     T, F, K = 64, 2048, 2048
     g = torch.Generator(device="cuda").manual_seed(4)
@@ -102,20 +101,6 @@ def test_zero_fill_and_kv_prefetch_ride_along():
     torch.cuda.synchronize()
     _close(out, x.float() @ w.float().t() + resid, 2e-3, "o_proj split-K")
     assert torch.count_nonzero(acc) == 0
-    # prefetch: ragged lengths (0 pages .. all pages), a permuted page table, pages of 32 KB
-    B, max_pages, dh = 5, 4, 256
-    pool = B * max_pages + 3
-    k_pages = torch.randn(pool, 64, dh, device="cuda", generator=g).bfloat16()
-    v_pages = torch.randn(pool, 64, dh, device="cuda", generator=g).bfloat16()
-    table = torch.randperm(pool, device="cuda", generator=g)[: B * max_pages].int().view(B, max_pages).contiguous()
-    kv_len = torch.tensor([1, 64, 65, 256, 200], device="cuda", dtype=torch.int32)
-    kb, vb = k_pages.clone(), v_pages.clone()
-    h, nw, wq = _mk(B, 2560, 2048, 5)
-    o = torch.zeros(B, 2560, device="cuda")
-    _lib.gemm_fused(wq, o, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=nw, split_k=7, kv_prefetch=(k_pages, v_pages, table, kv_len))
-    torch.cuda.synchronize()
-    _close(o, _operand(h, nw) @ wq.float().t(), 2e-3, "projection with prefetch")
-    assert torch.equal(k_pages, kb) and torch.equal(v_pages, vb)
 
 
 def test_fused_rejects_bad_args():

@@ -103,7 +103,10 @@ def test_load_hf_model_logits_match_direct_state_dict_and_oracle(tmp_path):
     loaded.language_model.deterministic_decode = direct.language_model.deterministic_decode = True
     _, a = loaded.generate(*args, return_logits=True, forced_tokens=ref_t)
     _, b = direct.generate(*args, return_logits=True, forced_tokens=ref_t)
-    assert torch.equal(a, b), "loader path and direct state-dict path hold different weights"
+    # (not bitwise: the few-token vision-tower GEMMs split K over CTAs and red.add their partials in arrival order)
+    assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item(), "loader path and direct state-dict path hold different weights"
+    for k, v in direct.state_dict().items():
+        assert torch.equal(loaded.state_dict()[k], v), k
     err, absmax = (a.cpu() - ref_l).abs().max().item(), ref_l.abs().max().item()
     cos = torch.nn.functional.cosine_similarity(a.cpu().flatten().double(), ref_l.flatten().double(), dim=0).item()
     assert cos >= 0.9999 and err <= 0.01 * absmax, (err, absmax, cos)
@@ -123,4 +126,5 @@ def test_projector_bias_of_real_checkpoints_is_applied(tmp_path):
     with_b = model.image_features(px).clone()
     model.set_projector_bias(None)
     without = model.image_features(px)
-    assert (with_b - without - bias.cuda()).abs().max().item() <= 1e-3
+    # run-to-run noise of the split-K vision GEMMs is ~1e-3 of the feature scale; a dropped bias would be off by ~0.5
+    assert (with_b - without - bias.cuda()).abs().max().item() <= 1e-2 * max(1.0, without.abs().max().item())
