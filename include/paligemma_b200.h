@@ -60,29 +60,17 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
                  int act_gelu, float scale, int swap, int split_k, void* stream);
 
 /*
- * pg_gemm_bf16 with the decode-step fusions of the swap-AB (tokens <= 128) kernels; `fusion` may be NULL (= pg_gemm_bf16).
+ * pg_gemm_bf16 with the decode-step chores of the swap-AB (tokens <= 128) kernels; `fusion` may be NULL (= pg_gemm_bf16).
  *
- *  - x_f32 != NULL: the activation operand is built IN the kernel from fp32 rows (the residual stream), x is ignored:
- *        X[t,k] = bf16(x_f32[t,k] * (1 + norm_w[k]))
- *    i.e. GemmaRMSNorm (modeling_gemma.py:172-181) without its per-token factor r[t] = rsqrt(mean_k x_f32[t,k]^2 + eps), which
- *    is linear in the GEMM.  apply_rstd = 1 (split_k must be 1): the epilogue multiplies the accumulator by r[t] before bias /
- *    activation / GEGLU, so out = Linear(GemmaRMSNorm(x_f32)) exactly as modeling_gemma.py:395-396,412-413 chain them.
- *    apply_rstd = 0: the CONSUMER applies r[t] (split-K q/k/v projection -> pg_attention_decode_fused, which computes r[t]
- *    from the same rows).  Replaces the standalone RMSNorm launch and its bf16 round trip.
- *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; used to reset the
- *    split-K accumulator that a later kernel of the chain red.adds into.
- *  - stats (PG_EPI_F32 only, no resid / x_f32 / split-K): the lm_head of a decode step (modeling_gemma.py:523-525) also emits,
- *    for every token t and every 32-row vocabulary segment g (g = f / 32), stats[t * stats_ld + g] = (m, s) with
+ *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; o_proj uses it to
+ *    reset the split-K accumulator of the q/k/v projection once the attention kernel has consumed it.
+ *  - stats (PG_EPI_F32 only, no resid / split-K): the lm_head of a decode step (modeling_gemma.py:523-525) also emits, for
+ *    every token t and every 32-row vocabulary segment g (g = f / 32), stats[t * stats_ld + g] = (m, s) with
  *    m = max logit of the segment and s = sum exp2((logit - m) * stat_c), stat_c = inv_temperature * log2(e) -- temperature
  *    scaling and the max / partition-function passes of softmax + top-p (inference.py:63-66,90-106) folded into the GEMM
  *    epilogue; consumed by pg_sample_top_p_stats / pg_argmax_stats.  stats_ld >= 4 * ceil(features / 128) (float2 units).
  */
 typedef struct PgGemmFusion {
-  const float* x_f32;
-  long long ldx_f32;
-  const float* norm_w;
-  int apply_rstd;
-  float eps;
   float* zero_buf;
   long long zero_count;
   void* stats;
@@ -105,7 +93,7 @@ int pg_layernorm(const float* x, const float* gamma, const float* beta, void* y_
                  float eps, void* stream);
 
 /* GemmaRMSNorm (modeling_gemma.py:157-182): y = x * rsqrt(mean(x^2) + eps) * (1 + w); x fp32 -> y bf16.  (Prefill, and the
- * final norm of a decode step; the per-layer norms of a decode step are folded into pg_gemm_bf16_fused.) */
+ * decode norms.) */
 int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, void* stream);
 
 /*
@@ -172,14 +160,10 @@ int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos, void* q_o
  * contiguous range of 64-key pages (TMA tensor loads into 128B-swizzled shared memory) and the ranks merge through
  * distributed shared memory.  num_pages = pages in the pool (k_pages / v_pages are [num_pages, 64, Hkv*dh] bf16).
  * GQA group Hq/Hkv <= 8, dh in {64, 256}.
- * h_norm != NULL: qkv holds the projections of the UN-normalised rows (pg_gemm_bf16_fused with apply_rstd = 0); the kernel
- * computes r[b] = rsqrt(mean(h_norm[b, 0:norm_dim]^2) + eps) (fp32 rows, pitch norm_dim) and scales q, k and v by it before
- * RoPE / append -- the input_layernorm factor of modeling_gemma.py:395, applied where it is cheapest.
  */
 int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
                               void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh,
-                              int page_size, int num_pages, int max_pages, float scale, const float* h_norm, int norm_dim,
-                              float eps, void* stream);
+                              int page_size, int num_pages, int max_pages, float scale, void* stream);
 
 /* Gathers the dense K or V of one layer, [B, Hkv, len, dh] bf16, from the paged cache (KVCache.k_cache / v_cache
  * views, modeling_gemma.py:8-64). */

@@ -44,7 +44,7 @@ SIGNATURES = {
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_attention_prefill_varlen": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
-    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p, i32, f32, p],
+    "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
@@ -62,7 +62,6 @@ _RESTYPE = {"pg_launch_count": i64}
 class GemmFusion(C.Structure):
     """Mirror of PgGemmFusion (include/paligemma_b200.h)."""
     _fields_ = [
-        ("x_f32", p), ("ldx_f32", i64), ("norm_w", p), ("apply_rstd", i32), ("eps", f32),
         ("zero_buf", p), ("zero_count", i64),
         ("stats", p), ("stats_ld", i64), ("stat_c", f32),
     ]
@@ -136,34 +135,22 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
 LOG2E = 1.4426950408889634
 
 
-def gemm_fused(w, out, *, mode, x=None, x_f32=None, norm_w=None, apply_rstd=False, eps=1e-6, zero_buf=None, bias=None, split_k=1, stats=None, inv_temperature=1.0):
-    """Decode-step (swap-AB, tokens <= 128) GEMM with the fusions of pg_gemm_bf16_fused:
-      x_f32 / norm_w   activation operand built in the kernel from the fp32 residual rows, bf16(x * (1 + norm_w)) -- the
-                       GemmaRMSNorm that precedes the projection, minus its per-token factor (apply_rstd: applied in the
-                       epilogue; otherwise the consumer applies it);
-      zero_buf         fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
-      stats            fp32 [T, nseg, 2] (nseg >= 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
-                       `inv_temperature`, for pg_sample_top_p_stats / pg_argmax_stats (mode EPI_F32 only)."""
-    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+def gemm_fused(x, w, out, *, mode, zero_buf=None, bias=None, split_k=1, stats=None, inv_temperature=1.0):
+    """Decode-step (swap-AB, tokens <= 128) GEMM with the chores of pg_gemm_bf16_fused:
+      zero_buf   fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
+      stats      fp32 [T, nseg, 2] (nseg >= 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
+                 `inv_temperature`, for pg_sample_top_p_stats / pg_argmax_stats (mode EPI_F32 only)."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1 and x.shape[1] == w.shape[1]
+    T, K = x.shape
     fu = GemmFusion()
-    if x_f32 is not None:
-        assert x is None and x_f32.dtype == torch.float32 and x_f32.stride(1) == 1 and norm_w.dtype == torch.float32
-        T, K = x_f32.shape
-        fu.x_f32, fu.ldx_f32, fu.norm_w, fu.apply_rstd, fu.eps = x_f32.data_ptr(), x_f32.stride(0), norm_w.data_ptr(), int(apply_rstd), float(eps)
-        xp, ldx = 0, 0
-    else:
-        assert x.dtype == torch.bfloat16 and x.stride(1) == 1
-        T, K = x.shape
-        xp, ldx = x.data_ptr(), x.stride(0)
-    assert w.shape[1] == K
     if zero_buf is not None:
         assert zero_buf.dtype == torch.float32 and zero_buf.is_contiguous()
         fu.zero_buf, fu.zero_count = zero_buf.data_ptr(), zero_buf.numel()
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[2] == 2 and stats.is_contiguous()
         fu.stats, fu.stats_ld, fu.stat_c = stats.data_ptr(), stats.shape[1], float(inv_temperature) * LOG2E
-    check(lib().pg_gemm_bf16_fused(xp, ldx, w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias), 0, 0, T, w.shape[0], K,
-                                   mode, 0, 1.0, 1, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")
+    check(lib().pg_gemm_bf16_fused(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias), 0, 0, T,
+                                   w.shape[0], K, mode, 0, 1.0, 1, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")
     return out
 
 

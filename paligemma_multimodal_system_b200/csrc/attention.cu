@@ -15,8 +15,7 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
 
 int pg_attention_decode_v3(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
                            void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh, int num_pages,
-                           int max_pages, float sl2, int cluster_size, const float* h_norm, int norm_dim, float eps,
-                           long long* trace, void* stream);  // attention_decode.cu
+                           int max_pages, float sl2, int cluster_size, long long* trace, void* stream);  // attention_decode.cu
 
 extern "C" int pg_attention_prefill(const void* q, const void* k, const void* v, void* o, int B, int H, int rows, int keys,
                                     int dh, int group, long long q_bs, long long q_ts, long long q_hs, long long q_head_off,
@@ -49,11 +48,10 @@ extern "C" int pg_debug_set_attn_trace(long long* p) { g_attn_trace = p; g_attn_
 extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq,
                                          void* k_pages, void* v_pages, const int* page_table, void* out, int B, int Hq,
                                          int Hkv, int dh, int page_size, int num_pages, int max_pages, float scale,
-                                         const float* h_norm, int norm_dim, float eps, void* stream) {
+                                         void* stream) {
   if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 8 || page_size != 64 || max_pages <= 0 || num_pages <= 0)
     return PG_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(k_pages) & 15) || (reinterpret_cast<uintptr_t>(v_pages) & 15)) return PG_ERR_ARG;
-  if (h_norm != nullptr && (norm_dim <= 0 || (norm_dim % 4) != 0 || (reinterpret_cast<uintptr_t>(h_norm) & 15))) return PG_ERR_ARG;
   long long* trace = g_attn_trace ? g_attn_trace + 8 * (g_attn_trace_idx++ % 32) : nullptr;
   // cluster size: as many CTAs as fit in ONE wave (the 3-deep page ring allows one CTA per SM), at most one page per
   // rank, at most 8 (portable cluster limit)
@@ -61,5 +59,5 @@ extern "C" int pg_attention_decode_fused(const float* qkv, const int* pos, const
   if (cs > max_pages) cs = max_pages;
   cs = cs >= 8 ? 8 : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
   return pg_attention_decode_v3(qkv, pos, kv_len, inv_freq, k_pages, v_pages, page_table, out, B, Hq, Hkv, dh, num_pages,
-                                max_pages, scale * 1.4426950408889634f, cs, h_norm, norm_dim, eps, trace, stream);
+                                max_pages, scale * 1.4426950408889634f, cs, trace, stream);
 }

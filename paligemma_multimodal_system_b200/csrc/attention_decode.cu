@@ -37,10 +37,6 @@ struct Params {
   bf16* out;              // [B, Hq*dh]
   int B, Hq, Hkv, max_pages;
   float sl2;
-  // optional input_layernorm factor: qkv holds projections of the un-normalised row; r = rsqrt(mean(h_norm[b]^2) + eps)
-  const float* h_norm;  // [B, norm_dim] fp32 residual stream (final before this kernel's predecessor started)
-  int norm_dim;
-  float eps;
   long long* trace;
 };
 
@@ -142,28 +138,6 @@ __global__ void __launch_bounds__(256) attn_decode_v3_kernel(const __grid_consta
   // byte offset of element (row r, column c) inside a swizzled K (or V) page
   auto swz = [&](int r, int c) -> int { return (c >> 6) * BOX_BYTES + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
 
-  // GemmaRMSNorm factor of this sequence's row (modeling_gemma.py:172-181,395), still before the dependency wait: the
-  // residual stream was final before the projection GEMM that precedes this kernel passed ITS dependency wait, which is
-  // when it triggered this launch.  q, k and v are linear in it, so it is applied to the raw projections below.
-  float rstd = 1.f;
-  if (p.h_norm != nullptr) {
-    __shared__ float s_red[8];
-    const float4* hr = reinterpret_cast<const float4*>(p.h_norm + static_cast<long long>(b) * p.norm_dim);
-    float ss = 0.f;
-    for (int i = threadIdx.x; i < p.norm_dim / 4; i += NT) {
-      const float4 v = __ldcg(hr + i);
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    if (lane == 0) s_red[warp] = ss;
-    __syncthreads();
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) tot += s_red[w];
-    rstd = rsqrtf(tot / static_cast<float>(p.norm_dim) + p.eps);
-  }
-
   // (measured, not kept: computing sincos before the wait, and signalling the rank merge through per-rank mbarriers
   //  instead of the cluster barrier -- the cluster-scope release of the pushed partials costs the ~1.5 us, not the barrier)
   griddep_wait();  // the qkv row of the new token
@@ -185,17 +159,17 @@ __global__ void __launch_bounds__(256) attn_decode_v3_kernel(const __grid_consta
       const int g = partid + gi * NPART;
       if (g < group) {
         const float* qh = row + (hk * group + g) * DH;
-        x1[gi] = __ldcg(qh + i) * rstd;
-        x2[gi] = __ldcg(qh + i + HALF) * rstd;
+        x1[gi] = __ldcg(qh + i);
+        x2[gi] = __ldcg(qh + i + HALF);
       }
     }
     if (do_k) {
       const float* kh = row + (p.Hq + hk) * DH;
-      kx1 = __ldcg(kh + i) * rstd; kx2 = __ldcg(kh + i + HALF) * rstd;
+      kx1 = __ldcg(kh + i); kx2 = __ldcg(kh + i + HALF);
     }
     if (do_v) {
       const float* vh = row + (p.Hq + p.Hkv + hk) * DH;
-      vx1 = __ldcg(vh + i) * rstd; vx2 = __ldcg(vh + i + HALF) * rstd;
+      vx1 = __ldcg(vh + i); vx2 = __ldcg(vh + i + HALF);
     }
     float sn, cs;
     sincosf(posf * freq, &sn, &cs);
@@ -468,14 +442,12 @@ static int launch(const Params& p, int num_pages, int cluster_size, cudaStream_t
 // called by pg_attention_decode_fused (attention.cu) for GQA groups <= 8
 int pg_attention_decode_v3(const float* qkv, const int* pos, const int* kv_len, const float* inv_freq, void* k_pages,
                            void* v_pages, const int* page_table, void* out, int B, int Hq, int Hkv, int dh, int num_pages,
-                           int max_pages, float sl2, int cluster_size, const float* h_norm, int norm_dim, float eps,
-                           long long* trace, void* stream) {
+                           int max_pages, float sl2, int cluster_size, long long* trace, void* stream) {
   pg::ad::Params p;
   p.qkv = qkv; p.pos = pos; p.kv_len = kv_len; p.inv_freq = inv_freq;
   p.k_pages = static_cast<__nv_bfloat16*>(k_pages); p.v_pages = static_cast<__nv_bfloat16*>(v_pages);
   p.page_table = page_table; p.out = static_cast<__nv_bfloat16*>(out);
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.max_pages = max_pages; p.sl2 = sl2; p.trace = trace;
-  p.h_norm = h_norm; p.norm_dim = norm_dim; p.eps = eps;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dh) {
     case 64: return pg::ad::launch<64>(p, num_pages, cluster_size, st);

@@ -13,14 +13,6 @@
 //   SWAP = false (prefill, many tokens):  UMMA M = 128 tokens,   N = BN features
 //   SWAP = true  (decode, tokens <= 128): UMMA M = 128 features, N = BN tokens  (weight streaming, HBM bound),
 //                                         optional split-K with fp32 red.global.add into the output
-//   BF32 = true  (decode, SWAP only): the activation operand is the fp32 residual stream itself.  The epilogue warps
-//                                         turn each 64-column slice of it into the bf16, 128B-swizzled B tile
-//                                         (x * (1 + norm_w): GemmaRMSNorm, modeling_gemma.py:172-181, minus its
-//                                         per-token factor) while the weight tiles arrive by TMA; the factor
-//                                         rsqrt(mean(x^2) + eps) is linear in the GEMM and is applied in the epilogue
-//                                         (full-K tiles) or by the consumer (split-K qkv -> the attention kernel).
-//                                         No standalone RMSNorm launch, no bf16 activation round trip.
-
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"
@@ -35,8 +27,8 @@ constexpr int ACC_STAGES = 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int BN) { return BN * BK * 2; }
 __host__ __device__ constexpr int stage_bytes(int BN) { return A_TILE_BYTES + b_tile_bytes(BN); }
-// swap: GeGLU exchange area + per-token factors; token-major: eight warp-private 4 KB transposition tiles (coalescing epilogues)
-__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 + BN * 4 : 8 * 4096; }
+// swap: GeGLU exchange area; token-major: eight warp-private 4 KB transposition tiles (coalescing epilogues)
+__host__ __device__ constexpr int xch_bytes(int BN, bool swap) { return swap ? 64 * BN * 4 : 8 * 4096; }
 // decode (SWAP, BN <= 64): two CTAs per SM (115712 B each) so that, with programmatic dependent launch, the next
 // kernel's CTAs become resident and prefetch their weights while this kernel drains; otherwise one CTA with <= 200 KB
 __host__ __device__ constexpr bool two_per_sm(int BN, bool swap) { return swap && BN <= 64; }
@@ -66,12 +58,6 @@ struct GemmArgs {
   int n_fast;  // tile raster order (decode_tile)
   int f32_coalesced;  // token-major fp32 epilogue through the shared-memory transposition (alignment checked by the host)
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
-  // ---- BF32 kernels: B operand = bf16(xf[t, k] * (1 + norm_w[k])) built in the kernel from fp32 rows ----
-  const float* xf;
-  long long ldxf;
-  const float* norm_w;
-  int apply_rstd;  // full-K tiles: multiply the accumulator by rsqrt(sum_k xf[t,k]^2 / K + eps) in the epilogue
-  float eps;
   // ---- decode-step chores of the SWAP kernels ----
   float* zero_buf;  // zero-filled after the dependency wait (the split-K accumulator of a LATER kernel of the chain)
   long long zero_count;
@@ -117,10 +103,9 @@ PG_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0,
 // Epilogue of one swap-AB tile for the non-GEGLU modes: thread = weight row (feature) fr, columns = tokens.  The mode is a
 // template parameter and the output pointer is advanced by a precomputed byte stride, so that one element costs a
 // handful of instructions (the epilogue of the decode GEMMs is issue-bound: 4 warps x 64 elements per tile).
-// rs_tab: optional per-token factors in shared memory (RMSNorm of the producer), already multiplied by args.scale.
 template <int BN, int MODE>
 PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, int j_base, bool first_split,
-                                  const float* __restrict__ rs_tab, int col_begin = 0, int col_end = BN) {
+                                  int col_begin = 0, int col_end = BN) {
   const bool f_ok = fr < args.features;
   const int nvalid = min(min(BN, col_end), args.tokens - j_base);
   const float scale = args.scale;
@@ -143,8 +128,7 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (i < n) {
-        const float m = rs_tab != nullptr ? rs_tab[c0 + i] : scale;
-        float x = fmaf(__uint_as_float(r[i]), m, bias_s);
+        float x = fmaf(__uint_as_float(r[i]), scale, bias_s);
         if (MODE == PG_EPI_BF16) {
           if (gelu) x = gelu_tanh_fast(x);
           *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(x);
@@ -420,7 +404,7 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
 // 64 features per token).  `xg` = the group's exchange area (64 * CG floats), `bar` = its named barrier.
 template <int CG>
 PG_DEVINL void geglu_swap_epilogue_group(const GemmArgs& args, uint32_t taddr, float* xg, int bar, int q, int lane, int et,
-                                         int j0, int m_blk, const float* rs_tab) {
+                                         int j0, int m_blk) {
   constexpr int HB = CG / 2;
   constexpr int LDN = HB >= 16 ? 16 : 8;
   __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
@@ -454,11 +438,6 @@ PG_DEVINL void geglu_swap_epilogue_group(const GemmArgs& args, uint32_t taddr, f
       for (int e = 0; e < 2; ++e) {
         float mine = __uint_as_float(v[i + e]);
         float other = xrecv[r * HB + ((c0 + i + e) ^ (r & (HB - 1) & 31))];
-        if (rs_tab != nullptr) {
-          const float rs = rs_tab[keep0 + c0 + i + e];
-          mine *= rs;
-          other *= rs;
-        }
         res[e] = is_gate ? gelu_tanh_fast(mine) * other : gelu_tanh_fast(other) * mine;
       }
       pk[(c0 + i) / 2] = pack_bf16(res[0], res[1]);
@@ -489,76 +468,19 @@ PG_DEVINL void geglu_swap_epilogue_group(const GemmArgs& args, uint32_t taddr, f
 }
 template <int BN>
 PG_DEVINL void geglu_swap_epilogue(const GemmArgs& args, uint32_t taddr, float* xch, int bar, int q, int lane, int et,
-                                   int j_base, int m_blk, const float* rs_tab) {
-  geglu_swap_epilogue_group<BN>(args, taddr, xch, bar, q, lane, et, j_base, m_blk, rs_tab);
+                                   int j_base, int m_blk) {
+  geglu_swap_epilogue_group<BN>(args, taddr, xch, bar, q, lane, et, j_base, m_blk);
 }
-
-// BF32 kernels: the NEPI epilogue warps build the B tiles (tokens x 64 k, bf16, K-major, 128B swizzle: row = token, 16-byte
-// chunk c of a row sits at chunk position c ^ (row & 7) -- the layout TMA would have produced) of the k-blocks [kb0, kb1)
-// of one output tile from the fp32 rows xf[t, :], scaled by (1 + norm_w[k]).  Work item = (token, 16-float segment): four
-// threads share a token, so a token's sum of squares is one quad reduction away.  The loads of the next k-block are in
-// flight while the current one waits for its pipeline slot.  Returns this thread's partial sum of squares of its token
-// (items beyond the first only exist when BN * 4 > threads; their partials are folded into `ssq[j]`).
-template <int BN, int NEPI>
-struct BTileConverter {
-  static constexpr int NT = NEPI * 32;
-  static constexpr int ITEMS = BN * 4;
-  static constexpr int PER = (ITEMS + NT - 1) / NT;
-  // k-blocks whose loads are in flight per thread (16 registers each per item): one L2 round trip (~1 us under load) has
-  // to cover DEPTH k-blocks, or the converters, not the weight stream, pace the main loop (measured with DEPTH = 1:
-  // gate||up 22 -> 48 us, qkv 5.5 -> 9.0 us)
-  static constexpr int DEPTH = PER >= 4 ? 1 : 4 / PER;
-
-  PG_DEVINL static void load(const GemmArgs& args, int j_base, int kb, int et, float4 (&v)[PER][4]) {
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int idx = et + j * NT;
-      const int tok = j_base + (idx >> 2), k0 = kb * BK + (idx & 3) * 16;
-      const bool row_ok = idx < ITEMS && tok < args.tokens;
-      const float* src = args.xf + static_cast<long long>(tok) * args.ldxf + k0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)  // K % 8 == 0 and k0 % 16 == 0: a float4 is either fully inside the row or fully outside
-        v[j][i] = (row_ok && k0 + 4 * i < args.K) ? __ldcg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-
-  PG_DEVINL static void store(const GemmArgs& args, uint32_t b_tile, int kb, int et, const float4 (&v)[PER][4], float (&ssq)[PER]) {
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int idx = et + j * NT;
-      if (idx >= ITEMS) continue;
-      const int row = idx >> 2, seg = idx & 3, k0 = kb * BK + seg * 16;
-      uint32_t pk[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + 4 * i < args.K) w = __ldg(reinterpret_cast<const float4*>(args.norm_w + k0) + i);
-        const float4 x = v[j][i];
-        ssq[j] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-        pk[2 * i] = pack_bf16(x.x * (1.0f + w.x), x.y * (1.0f + w.y));
-        pk[2 * i + 1] = pack_bf16(x.z * (1.0f + w.z), x.w * (1.0f + w.w));
-      }
-      const uint32_t base = b_tile + row * 128;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((2 * seg) ^ (row & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
-                   "r"(pk[2]), "r"(pk[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((2 * seg + 1) ^ (row & 7)) << 4)), "r"(pk[4]), "r"(pk[5]),
-                   "r"(pk[6]), "r"(pk[7]) : "memory");
-    }
-  }
-};
 
 // SPLITK = true: swap-AB kernel specialised for the split-K red.add epilogue with EIGHT epilogue warps (two per TMEM lane
 // quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
 // red.add epilogue is compiled out, which keeps the 320-thread CTA at two per SM.
-template <int BN, bool SWAP, bool SPLITK = false, bool BF32 = false>
-__global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, (two_per_sm(BN, SWAP) && !BF32) ? 2 : 1)
+template <int BN, bool SWAP, bool SPLITK = false>
+__global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
-  static_assert(!BF32 || SWAP, "the in-kernel fp32 -> bf16 operand conversion exists for the decode (swap-AB) kernels");
-  constexpr int NEPI = SPLITK ? 8 : 4;  // epilogue warps (they also build the B tiles of the BF32 kernels)
-  // bytes the TMA producer brings into one pipeline stage (BF32: the weight tile only)
-  constexpr uint32_t TMA_STAGE_BYTES = BF32 ? A_TILE_BYTES : stage_bytes(BN);
+  constexpr int NEPI = SPLITK ? 8 : 4;  // epilogue warps
   // (token-major kernel: SPLITK = true selects the same 320-thread shape, eight epilogue warps that split the columns;
   //  it pays for the short-K SigLIP GEMMs whose epilogue outlasts the main loop, and costs registers on the long-K ones)
   constexpr int STAGES = num_stages(BN, SWAP);
@@ -598,7 +520,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), BF32 ? 1 + NEPI : 1);  // BF32: + one arrival per converter warp (the B tile is in place)
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
@@ -633,7 +555,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const TileInfo t = decode_tile(blockIdx.x, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
         pre = min(STAGES, t.kb1 - t.kb0);
         for (int s = 0; s < pre; ++s) {
-          mbar_expect_tx(full_bar(s), TMA_STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
           if (SWAP) tma_load_2d(smem_base + s * STAGE_BYTES, &tmapA, full_bar(s), (t.kb0 + s) * BK, t.m_blk * BM, hintA);
           else tma_load_2d(smem_base + s * STAGE_BYTES + A_TILE_BYTES, &tmapB, full_bar(s), (t.kb0 + s) * BK, t.n_blk * BN, hintB);
         }
@@ -651,11 +573,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             --pre;
           } else {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), TMA_STAGE_BYTES);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           }
           if (!(SWAP && weights_in_flight)) tma_load_2d(sa, &tmapA, full_bar(stage), kb * BK, t.m_blk * BM, hintA);
-          if (!BF32 && !(!SWAP && weights_in_flight))
-            tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
+          if (!(!SWAP && weights_in_flight)) tma_load_2d(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN, hintB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -707,55 +628,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cstage = 0;           // BF32: pipeline position of the converter (walks the same k-blocks as producer and issuer)
-    uint32_t cphase = 0;
     const int mode = args.mode;
     __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
     float* out_f = reinterpret_cast<float*>(args.out);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, args.split_k, args.n_fast);
-      const float* rs_tab = nullptr;  // per-token epilogue factors (x args.scale) in shared memory
-      if constexpr (BF32) {
-        using Conv = BTileConverter<BN, NEPI>;
-        constexpr int DEPTH = Conv::DEPTH;
-        float4 ring[DEPTH][Conv::PER][4];  // register ring: the loads of DEPTH k-blocks are in flight
-        float ssq[Conv::PER];
-#pragma unroll
-        for (int j = 0; j < Conv::PER; ++j) ssq[j] = 0.f;
-        const int j_base = t.n_blk * BN;
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d)
-          if (t.kb0 + d < t.kb1) Conv::load(args, j_base, t.kb0 + d, et, ring[d]);
-#pragma unroll 1
-        for (int kb = t.kb0; kb < t.kb1; kb += DEPTH) {
-#pragma unroll
-          for (int d = 0; d < DEPTH; ++d) {
-            if (kb + d < t.kb1) {  // warp-uniform
-              mbar_wait(empty_bar(cstage), cphase ^ 1);  // the MMAs that read this slot's previous tile have completed
-              Conv::store(args, smem_base + cstage * STAGE_BYTES + A_TILE_BYTES, kb + d, et, ring[d], ssq);
-              fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-              __syncwarp();
-              if (lane == 0) mbar_arrive(full_bar(cstage));
-              if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
-              if (kb + d + DEPTH < t.kb1) Conv::load(args, j_base, kb + d + DEPTH, et, ring[d]);
-            }
-          }
-        }
-        if (args.apply_rstd) {  // (host: split_k == 1, so this CTA has seen every column of its tokens)
-          float* tab = xch + 64 * BN;  // BN floats after the exchange area
-          named_bar_sync(3, NEPI * 32);  // the previous tile's epilogue has read the table
-#pragma unroll
-          for (int j = 0; j < Conv::PER; ++j) {
-            float v = ssq[j];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            const int idx = et + j * Conv::NT;
-            if ((idx & 3) == 0 && idx < Conv::ITEMS) tab[idx >> 2] = rsqrtf(v / static_cast<float>(args.K) + args.eps) * args.scale;
-          }
-          named_bar_sync(3, NEPI * 32);
-          rs_tab = tab;
-        }
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       if (tr && threadIdx.x == 64) args.trace[3] = clock64();  // accumulator ready (first tile)
       tc_fence_after();
@@ -770,10 +647,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         if (mode == PG_EPI_GEGLU) {
           if constexpr (BN >= 32)
             geglu_swap_epilogue_group<HALF_COLS>(args, taddr + half * HALF_COLS, xch + half * 64 * HALF_COLS, 1 + half, q, lane,
-                                                 ((warp - 2) & 3) * 32 + lane, t.n_blk * BN + half * HALF_COLS, t.m_blk,
-                                                 rs_tab != nullptr ? rs_tab + half * HALF_COLS : nullptr);
+                                                 ((warp - 2) & 3) * 32 + lane, t.n_blk * BN + half * HALF_COLS, t.m_blk);
         } else if (half * HALF_COLS < BN) {
-          swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split, rs_tab,
+          swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, t.m_blk * BM + rl, t.n_blk * BN, first_split,
                                                     half * HALF_COLS, (half + 1) * HALF_COLS);
         }
       } else if constexpr (!SWAP) {
@@ -834,13 +710,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const int fr = t.m_blk * BM + rl;
         const int j_base = t.n_blk * BN;
         if (mode == PG_EPI_GEGLU) {
-          geglu_swap_epilogue<BN>(args, taddr, xch, 1, q, lane, (warp - 2) * 32 + lane, j_base, t.m_blk, rs_tab);
+          geglu_swap_epilogue<BN>(args, taddr, xch, 1, q, lane, (warp - 2) * 32 + lane, j_base, t.m_blk);
         } else {
           // (measured: 16-byte REDG.F32x4 after a lane-quad transpose is ~2x SLOWER here than 4-byte coalesced reds)
-          if (mode == PG_EPI_ATOMIC_F32) swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, fr, j_base, first_split, rs_tab);
+          if (mode == PG_EPI_ATOMIC_F32) swap_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, fr, j_base, first_split);
           else if (mode == PG_EPI_F32 && args.stats != nullptr) swap_tile_epilogue_f32_stats<BN>(args, taddr, fr, j_base, t.m_blk * 4 + q, lane);
-          else if (mode == PG_EPI_F32) swap_tile_epilogue<BN, PG_EPI_F32>(args, taddr, fr, j_base, first_split, rs_tab);
-          else swap_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, fr, j_base, first_split, rs_tab);
+          else if (mode == PG_EPI_F32) swap_tile_epilogue<BN, PG_EPI_F32>(args, taddr, fr, j_base, first_split);
+          else swap_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, fr, j_base, first_split);
         }
       }
       tc_fence_before();
@@ -875,13 +751,13 @@ extern "C" int pg_debug_set_gemm_bn(int bn) {
   return 0;
 }
 
-template <int BN, bool SWAP, bool SPLITK = false, bool BF32 = false>
+template <int BN, bool SWAP, bool SPLITK = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};
   constexpr int smem = smem_bytes(BN, SWAP);
   const int dev = current_device();
   if (!configured[dev]) {  // function attributes are per device
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK, BF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();  // do not leave a sticky error behind
       return PG_ERR_CUDA;
     }
@@ -889,7 +765,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   }
   const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
   const int grid = num_tiles < slots ? num_tiles : slots;
-  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK, BF32>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess
+  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess
              ? PG_OK : PG_ERR_CUDA;
 }
 
@@ -909,10 +785,9 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
                                   int mode, int act_gelu, float scale, int swap, int split_k, const PgGemmFusion* fu,
                                   void* stream) {
   if (tokens <= 0 || features <= 0 || K <= 0) return PG_ERR_ARG;
-  const bool bf32 = fu != nullptr && fu->x_f32 != nullptr;
   if ((K % 8) != 0 || (ldw % 8) != 0) return PG_ERR_ARG;  // TMA: 16 B pitch granularity
   if (reinterpret_cast<uintptr_t>(w) & 15) return PG_ERR_ARG;
-  if (!bf32 && (x == nullptr || (ldx % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15))) return PG_ERR_ARG;
+  if (x == nullptr || (ldx % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return PG_ERR_ARG;
   if (mode < PG_EPI_BF16 || mode > PG_EPI_GEGLU) return PG_ERR_ARG;
   if (mode == PG_EPI_GEGLU && (features % 128) != 0) return PG_ERR_ARG;
   if (swap < 0) swap = tokens <= 128 ? 1 : 0;
@@ -932,20 +807,13 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
   a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
   if (fu != nullptr) {
     if (!swap) return PG_ERR_ARG;  // the fusions below belong to the decode (swap-AB) kernels
-    if (bf32) {
-      if (fu->norm_w == nullptr || (fu->ldx_f32 % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->x_f32) & 15) ||
-          (reinterpret_cast<uintptr_t>(fu->norm_w) & 15))
-        return PG_ERR_ARG;
-      if (fu->apply_rstd && split_k != 1) return PG_ERR_ARG;  // a split only sees a slice of the row
-      a.xf = fu->x_f32; a.ldxf = fu->ldx_f32; a.norm_w = fu->norm_w; a.apply_rstd = fu->apply_rstd ? 1 : 0; a.eps = fu->eps;
-    }
     if (fu->zero_count > 0) {
       if (fu->zero_buf == nullptr || (fu->zero_count % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->zero_buf) & 15)) return PG_ERR_ARG;
       a.zero_buf = fu->zero_buf; a.zero_count = fu->zero_count;
     }
     if (fu->stats != nullptr) {
       // plain fp32 logits + bias only (no residual, no in-kernel norm factor), one CTA per output tile
-      if (mode != PG_EPI_F32 || resid != nullptr || bf32 || split_k != 1 || fu->stats_ld < 4ll * ((features + BM - 1) / BM) ||
+      if (mode != PG_EPI_F32 || resid != nullptr || split_k != 1 || fu->stats_ld < 4ll * ((features + BM - 1) / BM) ||
           (reinterpret_cast<uintptr_t>(fu->stats) & 7) || !(fu->stat_c > 0.f))
         return PG_ERR_ARG;
       a.stats = static_cast<float2*>(fu->stats); a.stats_ld = fu->stats_ld; a.stat_c = fu->stat_c;
@@ -970,20 +838,10 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
   if (swap) {
     int BN = tokens <= 16 ? 16 : tokens <= 32 ? 32 : tokens <= 64 ? 64 : 128;
     if ((rc = make_tmap_2d(&ta, w, features, K, ldw, BM)) != PG_OK) return rc;
-    if (bf32) tb = ta;  // unused by the BF32 kernels (the B tiles are built from the fp32 rows)
-    else if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
+    if ((rc = make_tmap_2d(&tb, x, tokens, K, ldx, BN)) != PG_OK) return rc;
     const int tiles = ((features + BM - 1) / BM) * split_k;
     // 33..64 tokens, red.add or GEGLU epilogue: the 320-thread variant with eight epilogue warps
     const bool eight = (mode == PG_EPI_ATOMIC_F32 || mode == PG_EPI_GEGLU) && BN == 64;
-    if (bf32) {
-      if (eight) return launch<64, true, true, true>(ta, tb, a, tiles, st);
-      switch (BN) {
-        case 16: return launch<16, true, false, true>(ta, tb, a, tiles, st);
-        case 32: return launch<32, true, false, true>(ta, tb, a, tiles, st);
-        case 64: return launch<64, true, false, true>(ta, tb, a, tiles, st);
-        default: return launch<128, true, false, true>(ta, tb, a, tiles, st);
-      }
-    }
     if (eight) return launch<64, true, true>(ta, tb, a, tiles, st);
     switch (BN) {
       case 16: return launch<16, true>(ta, tb, a, tiles, st);

@@ -376,15 +376,11 @@ class GemmaForCausalLM(nn.Module):
     @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B, inv_temperature: float = 1.0):
         """One decode step over all layers (modeling_gemma.py:385-418 at q_len == 1); reads bufs['h'] (fp32 embeddings),
-        leaves fp32 logits in bufs['logits'].  SIX launches per layer:
-          1. q/k/v projection, split-K red.add into the zeroed fp32 `qkv`; its activation operand is built in the kernel
-             from the fp32 residual stream (input_layernorm without the per-token factor);
-          2. RoPE + KV append + attention (applies the input_layernorm factor to q, k, v);
-          3. o_proj, split-K red.add into the residual stream; re-zeroes `qkv`;
-          4. post_attention_layernorm (standalone: folding it into gate||up makes each of the 256 weight-streaming CTAs
-             convert the whole 64 x 2048 fp32 activation matrix -- measured 22 -> 48 us, DESIGN.md 4);
-          5. gate||up with GeGLU epilogue;
-          6. down_proj, split-K red.add into the residual stream.
+        leaves fp32 logits in bufs['logits'].  Seven launches per layer: RMSNorm, QKV GEMM, fused RoPE + KV append +
+        attention, O GEMM, RMSNorm, gate||up GEGLU GEMM, down GEMM; the three small-output GEMMs split K over CTAs and
+        red.add their fp32 partials straight into the residual stream / the zeroed `qkv` accumulator, which the o_proj launch
+        resets for the next layer.  (Folding the norms into the GEMMs -- the consumer converting the fp32 residual stream into its
+        own bf16 operand tiles -- was built and measured: slower)
         Then the final RMSNorm and the lm_head (modeling_gemma.py:523-525), whose epilogue also leaves the softmax statistics
         of every 32-token vocabulary segment at `inv_temperature` in bufs['stats'] (pg_sample_top_p_stats / pg_argmax_stats).
         Every launch reads its sizes from device counters, so the sequence can be captured in a CUDA graph."""
@@ -407,17 +403,18 @@ class GemmaForCausalLM(nn.Module):
             # reproducible run to run (the split-K partials otherwise arrive in a different order every launch)
             sp_qkv = sp_o = sp_down = 1
         for li, lw in enumerate(pk["layers"]):
-            _lib.gemm_fused(lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=lw["ln1"], split_k=sp_qkv)
+            _lib.rmsnorm(h, lw["ln1"], hn, eps=eps)
+            _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
-                kv_cache.k_pages.shape[1], max_pages, scale, h.data_ptr(), D, eps, st), "pg_attention_decode_fused")
-            _lib.gemm_fused(lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, x=att, split_k=sp_o, zero_buf=qkv)
+                kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
+            _lib.gemm_fused(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, split_k=sp_o, zero_buf=qkv)
             _lib.rmsnorm(h, lw["ln2"], hn, eps=eps)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
             _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
         _lib.rmsnorm(h, pk["norm_w"], hn, eps=eps)
-        _lib.gemm_fused(pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, x=hn, bias=pk["head_b"], stats=bufs["stats"],
+        _lib.gemm_fused(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], stats=bufs["stats"],
                         inv_temperature=inv_temperature)
         return bufs["logits"]
 

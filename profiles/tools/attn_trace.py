@@ -13,7 +13,7 @@ qkvf=torch.randn(B, W, device="cuda")*0.5
 out=torch.empty(B, Hq*dh, device="cuda", dtype=torch.bfloat16)
 tr = torch.zeros(8 * 64 + 256, device="cuda", dtype=torch.int64)
 def attn(i):
-    _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), out.data_ptr(), B, Hq, Hkv, dh, PAGE, B*max_pages, max_pages, 1.0/16, 0, 0, 0.0, _lib.stream()), "attn")
+    _lib.check(L.pg_attention_decode_fused(qkvf.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(), v_pages[i].data_ptr(), table.data_ptr(), out.data_ptr(), B, Hq, Hkv, dh, PAGE, B*max_pages, max_pages, 1.0/16, _lib.stream()), "attn")
 for i in range(NL): attn(i)
 torch.cuda.synchronize()
 s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())

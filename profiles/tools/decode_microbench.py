@@ -77,52 +77,57 @@ def graph_time(name, fn, bytes_per_launch, reps=5):
     return us
 
 
-def attn(i, norm=False):
+def attn(i):
     _lib.check(L.pg_attention_decode_fused(qkv.data_ptr(), posd.data_ptr(), kvl.data_ptr(), inv_freq.data_ptr(), k_pages[i].data_ptr(),
                                            v_pages[i].data_ptr(), table.data_ptr(), attout.data_ptr(), B, Hq, Hkv, dh, PAGE, B * max_pages,
-                                           max_pages, 1.0 / 16, h.data_ptr() if norm else 0, D, 1e-6, _lib.stream()), "attn")
+                                           max_pages, 1.0 / 16, _lib.stream()), "attn")
 
 
-def old_layer(i):
+def layer(i, sq=SQ, so=SO, sd=SD):
     _lib.rmsnorm(h, ln_w, hn_out)
-    _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ)
+    _lib.gemm(hn_out, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sq)
     attn(i)
-    _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=attout, split_k=SO, zero_buf=qkv)
+    _lib.gemm_fused(attout, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, split_k=so, zero_buf=qkv)
     _lib.rmsnorm(h, ln_w, hn_out)
     _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
-    _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD)
-
-
-def make_new_layer(fold_qkv=True, fold_gu=True):
-    def f(i):
-        if fold_qkv:
-            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ)
-        else:
-            _lib.rmsnorm(h, ln_w, hn_out)
-            _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn_out, split_k=SQ)
-        attn(i, norm=fold_qkv)
-        _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=attout, split_k=SO, zero_buf=qkv)
-        if fold_gu:
-            _lib.gemm_fused(gu_w[i], midout, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=ln_w, apply_rstd=True)
-        else:
-            _lib.rmsnorm(h, ln_w, hn_out)
-            _lib.gemm(hn_out, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1)
-        _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD)
-    return f
+    _lib.gemm(midout, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sd)
 
 
 layer_bytes = (W * D + D * D + 3 * F * D) * 2 + B * kvlen * dh * 4
 print(f"==== B={B} kv={kvlen} splits qkv {SQ} o {SO} down {SD}")
-graph_time("qkv  bf16 operand (TMA)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x=hn, split_k=SQ), W * D * 2)
-graph_time("qkv  fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, x_f32=h, norm_w=ln_w, split_k=SQ), W * D * 2)
-graph_time("o    split-K", lambda i: _lib.gemm_fused(o_w[i], h, mode=_lib.EPI_ATOMIC_F32, x=att, split_k=SO), D * D * 2)
-graph_time("gate-up geglu, bf16 operand (TMA)", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
-graph_time("gate-up geglu, fp32 operand (in-kernel norm)", lambda i: _lib.gemm_fused(gu_w[i], midout, mode=_lib.EPI_GEGLU, x_f32=h, norm_w=ln_w, apply_rstd=True), 2 * F * D * 2)
-graph_time("down split-K", lambda i: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SD), D * F * 2)
+graph_time("qkv split-K", lambda i: _lib.gemm(hn, qkv_w[i], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=SQ), W * D * 2)
+graph_time("o   split-K (+ zero-fill of qkv)", lambda i: _lib.gemm_fused(att, o_w[i], h, mode=_lib.EPI_ATOMIC_F32, split_k=SO, zero_buf=qkv), D * D * 2)
+graph_time("gate-up geglu", lambda i: _lib.gemm(hn, gu_w[i], midout, mode=_lib.EPI_GEGLU, swap=1), 2 * F * D * 2)
+for sd in (SD, 2 * SD, 37):
+    graph_time(f"down split-K {sd}", lambda i, sd=sd: _lib.gemm(mid, down_w[i], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sd), D * F * 2)
 graph_time("rmsnorm", lambda i: _lib.rmsnorm(h, ln_w, hn_out), B * D * 6)
-graph_time("attention (cold KV)", lambda i: attn(i), B * kvlen * dh * 4)
-graph_time("attention (cold KV, + norm factor)", lambda i: attn(i, True), B * kvlen * dh * 4)
-graph_time("lm_head", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
-graph_time("LAYER 7 launches (round-1 chain)", old_layer, layer_bytes)
-graph_time("LAYER 6 launches: qkv norm folded (default)", make_new_layer(fold_gu=False), layer_bytes)
-graph_time("LAYER 5 launches: both norms folded", make_new_layer(), layer_bytes)
+graph_time("attention", lambda i: attn(i), B * kvlen * dh * 4)
+graph_time("LAYER (7 launches)", layer, layer_bytes)
+graph_time("LAYER, down split 37", lambda i: layer(i, sd=37), layer_bytes)
+
+# ---- lm_head and the samplers (per decode step, not per layer: one launch per graph node, 18 nodes) ----
+stats = torch.empty(B, 4 * ((V + 127) // 128), 2, device=dev)
+nxt = torch.empty(B, device=dev, dtype=torch.int32)
+step = torch.zeros(1, device=dev, dtype=torch.int32)
+graph_time("lm_head (fp32 logits + bias)", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
+graph_time("lm_head + segment statistics", lambda i: _lib.gemm_fused(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, stats=stats, inv_temperature=1.25), V * D * 2, reps=1)
+logits.normal_(0, 2.0)
+_lib.gemm_fused(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, stats=stats, inv_temperature=1.25)
+graph_time("top-p, 3 passes over the row (pg_sample_top_p)", lambda i: _lib.check(L.pg_sample_top_p(logits.data_ptr(), V, nxt.data_ptr(), 0, B, V, 1.25, 0.9, 1, step.data_ptr(), _lib.stream()), "s"), B * V * 4, reps=3)
+graph_time("top-p from statistics (pg_sample_top_p_stats)", lambda i: _lib.check(L.pg_sample_top_p_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, 1.25, 0.9, 1, 0, step.data_ptr(), _lib.stream()), "s"), B * V * 4, reps=3)
+graph_time("argmax over the row (pg_argmax)", lambda i: _lib.check(L.pg_argmax(logits.data_ptr(), V, nxt.data_ptr(), B, V, _lib.stream()), "a"), B * V * 4, reps=3)
+graph_time("argmax from statistics (pg_argmax_stats)", lambda i: _lib.check(L.pg_argmax_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, _lib.stream()), "a"), B * V * 4, reps=3)
+
+
+def head_and_sample(i):
+    _lib.gemm_fused(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, stats=stats, inv_temperature=1.25)
+    _lib.check(L.pg_sample_top_p_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, 1.25, 0.9, 1, 0, step.data_ptr(), _lib.stream()), "s")
+
+
+def head_and_sample_old(i):
+    _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1)
+    _lib.check(L.pg_sample_top_p(logits.data_ptr(), V, nxt.data_ptr(), 0, B, V, 1.25, 0.9, 1, step.data_ptr(), _lib.stream()), "s")
+
+
+graph_time("lm_head -> top-p, round-1 kernels", head_and_sample_old, V * D * 2, reps=1)
+graph_time("lm_head + statistics -> top-p from statistics", head_and_sample, V * D * 2, reps=1)

@@ -54,12 +54,10 @@ def test_gemma_prefill_attention(B, S, Hq, dh):
     _close(out, ref, 1.5e-2, "gemma prefill attention")
 
 
-@pytest.mark.parametrize("with_norm", [False, True])
 @pytest.mark.parametrize("B,Hq,dh,lens", [(4, 8, 256, [261, 300, 64, 1]), (2, 4, 64, [17, 130]), (64, 8, 256, None), (3, 8, 256, [128, 129, 65]),
                                           (1, 8, 256, [4100]), (40, 8, 256, None), (160, 8, 256, None)])
-def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens, with_norm):
-    """pg_attention_decode_fused == RoPE(q,k_new) + cache append + softmax(QK^T/sqrt(dh))V over the whole cache; with
-    `h_norm` the raw projections are first scaled by the row's RMSNorm factor rsqrt(mean(h^2) + eps)."""
+def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens):
+    """pg_attention_decode_fused == RoPE(q,k_new) + cache append + softmax(QK^T/sqrt(dh))V over the whole cache."""
     from paligemma_multimodal_system_b200 import _lib
     if lens is None:
         lens = [260 + (i % 70) for i in range(B)]
@@ -77,20 +75,15 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens, with_norm):
     out = torch.full((B, Hq * dh), float("nan"), device="cuda", dtype=torch.bfloat16)
     k_before, v_before = k_pages.clone(), v_pages.clone()
     scale = 1.0 / math.sqrt(dh)
-    D, eps = 520, 1e-6
-    hres = torch.randn(B, D, device="cuda", generator=g) * torch.linspace(0.3, 3.0, B, device="cuda")[:, None]
     for rep in range(2):
         k_pages.copy_(k_before); v_pages.copy_(v_before)
         rc = _lib.lib().pg_attention_decode_fused(qkv.data_ptr(), pos.data_ptr(), kv_len.data_ptr(), inv_freq.data_ptr(),
                                                   k_pages.data_ptr(), v_pages.data_ptr(), table.data_ptr(), out.data_ptr(),
-                                                  B, Hq, 1, dh, page, num_pages, max_pages, scale,
-                                                  hres.data_ptr() if with_norm else 0, D, eps, _lib.stream())
+                                                  B, Hq, 1, dh, page, num_pages, max_pages, scale, _lib.stream())
         _lib.check(rc, "fused decode attn")
         torch.cuda.synchronize()
     half = dh // 2
     rot = lambda t: torch.cat([-t[..., half:], t[..., :half]], -1)
-    if with_norm:  # the kernel's inputs are the projections of the un-normalised rows
-        qkv = qkv * torch.rsqrt(hres.pow(2).mean(-1, keepdim=True) + eps)
     for b in range(B):
         L = lens[b]
         ang = pos[b].float() * inv_freq
@@ -110,7 +103,7 @@ def test_decode_attention_fused_rope_append_combine(B, Hq, dh, lens, with_norm):
         # the append landed in the right page slot, nothing else in the cache changed
         pg_, off = table[b, (L - 1) // page].item(), (L - 1) % page
         assert (k_pages[pg_, off].float() - kr.float()).abs().max() <= 2 ** -7 * kr.float().abs().max()
-        assert (v_pages[pg_, off].float() - vn).abs().max() <= 2 ** -7 * vn.abs().max()
+        assert torch.equal(v_pages[pg_, off], vn.bfloat16())
     changed = (k_pages != k_before).any(-1).sum().item()
     assert changed <= B
 
@@ -169,4 +162,4 @@ def test_attention_shapes_without_a_kernel_are_errors():
     i = torch.ones(4, device="cuda", dtype=torch.int32)
     # GQA group 16 > 8: no decode kernel
     assert _lib.lib().pg_attention_decode_fused(f.data_ptr(), i.data_ptr(), i.data_ptr(), f.data_ptr(), x.data_ptr(), x.data_ptr(),
-                                                i.data_ptr(), x.data_ptr(), 1, 16, 1, 64, 64, 1, 1, 0.1, 0, 0, 0.0, _lib.stream()) == -1
+                                                i.data_ptr(), x.data_ptr(), 1, 16, 1, 64, 64, 1, 1, 0.1, _lib.stream()) == -1

@@ -156,7 +156,7 @@ def test_lm_head_epilogue_statistics(T, V, K):
     nseg = 4 * ((V + 127) // 128)
     logits = torch.full((T, V), float("nan"), device="cuda")
     stats = torch.full((T, nseg, 2), float("nan"), device="cuda")
-    _lib.gemm_fused(w, logits, mode=_lib.EPI_F32, x=x, bias=bias, stats=stats, inv_temperature=inv_temp)
+    _lib.gemm_fused(x, w, logits, mode=_lib.EPI_F32, bias=bias, stats=stats, inv_temperature=inv_temp)
     plain = torch.empty(T, V, device="cuda")
     _lib.gemm(x, w, plain, mode=_lib.EPI_F32, bias=bias, swap=1)
     torch.cuda.synchronize()
