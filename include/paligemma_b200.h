@@ -46,6 +46,8 @@ int pg_debug_set_gemm_bn(int bn); /* tuning sweeps: force the N tile (64 / 128 /
 int pg_debug_set_topp_bracket(int half_width_bins); /* > 0 overrides the estimated-bracket half width of pg_sample_top_p */
 int pg_debug_topp_trace(long long* host_out16); /* clock64 stamps of CTA 0 after each phase of the last pg_sample_top_p */
 int pg_debug_topp_retries(void); /* rows whose estimated top-p bracket failed verification (second full pass), cumulative */
+int pg_debug_set_sampler_cluster(int ctas_per_row); /* tuning sweeps: cluster size of pg_sample_top_p_stats (1/2/4/8), 0 = automatic */
+int pg_debug_set_sampler_cluster(int ctas_per_row); /* tuning sweeps: cluster size of pg_sample_top_p_stats (1/2/4/8), 0 = automatic */
 int pg_debug_set_attn_trace(long long* device_buffer); /* same for pg_attention_decode_fused (8 stamps per launch) */
 
 /*
@@ -65,10 +67,10 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
  *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; o_proj uses it to
  *    reset the split-K accumulator of the q/k/v projection once the attention kernel has consumed it.
  *  - stats (PG_EPI_F32 only, no resid / split-K): the lm_head of a decode step (modeling_gemma.py:523-525) also emits, for
- *    every token t and every 32-row vocabulary segment g (g = f / 32), stats[t * stats_ld + g] = (m, s) with
+ *    every token t and every 32-row vocabulary segment g (g = f / 32), stats[g * stats_ld + t] = (m, s) with
  *    m = max logit of the segment and s = sum exp2((logit - m) * stat_c), stat_c = inv_temperature * log2(e) -- temperature
  *    scaling and the max / partition-function passes of softmax + top-p (inference.py:63-66,90-106) folded into the GEMM
- *    epilogue; consumed by pg_sample_top_p_stats / pg_argmax_stats.  stats_ld >= 4 * ceil(features / 128) (float2 units).
+ *    epilogue; consumed by pg_sample_top_p_stats / pg_argmax_stats.  float2 [4 * ceil(features / 128)][stats_ld >= tokens].
  */
 typedef struct PgGemmFusion {
   float* zero_buf;
@@ -203,7 +205,7 @@ int pg_sample_top_p(const float* logits, long long ld, int* out, int* kept_count
  * segment, max logit and sum exp2((x - max) * inv_temperature * log2 e)): row maximum, partition function and the segment
  * masses of the inverse-CDF draw come from 8 bytes per segment instead of passes over the fp32 row; only the top-p
  * verification pass (mass of strictly more probable tokens <= top_p, inference.py:96-100) still reads the logits.
- * stats: float2 [B, stats_ld], stats_ld >= ceil(V / 32); the statistics must have been produced with the SAME
+ * stats: float2 [ceil(V / 32) or more segment rows][stats_ld >= B]; the statistics must have been produced with the SAME
  * inv_temperature.  seed_ptr (device, optional) overrides `seed`, so that a captured CUDA graph serves every seed.
  * A row whose 64 candidates are all rejected (top_p far below the largest probability) yields its most probable token.
  */

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_gemm_bn": [i32],
     "pg_debug_set_attn_trace": [p],
+    "pg_debug_set_sampler_cluster": [i32],
     "pg_debug_topp_retries": [],
     "pg_debug_topp_trace": [p],
     "pg_debug_set_topp_bracket": [i32],
@@ -138,7 +139,7 @@ LOG2E = 1.4426950408889634
 def gemm_fused(x, w, out, *, mode, zero_buf=None, bias=None, split_k=1, stats=None, inv_temperature=1.0):
     """Decode-step (swap-AB, tokens <= 128) GEMM with the chores of pg_gemm_bf16_fused:
       zero_buf   fp32 tensor zero-filled after the dependency wait (split-K accumulator of a later kernel);
-      stats      fp32 [T, nseg, 2] (nseg >= 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
+      stats      fp32 [nseg, T, 2] (nseg = 4 * ceil(F / 128)): lm_head segment statistics (max, sum exp2) at
                  `inv_temperature`, for pg_sample_top_p_stats / pg_argmax_stats (mode EPI_F32 only)."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1 and x.shape[1] == w.shape[1]
     T, K = x.shape
@@ -148,6 +149,7 @@ def gemm_fused(x, w, out, *, mode, zero_buf=None, bias=None, split_k=1, stats=No
         fu.zero_buf, fu.zero_count = zero_buf.data_ptr(), zero_buf.numel()
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 3 and stats.shape[2] == 2 and stats.is_contiguous()
+        assert stats.shape[0] >= 4 * ((w.shape[0] + 127) // 128) and stats.shape[1] >= T
         fu.stats, fu.stats_ld, fu.stat_c = stats.data_ptr(), stats.shape[1], float(inv_temperature) * LOG2E
     check(lib().pg_gemm_bf16_fused(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias), 0, 0, T,
                                    w.shape[0], K, mode, 0, 1.0, 1, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")

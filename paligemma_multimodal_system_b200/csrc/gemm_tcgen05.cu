@@ -62,8 +62,8 @@ struct GemmArgs {
   float* zero_buf;  // zero-filled after the dependency wait (the split-K accumulator of a LATER kernel of the chain)
   long long zero_count;
   // lm_head (PG_EPI_F32, swap): softmax statistics of every 32-row vocabulary segment, for the sampler that follows
-  float2* stats;       // [tokens][stats_ld]: (max logit of the segment, sum exp2((x - max) * stat_c))
-  long long stats_ld;  // segments per token row (>= 4 * ceil(features / 128))
+  float2* stats;       // [segments][stats_ld]: (max logit of the segment, sum exp2((x - max) * stat_c)) per token
+  long long stats_ld;  // tokens per segment row (>= tokens); 4 * ceil(features / 128) segment rows
   float stat_c;        // inv_temperature * log2(e)
 };
 
@@ -150,7 +150,17 @@ PG_DEVINL void swap_tile_epilogue(const GemmArgs& args, uint32_t taddr, int fr, 
 // sampler (sampler.cu) turns them into the row maximum, the partition function and the segment masses of its inverse-CDF
 // draw without touching the 1 MB logit row: temperature scaling + the first two passes of softmax/top-p
 // (inference.py:63-66,90-106) folded into the GEMM that produces the logits (modeling_gemma.py:523-525).
-// Rows past `features` (vocabulary tail) count as -inf; all 32 lanes take part in the shuffles.
+// Both warp reductions are single redux.sync instructions: the maximum on an order-preserving integer key, the sum on
+// 2^-24 fixed point (every term is in [0, 1] and the maximum contributes exactly 2^24, so the sum of 32 terms is exact to
+// 32 * 2^-25 relative) -- five-step shuffle butterflies for 64 columns x 2 quantities per tile made the epilogue, not the
+// weight stream, pace the kernel (measured: 176 -> 195 us).  Rows past `features` (vocabulary tail) count as -inf; all 32
+// lanes take part.  Layout: stats[segment][token] (one coalesced 8-byte-per-lane store per 16 columns).
+PG_DEVINL uint32_t ordered_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+PG_DEVINL float ordered_key_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
 template <int BN>
 PG_DEVINL void swap_tile_epilogue_f32_stats(const GemmArgs& args, uint32_t taddr, int fr, int j_base, int seg, int lane) {
   const bool f_ok = fr < args.features;
@@ -158,6 +168,7 @@ PG_DEVINL void swap_tile_epilogue_f32_stats(const GemmArgs& args, uint32_t taddr
   const float scale = args.scale, c = args.stat_c;
   const float bias_s = (args.bias != nullptr && f_ok) ? __ldg(args.bias + fr) * scale : 0.f;
   float* dst = reinterpret_cast<float*>(args.out) + static_cast<long long>(j_base) * args.ldo + fr;
+  float2* srow = args.stats + static_cast<long long>(seg) * args.stats_ld + j_base;
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 16) {
     if (c0 >= nvalid) break;  // warp-uniform
@@ -170,15 +181,12 @@ PG_DEVINL void swap_tile_epilogue_f32_stats(const GemmArgs& args, uint32_t taddr
     for (int i = 0; i < 16; ++i) {
       const float x = f_ok ? fmaf(__uint_as_float(r[i]), scale, bias_s) : -INFINITY;
       if (i < n && f_ok) dst[static_cast<long long>(c0 + i) * args.ldo] = x;
-      float m = x;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      float e = x == -INFINITY ? 0.f : exp2f((x - m) * c);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-      if (lane == i) { keep_m = m; keep_s = e; }
+      const float m = ordered_key_inv(__reduce_max_sync(0xffffffffu, ordered_key(x)));
+      const float e = x == -INFINITY ? 0.f : exp2f((x - m) * c);
+      const uint32_t sum = __reduce_add_sync(0xffffffffu, __float2uint_rn(e * 16777216.f));
+      if (lane == i) { keep_m = m; keep_s = static_cast<float>(sum) * (1.0f / 16777216.f); }
     }
-    if (lane < n) args.stats[static_cast<long long>(j_base + c0 + lane) * args.stats_ld + seg] = make_float2(keep_m, keep_s);
+    if (lane < n) srow[c0 + lane] = make_float2(keep_m, keep_s);
   }
 }
 
@@ -813,7 +821,7 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
     }
     if (fu->stats != nullptr) {
       // plain fp32 logits + bias only (no residual, no in-kernel norm factor), one CTA per output tile
-      if (mode != PG_EPI_F32 || resid != nullptr || split_k != 1 || fu->stats_ld < 4ll * ((features + BM - 1) / BM) ||
+      if (mode != PG_EPI_F32 || resid != nullptr || split_k != 1 || fu->stats_ld < tokens ||
           (reinterpret_cast<uintptr_t>(fu->stats) & 7) || !(fu->stat_c > 0.f))
         return PG_ERR_ARG;
       a.stats = static_cast<float2*>(fu->stats); a.stats_ld = fu->stats_ld; a.stat_c = fu->stat_c;

@@ -118,6 +118,27 @@ PG_DEVINL float block_reduce_sum(float v, BlockRed& r) {
   return r.f[32];
 }
 
+// four block-wide sums in one exchange (the verification pass of the rejection samplers carries four candidates)
+PG_DEVINL void block_reduce_sum4(float (&v)[4], float (*buf)[4], float (&out)[4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __syncthreads();  // protect `buf` from its previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) buf[warp][k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += buf[w][k];  // same order in every thread: identical results block-wide
+    out[k] = t;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // top-p sampler: one thread-block CLUSTER of R CTAs (1024 threads each) per row; each warp owns a contiguous segment of
 // the row; cross-CTA reductions and histogram merges go through distributed shared memory.
@@ -764,6 +785,7 @@ struct StatShared {
   float z;
   int accepted;
   int max_seg;          // lowest segment holding the row maximum (fallback: the most probable token is always kept)
+  float red4[32][4];
 };
 
 __global__ void __launch_bounds__(1024) sample_top_p_stats_kernel(const float* __restrict__ logits, long long ld,
@@ -778,7 +800,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_stats_kernel(const float* _
   const int row_idx = blockIdx.x / R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ row = logits + row_idx * ld;
-  const float2* __restrict__ st = stats + row_idx * stats_ld;
+  const float2* __restrict__ st = stats + row_idx;  // segment g of this row: st[g * stats_ld]
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
   auto remote = [&](auto* ptr, int r) { return cluster.map_shared_rank(ptr, r); };
@@ -792,7 +814,7 @@ __global__ void __launch_bounds__(1024) sample_top_p_stats_kernel(const float* _
   float mx = -INFINITY;
 #pragma unroll
   for (int k = 0; k < kStatMaxPer; ++k) {
-    my[k] = (k < per && s_lo + k < s_hi) ? __ldcg(st + s_lo + k) : make_float2(-INFINITY, 0.f);
+    my[k] = (k < per && s_lo + k < s_hi) ? __ldcg(st + (s_lo + k) * stats_ld) : make_float2(-INFINITY, 0.f);
     if (my[k].y > 0.f) mx = fmaxf(mx, my[k].x);
   }
   if (tid == 0) { S.accepted = -1; S.max_seg = 0x7fffffff; }
@@ -917,18 +939,18 @@ __global__ void __launch_bounds__(1024) sample_top_p_stats_kernel(const float* _
     cluster.sync();
     // ---- mass strictly above each candidate ----
     const float cx0 = S.cand_x[0], cx1 = S.cand_x[1], cx2 = S.cand_x[2], cx3 = S.cand_x[3];
-    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    float mm[4] = {0.f, 0.f, 0.f, 0.f};
     for_each_in_segment(row, e_lo, e_hi, vec, lane, [&](float x, int) {
       const float w = w_of(x);
-      m0 += x > cx0 ? w : 0.f;
-      m1 += x > cx1 ? w : 0.f;
-      m2 += x > cx2 ? w : 0.f;
-      m3 += x > cx3 ? w : 0.f;
+      mm[0] += x > cx0 ? w : 0.f;
+      mm[1] += x > cx1 ? w : 0.f;
+      mm[2] += x > cx2 ? w : 0.f;
+      mm[3] += x > cx3 ? w : 0.f;
     });
     {
-      const float t0 = block_reduce_sum(m0, S.red), t1 = block_reduce_sum(m1, S.red);
-      const float t2 = block_reduce_sum(m2, S.red), t3 = block_reduce_sum(m3, S.red);
-      if (tid == 0) { S.mass[0] = t0; S.mass[1] = t1; S.mass[2] = t2; S.mass[3] = t3; }
+      float tot[4];
+      block_reduce_sum4(mm, S.red4, tot);
+      if (tid == 0) { S.mass[0] = tot[0]; S.mass[1] = tot[1]; S.mass[2] = tot[2]; S.mass[3] = tot[3]; }
     }
     cluster.sync();
     if (tid == 0) {
@@ -969,13 +991,13 @@ __global__ void __launch_bounds__(256) argmax_stats_kernel(const float* __restri
   __shared__ float sv[8];
   __shared__ int si[8];
   const float* __restrict__ row = logits + blockIdx.x * ld;
-  const float2* __restrict__ st = stats + blockIdx.x * stats_ld;
+  const float2* __restrict__ st = stats + blockIdx.x;  // segment g of this row: st[g * stats_ld]
   griddep_wait();
   if (threadIdx.x == 0) griddep_launch_dependents();
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int g = threadIdx.x; g < nseg; g += 256) {
-    const float2 v = __ldcg(st + g);
+    const float2 v = __ldcg(st + g * stats_ld);
     if (v.y > 0.f && (v.x > best || (v.x == best && g < bi))) { best = v.x; bi = g; }
   }
   auto merge = [&](float ov, int oi) { if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; } };
@@ -1054,9 +1076,16 @@ extern "C" int pg_sample_top_p(const float* logits, long long ld, int* out, int*
              : PG_ERR_CUDA;
 }
 
+static int g_stats_cluster = 0;  // tuning sweeps only: forces the cluster size of pg_sample_top_p_stats (0 = automatic)
+extern "C" int pg_debug_set_sampler_cluster(int r) {
+  if (r != 0 && r != 1 && r != 2 && r != 4 && r != 8) return PG_ERR_ARG;
+  g_stats_cluster = r;
+  return 0;
+}
+
 extern "C" int pg_argmax_stats(const float* logits, long long ld, const void* stats, long long stats_ld, int* out, int B, int V,
                                void* stream) {
-  if (B <= 0 || V <= 0 || stats == nullptr || stats_ld < (V + 31) / 32) return PG_ERR_ARG;
+  if (B <= 0 || V <= 0 || stats == nullptr || stats_ld < B) return PG_ERR_ARG;
   return launch_kernel(argmax_stats_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), logits, ld,
                        static_cast<const float2*>(stats), stats_ld, (V + 31) / 32, out, V) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
@@ -1066,8 +1095,12 @@ extern "C" int pg_sample_top_p_stats(const float* logits, long long ld, const vo
                                      const unsigned long long* seed_ptr, const int* step_ptr, void* stream) {
   if (B <= 0 || V <= 0 || !(inv_temperature > 0.f) || !(top_p >= 0.f) || stats == nullptr) return PG_ERR_ARG;
   const int nseg = (V + 31) / 32;
-  if (stats_ld < nseg) return PG_ERR_ARG;
-  int R = V >= 65536 ? 2 : 1;
+  if (stats_ld < B) return PG_ERR_ARG;
+  // CTAs per row: the verification pass is split over the cluster, every split costs cluster barriers (~1.5 us each, four
+  // per round); fill the GPU once when the batch alone does not
+  int R = 1;
+  if (g_stats_cluster > 0) R = g_stats_cluster;
+  else if (V >= 65536) { while (R < 8 && 2 * R * B <= pg::num_sms()) R *= 2; }
   while (nseg > kStatMaxPer * R * 1024 && R < 8) R *= 2;
   if (nseg > kStatMaxPer * R * 1024) return PG_ERR_ARG;  // > 2 M-token vocabularies: use pg_sample_top_p
   cudaLaunchConfig_t cfg = {};

@@ -357,7 +357,7 @@ class GemmaForCausalLM(nn.Module):
         shapes = dict(h=((B, D), torch.float32), hn=((B, D), torch.bfloat16), qkv=((B, (Hq + 2 * Hkv) * dh), torch.float32),
                       att=((B, Hq * dh), torch.bfloat16), mid=((B, F), torch.bfloat16), logits=((B, V), torch.float32),
                       # lm_head epilogue: (max, sum exp2) of every 32-token vocabulary segment, read by the samplers
-                      stats=((B, 4 * ((V + 127) // 128), 2), torch.float32))
+                      stats=((4 * ((V + 127) // 128), B, 2), torch.float32))
 
         def make(shp, dt, name):
             return (torch.zeros if name == "qkv" else torch.empty)(*shp, device="cuda", dtype=dt)

@@ -106,7 +106,7 @@ graph_time("LAYER (7 launches)", layer, layer_bytes)
 graph_time("LAYER, down split 37", lambda i: layer(i, sd=37), layer_bytes)
 
 # ---- lm_head and the samplers (per decode step, not per layer: one launch per graph node, 18 nodes) ----
-stats = torch.empty(B, 4 * ((V + 127) // 128), 2, device=dev)
+stats = torch.empty(4 * ((V + 127) // 128), B, 2, device=dev)
 nxt = torch.empty(B, device=dev, dtype=torch.int32)
 step = torch.zeros(1, device=dev, dtype=torch.int32)
 graph_time("lm_head (fp32 logits + bias)", lambda i: _lib.gemm(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, swap=1), V * D * 2, reps=1)
@@ -115,6 +115,10 @@ logits.normal_(0, 2.0)
 _lib.gemm_fused(hn, head_w, logits, mode=_lib.EPI_F32, bias=head_b, stats=stats, inv_temperature=1.25)
 graph_time("top-p, 3 passes over the row (pg_sample_top_p)", lambda i: _lib.check(L.pg_sample_top_p(logits.data_ptr(), V, nxt.data_ptr(), 0, B, V, 1.25, 0.9, 1, step.data_ptr(), _lib.stream()), "s"), B * V * 4, reps=3)
 graph_time("top-p from statistics (pg_sample_top_p_stats)", lambda i: _lib.check(L.pg_sample_top_p_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, 1.25, 0.9, 1, 0, step.data_ptr(), _lib.stream()), "s"), B * V * 4, reps=3)
+for r in (1, 2):
+    L.pg_debug_set_sampler_cluster(r)
+    graph_time(f"top-p from statistics, {r} CTA(s) per row", lambda i: _lib.check(L.pg_sample_top_p_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, 1.25, 0.9, 1, 0, step.data_ptr(), _lib.stream()), "s"), B * V * 4, reps=3)
+L.pg_debug_set_sampler_cluster(0)
 graph_time("argmax over the row (pg_argmax)", lambda i: _lib.check(L.pg_argmax(logits.data_ptr(), V, nxt.data_ptr(), B, V, _lib.stream()), "a"), B * V * 4, reps=3)
 graph_time("argmax from statistics (pg_argmax_stats)", lambda i: _lib.check(L.pg_argmax_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], nxt.data_ptr(), B, V, _lib.stream()), "a"), B * V * 4, reps=3)
 

@@ -129,7 +129,8 @@ def test_top_p_rejection_sampler_chi2_large_vocab(sigma, top_p):
 # samplers fed by the lm_head epilogue's segment statistics (pg_gemm_bf16_fused stats -> pg_*_stats)
 # ---------------------------------------------------------------------------------------------------------------------
 def _torch_stats(logits, inv_temp, nseg=None):
-    """(max, sum exp2((x - max) * inv_temp * log2 e)) of every 32-token segment, as the GEMM epilogue defines them."""
+    """(max, sum exp2((x - max) * inv_temp * log2 e)) of every 32-token segment, as the GEMM epilogue defines them; laid out
+    [segment, row, 2] like the epilogue writes them."""
     B, V = logits.shape
     n = (V + 31) // 32
     pad = torch.full((B, n * 32), float("-inf"), device=logits.device)
@@ -137,9 +138,9 @@ def _torch_stats(logits, inv_temp, nseg=None):
     seg = pad.view(B, n, 32)
     m = seg.max(-1).values
     s = torch.exp2((seg - m[..., None]) * (inv_temp * 1.4426950408889634)).sum(-1)
-    out = torch.zeros(B, nseg or n, 2, device=logits.device)
+    out = torch.zeros(nseg or n, B, 2, device=logits.device)
     out[:, :, 0] = float("-inf")
-    out[:, :n, 0], out[:, :n, 1] = m, s
+    out[:n, :, 0], out[:n, :, 1] = m.t(), s.t()
     return out.contiguous()
 
 
@@ -155,7 +156,7 @@ def test_lm_head_epilogue_statistics(T, V, K):
     inv_temp = 1.25
     nseg = 4 * ((V + 127) // 128)
     logits = torch.full((T, V), float("nan"), device="cuda")
-    stats = torch.full((T, nseg, 2), float("nan"), device="cuda")
+    stats = torch.full((nseg, T, 2), float("nan"), device="cuda")
     _lib.gemm_fused(x, w, logits, mode=_lib.EPI_F32, bias=bias, stats=stats, inv_temperature=inv_temp)
     plain = torch.empty(T, V, device="cuda")
     _lib.gemm(x, w, plain, mode=_lib.EPI_F32, bias=bias, swap=1)
@@ -163,7 +164,7 @@ def test_lm_head_epilogue_statistics(T, V, K):
     assert torch.equal(logits, plain), "the statistics epilogue must write the very same logits"
     ref = _torch_stats(logits, inv_temp, nseg)
     assert torch.equal(stats[..., 0], ref[..., 0]), "segment maxima are exact"
-    assert (stats[..., 1] - ref[..., 1]).abs().max().item() <= 2e-5 * 32
+    assert (stats[..., 1] - ref[..., 1]).abs().max().item() <= 2e-5 * 32  # (2^-24 fixed-point sum of <= 32 terms in [0, 1])
     assert not torch.isnan(stats).any()
 
 
@@ -222,7 +223,7 @@ def test_top_p_from_statistics_chi2(V, sigma, top_p):
     probs = torch.softmax(row.double() / temp, -1)
     keep = _kept_mask(probs, top_p)[0]
     pk = (probs[0] * keep) / (probs[0] * keep).sum()
-    stats = _torch_stats(row, 1.0 / temp).repeat(draws, 1, 1).contiguous()
+    stats = _torch_stats(row, 1.0 / temp).repeat(1, draws, 1).contiguous()
     out = torch.empty(draws, device="cuda", dtype=torch.int32)
     step = torch.zeros(1, device="cuda", dtype=torch.int32)
     _lib.check(_lib.lib().pg_sample_top_p_stats(logits.data_ptr(), V, stats.data_ptr(), stats.shape[1], out.data_ptr(), draws, V,
