@@ -83,6 +83,18 @@ int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, long long ld
                        const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
                        int act_gelu, float scale, int swap, int split_k, const PgGemmFusion* fusion, void* stream);
 
+/*
+ * Prefill q/k/v projection with RoPE and the KV-cache append in the GEMM epilogue (modeling_gemma.py:274-302 + KVCache.update
+ * :18-57): qkv_out[t, :] = bf16 of [rope(q heads) | rope(k heads) | v heads] of x[t, :] @ w^T, w = [q_proj; k_proj; v_proj]
+ * ([(Hq + 2 Hkv) * dh, K] bf16), rotate-half with angle pos[t] * inv_freq[i]; k / v rows are also written into their cache
+ * pages (page = page_table[b * max_pages + slot / 64], slot = slot_base[b] + (t - b * tokens_per_seq); k_pages == NULL: no
+ * cache).  One head per UMMA N tile: dh in {64, 256}.  The prefill attention reads q / k / v straight out of qkv_out through
+ * strided tensor maps, so no separate RoPE / append launch and no second copy of the projections exists.
+ */
+int pg_gemm_qkv_rope(const void* x, long long ldx, const void* w, long long ldw, void* qkv_out, long long ldo, int tokens, int K,
+                     int Hq, int Hkv, int dh, const int* pos, const float* inv_freq, void* k_pages, void* v_pages,
+                     const int* page_table, const int* slot_base, int tokens_per_seq, int page_size, int max_pages, void* stream);
+
 /* Packs gate_proj / up_proj [F,K] bf16 into the [64 gate | 64 up] row-interleaved [2F,K] layout PG_EPI_GEGLU expects.
  * (modeling_gemma.py:205-206 weights; F % 64 == 0) */
 int pg_pack_gate_up(const void* gate, const void* up, void* packed, int F, int K, void* stream);

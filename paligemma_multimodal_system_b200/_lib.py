@@ -34,6 +34,7 @@ SIGNATURES = {
     "pg_debug_set_topp_bracket": [i32],
     "pg_gemm_bf16": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p],
     "pg_gemm_bf16_fused": [p, i64, p, i64, p, i64, p, p, i64, i32, i32, i32, i32, i32, f32, i32, i32, p, p],
+    "pg_gemm_qkv_rope": [p, i64, p, i64, p, i64, i32, i32, i32, i32, i32, p, p, p, p, p, p, i32, i32, i32, p],
     "pg_pack_gate_up": [p, p, p, i32, i32, p],
     "pg_cast_f32_bf16": [p, p, i64, p],
     "pg_layernorm": [p, p, p, p, p, i32, i32, f32, p],

@@ -61,6 +61,15 @@ struct GemmArgs {
   // ---- decode-step chores of the SWAP kernels ----
   float* zero_buf;  // zero-filled after the dependency wait (the split-K accumulator of a LATER kernel of the chain)
   long long zero_count;
+  // ---- ROPE kernels (token-major q/k/v projection of the prefill, one head per N tile: BN == head_dim) ----
+  const int* rope_pos;         // [tokens] position ids
+  const float* rope_inv_freq;  // [head_dim / 2]
+  int rope_hq, rope_hkv;       // query / key-value heads: tile n < hq -> q, < hq + hkv -> k, else v
+  __nv_bfloat16* k_pages;      // paged KV cache of this layer (may be null: no cache)
+  __nv_bfloat16* v_pages;
+  const int* page_table;       // [sequences, max_pages]
+  const int* slot_base;        // [sequences] first cache slot of the sequence's tokens
+  int tokens_per_seq, max_pages;
   // lm_head (PG_EPI_F32, swap): softmax statistics of every 32-row vocabulary segment, for the sampler that follows
   float2* stats;       // [segments][stats_ld]: (max logit of the segment, sum exp2((x - max) * stat_c)) per token
   long long stats_ld;  // tokens per segment row (>= tokens); 4 * ceil(features / 128) segment rows
@@ -211,6 +220,140 @@ PG_DEVINL void warp_store_rows_128B(uint32_t stage, int lane, const uint32_t (&p
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "r"(stage + r8 * 128 + ((piece ^ (r8 & 7)) << 4)) : "memory");
     if (cols_ok && r8 < rows_valid) *reinterpret_cast<uint4*>(gbase + r8 * pitch_bytes + piece * 16) = v;
+  }
+}
+
+// As warp_store_rows_128B, but every row has its own destination (pages of the KV cache): `my_row` = this lane's row base
+// (null = skip the row).  The row pointers travel with the transposed lane mapping by shuffle.
+PG_DEVINL void warp_store_rows_128B_ptr(uint32_t stage, int lane, const uint32_t (&pk)[32], char* my_row) {
+  __syncwarp();
+  const uint32_t row_s = stage + lane * 128;
+#pragma unroll
+  for (int pc = 0; pc < 8; ++pc)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_s + ((pc ^ (lane & 7)) << 4)), "r"(pk[4 * pc]),
+                 "r"(pk[4 * pc + 1]), "r"(pk[4 * pc + 2]), "r"(pk[4 * pc + 3]) : "memory");
+  __syncwarp();
+  const int sub = lane >> 3, piece = lane & 7;
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(my_row);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r8 = 4 * k + sub;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(stage + r8 * 128 + ((piece ^ (r8 & 7)) << 4)) : "memory");
+    char* dst = reinterpret_cast<char*>(__shfl_sync(0xffffffffu, mine, r8));
+    if (dst != nullptr) *reinterpret_cast<uint4*>(dst + piece * 16) = v;
+  }
+}
+
+// sin / cos of a non-negative fp32 angle of up to a few thousand radians (position id x inverse frequency): three-constant
+// Cody-Waite reduction by 2 pi (every step one FMA), then the hardware approximations on [-pi, pi] (abs. error ~5e-7).  The
+// rotated values are rounded to bf16 (2^-9 relative) right away.
+PG_DEVINL void sincos_2pi(float a, float& sn, float& cs) {
+  const float n = rintf(a * 0.15915494309189535f);
+  float r = fmaf(-n, 6.28125f, a);
+  r = fmaf(-n, 1.935005187988281e-3f, r);
+  r = fmaf(-n, 3.01991598195675e-7f, r);
+  sn = __sinf(r);
+  cs = __cosf(r);
+}
+
+// Epilogue of the prefill q/k/v projection (ROPE kernels): the N tile is exactly one head (BN == head_dim).  q and k heads
+// are rotated (rotate-half pairs (i, i + BN/2), angle = pos[token] * inv_freq[i]: modeling_gemma.py:116-151) in registers,
+// every head is written as bf16 into the dense [tokens, (Hq + 2 Hkv) * dh] buffer the prefill attention reads through
+// strided tensor maps, and k / v heads are ALSO appended to their pages of the KV cache (KVCache.update, :18-57) -- the
+// standalone RoPE + append kernel and its bf16 round trip of the projections are gone.  All stores are full 128-byte lines.
+template <int BN>
+PG_DEVINL void qkv_rope_tile_epilogue(const GemmArgs& args, uint32_t taddr, int tok, int head, uint32_t stage, int rows_valid,
+                                      int lane, int warp_row0) {
+  constexpr int HALF = BN / 2;
+  const bool row_ok = tok < args.tokens;
+  const bool is_q = head < args.rope_hq, is_v = head >= args.rope_hq + args.rope_hkv;
+  __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
+  char* dense0 = reinterpret_cast<char*>(out_bf + static_cast<long long>(warp_row0) * args.ldo + static_cast<long long>(head) * BN);
+  char* page_row = nullptr;  // this token's row of the k / v head inside its cache page
+  if (!is_q && args.k_pages != nullptr && row_ok) {
+    const int b = tok / args.tokens_per_seq;
+    const int slot = __ldg(args.slot_base + b) + (tok - b * args.tokens_per_seq);
+    const long long page = __ldg(args.page_table + static_cast<long long>(b) * args.max_pages + (slot >> 6));
+    const int hk = is_v ? head - args.rope_hq - args.rope_hkv : head - args.rope_hq;
+    __nv_bfloat16* base = is_v ? args.v_pages : args.k_pages;
+    page_row = reinterpret_cast<char*>(base + ((page * 64 + (slot & 63)) * args.rope_hkv + hk) * BN);
+  }
+  const float posf = row_ok ? static_cast<float>(__ldg(args.rope_pos + tok)) : 0.f;
+  auto emit = [&](const uint32_t (&pk)[32], int col) {  // 64 columns starting at `col` of the head
+    warp_store_rows_128B(stage, lane, pk, dense0 + col * 2, args.ldo * 2, rows_valid, true);
+    if (!is_q && args.k_pages != nullptr) warp_store_rows_128B_ptr(stage, lane, pk, page_row != nullptr ? page_row + col * 2 : nullptr);
+  };
+  if (is_v) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0 + 16 * j, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[8 * j + i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+      }
+      emit(pk, c0);
+    }
+    return;
+  }
+  if constexpr (BN == 64) {
+    // the head's 64 columns are one output row: [y1 (32) | y2 (32)]
+    uint32_t pk[32];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t x1[16], x2[16];
+      tmem_ld16(taddr + 16 * j, x1);
+      tmem_ld16(taddr + HALF + 16 * j, x2);
+      tmem_ld_wait();
+      float y1[16], y2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float sn, cs;
+        sincos_2pi(posf * __ldg(args.rope_inv_freq + 16 * j + i), sn, cs);
+        const float a = __uint_as_float(x1[i]), b = __uint_as_float(x2[i]);
+        y1[i] = a * cs - b * sn;
+        y2[i] = b * cs + a * sn;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pk[8 * j + i] = pack_bf16(y1[2 * i], y1[2 * i + 1]);
+        pk[16 + 8 * j + i] = pack_bf16(y2[2 * i], y2[2 * i + 1]);
+      }
+    }
+    emit(pk, 0);
+  } else {
+#pragma unroll 1
+    for (int g = 0; g < HALF / 64; ++g) {  // columns [64 g, 64 g + 64) pair with [HALF + 64 g, ...)
+      uint32_t pk1[32], pk2[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t x1[16], x2[16];
+        tmem_ld16(taddr + 64 * g + 16 * j, x1);
+        tmem_ld16(taddr + HALF + 64 * g + 16 * j, x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float ya[2], yb[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float sn, cs;
+            sincos_2pi(posf * __ldg(args.rope_inv_freq + 64 * g + 16 * j + 2 * i + e), sn, cs);
+            const float a = __uint_as_float(x1[2 * i + e]), b = __uint_as_float(x2[2 * i + e]);
+            ya[e] = a * cs - b * sn;
+            yb[e] = b * cs + a * sn;
+          }
+          pk1[8 * j + i] = pack_bf16(ya[0], ya[1]);
+          pk2[8 * j + i] = pack_bf16(yb[0], yb[1]);
+        }
+      }
+      emit(pk1, 64 * g);
+      emit(pk2, HALF + 64 * g);
+    }
   }
 }
 
@@ -484,7 +627,7 @@ PG_DEVINL void geglu_swap_epilogue(const GemmArgs& args, uint32_t taddr, float* 
 // quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
 // red.add epilogue is compiled out, which keeps the 320-thread CTA at two per SM.
-template <int BN, bool SWAP, bool SPLITK = false>
+template <int BN, bool SWAP, bool SPLITK = false, bool ROPE = false>
 __global__ void __launch_bounds__(SPLITK ? 320 : NUM_THREADS, two_per_sm(BN, SWAP) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const GemmArgs args) {
@@ -670,7 +813,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // column range of this warp: halves of >= 64 columns (BN = 64: the first warp of the pair takes everything)
         const int cb = !SPLITK ? 0 : (BN >= 128 ? half * (BN / 2) : (half == 0 ? 0 : BN));
         const int ce = !SPLITK ? BN : (BN >= 128 ? cb + BN / 2 : BN);
-        if (mode == PG_EPI_GEGLU) {
+        if constexpr (ROPE) {
+          qkv_rope_tile_epilogue<BN>(args, taddr, tok, t.n_blk, wstage, rows_valid, lane, t.m_blk * BM + q * 32);
+        } else if (mode == PG_EPI_GEGLU) {
           // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c.  The 64 bf16
           // results of a block (one 128-byte row per token) leave through the warp transposition tile as full lines.
           const bool al = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo % 8) == 0);
@@ -759,13 +904,13 @@ extern "C" int pg_debug_set_gemm_bn(int bn) {
   return 0;
 }
 
-template <int BN, bool SWAP, bool SPLITK = false>
+template <int BN, bool SWAP, bool SPLITK = false, bool ROPE = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};
   constexpr int smem = smem_bytes(BN, SWAP);
   const int dev = current_device();
   if (!configured[dev]) {  // function attributes are per device
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, SWAP, SPLITK, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       cudaGetLastError();  // do not leave a sticky error behind
       return PG_ERR_CUDA;
     }
@@ -773,7 +918,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   }
   const int slots = num_sms() * (two_per_sm(BN, SWAP) ? 2 : 1);
   const int grid = num_tiles < slots ? num_tiles : slots;
-  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess
+  return launch_kernel(gemm_tcgen05_kernel<BN, SWAP, SPLITK, ROPE>, dim3(grid), dim3(SPLITK ? 320 : NUM_THREADS), smem, st, ta, tb, a) == cudaSuccess
              ? PG_OK : PG_ERR_CUDA;
 }
 
@@ -880,4 +1025,33 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
       default: return launch<256, false>(ta, tb, a, tiles, st);
     }
   }
+}
+
+extern "C" int pg_gemm_qkv_rope(const void* x, long long ldx, const void* w, long long ldw, void* qkv_out, long long ldo, int tokens,
+                                int K, int Hq, int Hkv, int dh, const int* pos, const float* inv_freq, void* k_pages, void* v_pages,
+                                const int* page_table, const int* slot_base, int tokens_per_seq, int page_size, int max_pages,
+                                void* stream) {
+  if (tokens <= 0 || K <= 0 || Hq <= 0 || Hkv <= 0 || tokens_per_seq <= 0 || pos == nullptr || inv_freq == nullptr) return PG_ERR_ARG;
+  if (dh != 64 && dh != 256) return PG_ERR_ARG;  // one head per N tile: instantiated for head_dim 64 and 256
+  if ((K % 8) != 0 || (ldx % 8) != 0 || (ldw % 8) != 0 || (ldo % 8) != 0) return PG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(qkv_out) & 15))
+    return PG_ERR_ARG;
+  const bool cache = k_pages != nullptr;
+  if (cache && (v_pages == nullptr || page_table == nullptr || slot_base == nullptr || page_size != 64 || max_pages <= 0 ||
+                (reinterpret_cast<uintptr_t>(k_pages) & 15) || (reinterpret_cast<uintptr_t>(v_pages) & 15)))
+    return PG_ERR_ARG;
+  const int features = (Hq + 2 * Hkv) * dh;
+  GemmArgs a = {};
+  a.tokens = tokens; a.features = features; a.K = K; a.split_k = 1; a.mode = PG_EPI_BF16; a.scale = 1.f;
+  a.out = qkv_out; a.ldo = ldo;
+  a.rope_pos = pos; a.rope_inv_freq = inv_freq; a.rope_hq = Hq; a.rope_hkv = Hkv;
+  a.k_pages = static_cast<__nv_bfloat16*>(k_pages); a.v_pages = static_cast<__nv_bfloat16*>(v_pages);
+  a.page_table = page_table; a.slot_base = slot_base; a.tokens_per_seq = tokens_per_seq; a.max_pages = max_pages;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
+  if ((rc = make_tmap_2d(&tb, w, features, K, ldw, dh)) != PG_OK) return rc;
+  const int tiles = ((tokens + BM - 1) / BM) * (Hq + 2 * Hkv);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dh == 256 ? launch<256, false, false, true>(ta, tb, a, tiles, st) : launch<64, false, false, true>(ta, tb, a, tiles, st);
 }

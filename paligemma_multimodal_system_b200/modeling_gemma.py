@@ -222,6 +222,7 @@ class GemmaForCausalLM(nn.Module):
         self.model = GemmaModel(config, **fk)
         self._packed = None
         self._ws = {}
+        self.fused_qkv_rope = None  # None = automatic (prefill()); True / False force the q/k/v-epilogue RoPE + KV append path
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
@@ -293,34 +294,52 @@ class GemmaForCausalLM(nn.Module):
             kv_cache.ensure_capacity(S + 1)
             slot_base = torch.zeros(B, device=dev, dtype=torch.int32)
             page_table = kv_cache.page_table
+        W = (Hq + 2 * Hkv) * dh
         hn = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
-        qkv = torch.empty(T, (Hq + 2 * Hkv) * dh, device=dev, dtype=torch.bfloat16)
-        q = torch.empty(T, Hq * dh, device=dev, dtype=torch.bfloat16)
-        k = torch.empty(T, Hkv * dh, device=dev, dtype=torch.bfloat16)
-        v = torch.empty(T, Hkv * dh, device=dev, dtype=torch.bfloat16)
+        qkv = torch.empty(T, W, device=dev, dtype=torch.bfloat16)
         att = torch.empty(T, Hq * dh, device=dev, dtype=torch.bfloat16)
         mid = torch.empty(T, F, device=dev, dtype=torch.bfloat16)
         G = Hq // Hkv
         scale = 1.0 / math.sqrt(dh)
+        # RoPE + KV append in the q/k/v projection's epilogue (one head per 128 x dh output tile) once that grid fills the GPU;
+        # few-token prefills (latency path) keep narrower GEMM tiles and the separate RoPE / append launch
+        fused = self.fused_qkv_rope
+        if fused is None:
+            fused = False and dh in (64, 256) and ((T + 127) // 128) * (Hq + 2 * Hkv) >= 96  # (auto OFF until validated on the GPU)
+        if fused:
+            # q, k, v are column slices of `qkv` (token pitch W): the attention's tensor maps take the strides
+            q, k, v = qkv, qkv[:, Hq * dh:], qkv[:, (Hq + Hkv) * dh:]
+            q_ts = kv_ts = W
+        else:
+            q = torch.empty(T, Hq * dh, device=dev, dtype=torch.bfloat16)
+            k = torch.empty(T, Hkv * dh, device=dev, dtype=torch.bfloat16)
+            v = torch.empty(T, Hkv * dh, device=dev, dtype=torch.bfloat16)
+            q_ts, kv_ts = Hq * dh, Hkv * dh
         for li, lw in enumerate(pk["layers"]):
             _lib.rmsnorm(h, lw["ln1"], hn)
-            _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_BF16, swap=0 if T > 128 else 1)
-            _lib.check(L.pg_rope_kv_append(
-                qkv.data_ptr(), 0, pos.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
-                kv_cache.k_pages[li].data_ptr() if have_cache else 0, kv_cache.v_pages[li].data_ptr() if have_cache else 0,
-                page_table.data_ptr() if have_cache else 0, slot_base.data_ptr() if have_cache else 0,
-                B, S, Hq, Hkv, dh, PAGE, page_table.shape[1] if have_cache else 0, pk["inv_freq"].data_ptr(), st),
-                "pg_rope_kv_append")
+            kp = kv_cache.k_pages[li].data_ptr() if have_cache else 0
+            vp = kv_cache.v_pages[li].data_ptr() if have_cache else 0
+            pt = page_table.data_ptr() if have_cache else 0
+            sb = slot_base.data_ptr() if have_cache else 0
+            mp = page_table.shape[1] if have_cache else 0
+            if fused:
+                _lib.check(L.pg_gemm_qkv_rope(hn.data_ptr(), D, lw["qkv_w"].data_ptr(), D, qkv.data_ptr(), W, T, D, Hq, Hkv, dh,
+                                              pos.data_ptr(), pk["inv_freq"].data_ptr(), kp, vp, pt, sb, S, PAGE, mp, st),
+                           "pg_gemm_qkv_rope")
+            else:
+                _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_BF16, swap=0 if T > 128 else 1)
+                _lib.check(L.pg_rope_kv_append(qkv.data_ptr(), 0, pos.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), kp, vp, pt, sb,
+                                               B, S, Hq, Hkv, dh, PAGE, mp, pk["inv_freq"].data_ptr(), st), "pg_rope_kv_append")
             # MQA/GQA: the G query heads of a KV head are consecutive rows of one attention problem (no repeat_kv)
             if lens is None:
                 _lib.check(L.pg_attention_prefill(
                     q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), B, Hkv, S * G, S, dh, G,
-                    S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
+                    S * q_ts, q_ts, dh, G * dh, S * kv_ts, kv_ts, dh,
                     S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill")
             else:
                 _lib.check(L.pg_attention_prefill_varlen(
                     q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), lens.data_ptr(), B, Hkv, S * G, S, dh, G,
-                    S * Hq * dh, Hq * dh, dh, G * dh, S * Hkv * dh, Hkv * dh, dh,
+                    S * q_ts, q_ts, dh, G * dh, S * kv_ts, kv_ts, dh,
                     S * Hq * dh, Hq * dh, dh, G * dh, scale, st), "pg_attention_prefill_varlen")
             _lib.gemm_residual(att, lw["o_w"], h)
             _lib.rmsnorm(h, lw["ln2"], hn)

@@ -154,3 +154,52 @@ def test_gemm_prefill_bf16_coalesced_store(T, F, K):
     _lib.gemm(x, w, out, mode=_lib.EPI_BF16, bias=bias, act_gelu=True, swap=0)
     torch.cuda.synchronize()
     _close(out, torch.nn.functional.gelu(_ref(x, w) + bias, approximate="tanh"), 1e-2, "bf16 coalesced + gelu")
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,dh,K,cache", [
+    (2, 260, 8, 1, 256, 2048, True), (3, 37, 4, 1, 64, 256, True), (1, 4100, 8, 1, 256, 512, True), (2, 130, 4, 2, 64, 256, True),
+    (1, 300, 8, 1, 256, 256, False), (5, 64, 2, 2, 256, 128, True)])
+def test_qkv_projection_with_rope_and_kv_append_epilogue(B, S, Hq, Hkv, dh, K, cache):
+    """pg_gemm_qkv_rope == Linear(q|k|v) -> rotate-half RoPE of the q and k heads (fp32 cos / sin of pos * inv_freq,
+    modeling_gemma.py:116-151) -> bf16, k / v rows appended to their cache pages (KVCache.update): one GEMM launch."""
+    from paligemma_multimodal_system_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + S)
+    T, W = B * S, (Hq + 2 * Hkv) * dh
+    x = (torch.randn(T, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(W, K, device="cuda", generator=g) * (1.0 / K ** 0.5)).bfloat16()
+    pos = (torch.arange(S, device="cuda").repeat(B) + torch.randint(1, 50, (B,), device="cuda", generator=g).repeat_interleave(S)).int()
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).cuda()
+    page, base0 = 64, 70  # the sequences' slots start inside the second page
+    max_pages = (base0 + S + page - 1) // page + 1
+    pool = B * max_pages + 3
+    k_pages = torch.full((pool, page, Hkv * dh), 7.0, device="cuda", dtype=torch.bfloat16)
+    v_pages = torch.full((pool, page, Hkv * dh), 7.0, device="cuda", dtype=torch.bfloat16)
+    table = torch.randperm(pool, device="cuda", generator=g)[: B * max_pages].int().view(B, max_pages).contiguous()
+    slot_base = torch.full((B,), base0, device="cuda", dtype=torch.int32)
+    out = torch.full((T, W), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = _lib.lib().pg_gemm_qkv_rope(x.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), W, T, K, Hq, Hkv, dh, pos.data_ptr(), inv_freq.data_ptr(),
+                                     k_pages.data_ptr() if cache else 0, v_pages.data_ptr() if cache else 0, table.data_ptr() if cache else 0,
+                                     slot_base.data_ptr() if cache else 0, S, page, max_pages if cache else 0, _lib.stream())
+    _lib.check(rc, "pg_gemm_qkv_rope")
+    torch.cuda.synchronize()
+    y = _ref(x, w).view(T, Hq + 2 * Hkv, dh)
+    ang = pos.float()[:, None] * inv_freq[None, :]                      # fp32 product, as the reference forms it
+    cos, sin = torch.cat([ang, ang], -1).cos()[:, None, :], torch.cat([ang, ang], -1).sin()[:, None, :]
+    half = dh // 2
+    rot = torch.cat([-y[..., half:], y[..., :half]], -1)
+    ref = y.clone()
+    ref[:, : Hq + Hkv] = y[:, : Hq + Hkv] * cos + rot[:, : Hq + Hkv] * sin
+    ref = ref.reshape(T, W)
+    _close(out, ref, 1e-2, "qkv + rope epilogue (dense)")
+    if cache:
+        kv_ref = out.view(T, Hq + 2 * Hkv, dh)
+        for b in range(B):
+            slots = base0 + torch.arange(S, device="cuda")
+            pg_ = table[b, (slots // page).long()].long()
+            rows_k = k_pages[pg_, (slots % page).long()].view(S, Hkv, dh)
+            rows_v = v_pages[pg_, (slots % page).long()].view(S, Hkv, dh)
+            assert torch.equal(rows_k, kv_ref[b * S:(b + 1) * S, Hq: Hq + Hkv]), "k pages hold exactly the dense rotated k rows"
+            assert torch.equal(rows_v, kv_ref[b * S:(b + 1) * S, Hq + Hkv:]), "v pages hold exactly the dense v rows"
+        # nothing outside the appended slots was touched
+        touched = (k_pages != 7.0).any(-1).sum().item()
+        assert touched == B * S, (touched, B * S)

@@ -242,3 +242,35 @@ def test_input_validation():
         model.vision_tower(torch.zeros(1, 3, 112, 112))
     with pytest.raises(RuntimeError):
         model.language_model.model.layers[0].mlp(torch.zeros(1))
+
+
+@pytest.mark.parametrize("regime", ["R0", "R1"])
+def test_prefill_with_rope_and_kv_append_in_the_qkv_epilogue(regime):
+    """The prefill whose q/k/v projection rotates and appends in its own epilogue (pg_gemm_qkv_rope; automatic once the grid
+    fills the GPU, forced here) against the oracle, against the path with the separate RoPE / append launch, and through decode
+    steps that read the cache pages it wrote."""
+    from paligemma_multimodal_system_b200.modeling_gemma import KVCache
+    sd = make_state_dict(TINY_CONFIG, regime, seed=11)
+    model = build_model(TINY_CONFIG, sd)
+    inp = make_inputs(TINY_CONFIG, batch=3, prompt_len=6, seed=7)
+    ids, px, mask = inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda()
+    ref = O.forward(sd, TINY_CONFIG, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], [])
+    outs, caches = {}, {}
+    for fused in (False, True):
+        model.language_model.fused_qkv_rope = fused
+        kv = KVCache()
+        outs[fused] = model(input_ids=ids, pixel_values=px, attention_mask=mask, kv_cache=kv)["logits"]
+        caches[fused] = (kv.k_cache, kv.v_cache)
+        _check(outs[fused], ref, regime, f"prefill logits, fused_qkv_rope={fused}")
+    for l in range(TINY_CONFIG["text_config"]["num_hidden_layers"]):
+        ka, kb = caches[False][0][l].float(), caches[True][0][l].float()
+        assert (ka - kb).abs().max().item() <= 2 ** -6 * ka.abs().max().item()  # one bf16 ulp: libm vs hardware sin / cos
+        va, vb = caches[False][1][l].float(), caches[True][1][l].float()
+        assert (va - vb).abs().max().item() <= 2 ** -6 * va.abs().max().item()
+    ref_t, ref_l = O.generate(sd, TINY_CONFIG, inp["input_ids"], inp["pixel_values"], inp["attention_mask"], 8, return_logits=True)
+    model.language_model.fused_qkv_rope = True
+    toks, logits = model.generate(ids, px, mask, 8, return_logits=True, forced_tokens=ref_t)
+    for r in range(3):
+        _check(logits[r], ref_l[r], regime, f"decode over pages written by the fused prefill, row {r}")
+    assert model.generate(ids, px, mask, 8).cpu().tolist() == ref_t.tolist()
+    model.language_model.fused_qkv_rope = None
