@@ -62,7 +62,8 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
                  int act_gelu, float scale, int swap, int split_k, void* stream);
 
 /*
- * pg_gemm_bf16 with the decode-step chores of the swap-AB (tokens <= 128) kernels; `fusion` may be NULL (= pg_gemm_bf16).
+ * pg_gemm_bf16 with per-call-site extras; `fusion` may be NULL (= pg_gemm_bf16).  zero_buf and stats belong to the swap-AB
+ * (tokens <= 128, decode) kernels, resid_row_mod to the token-major (prefill) kernels.
  *
  *  - zero_buf / zero_count: zero-filled (fp32, count % 4 == 0, 16-byte aligned) after the dependency wait; o_proj uses it to
  *    reset the split-K accumulator of the q/k/v projection once the attention kernel has consumed it.
@@ -71,6 +72,12 @@ int pg_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, voi
  *    m = max logit of the segment and s = sum exp2((logit - m) * stat_c), stat_c = inv_temperature * log2(e) -- temperature
  *    scaling and the max / partition-function passes of softmax + top-p (inference.py:63-66,90-106) folded into the GEMM
  *    epilogue; consumed by pg_sample_top_p_stats / pg_argmax_stats.  float2 [4 * ceil(features / 128)][stats_ld >= tokens].
+ *  - resid_row_mod > 0 (token-major kernels, PG_EPI_F32 with resid): the residual row of token t is t % resid_row_mod, i.e.
+ *    resid is a [resid_row_mod, features] table broadcast over the batch -- the position-embedding add of the SigLIP patch
+ *    embedding (modeling_siglip.py:289-298) folded into the patch GEMM's epilogue.
+ *  - out_row_map (token-major kernels, PG_EPI_F32 without resid): token t is written to output row out_row_map[t] -- the
+ *    multimodal projector (modeling_paligemma.py:57-65) scattering its rows, times `scale`, straight to the `<image>` positions of
+ *    the merged embedding sequence (masked_scatter of _merge_input_ids_with_image_features, :201-251); map from pg_merge_scan.
  */
 typedef struct PgGemmFusion {
   float* zero_buf;
@@ -78,6 +85,8 @@ typedef struct PgGemmFusion {
   void* stats;
   long long stats_ld;
   float stat_c;
+  int resid_row_mod;
+  const int* out_row_map;
 } PgGemmFusion;
 int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
                        const float* bias, const float* resid, long long ldr, int tokens, int features, int K, int mode,
@@ -126,9 +135,6 @@ int pg_resample_v_u8_norm(const void* src, float* out, int H, int Wd, int S, con
 /* SiglipVisionEmbeddings im2col (modeling_siglip.py:258-263,285-297): pixel fp32 [B,C,H,W] -> patches bf16
  * [B*(H/P)*(W/P), Kpad], column order (c, py, px) = Conv2d weight order, zero padded to Kpad. */
 int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream);
-
-/* x[b*N + n, :] += pos[n, :]  (positional_embeddings add, modeling_siglip.py:289-298); x fp32 [B*N, D]. */
-int pg_add_pos_emb(float* x, const float* pos, int B, int N, int D, void* stream);
 
 /*
  * Non-causal softmax(Q K^T * scale) V, flash style (modeling_siglip.py:96-136; modeling_gemma.py:307-339 prefill
@@ -195,6 +201,17 @@ int pg_kv_gather(const void* pages, const int* page_table, void* dense, int B, i
 int pg_merge_embeddings(const long long* input_ids, const long long* attn_mask, const void* embed, const float* img,
                         float* h, int* pos, int* src_scratch, int* err_flag, int B, int S, int D, int N,
                         long long image_token, long long pad_token, float text_scale, float img_scale, void* stream);
+
+/*
+ * The same merge as two halves around the projector GEMM, so that the image features never take a round trip of their own:
+ *   pg_merge_scan  -> pos[b,s], src_scratch[b,s] (j >= 0: j-th image token | -1 text | -2 pad), err_flag, and (dst_row != NULL)
+ *                     dst_row[b*N + j] = b*S + s: the merged row of image feature j, the out_row_map of the projector GEMM;
+ *   pg_merge_text  -> fills the text / pad rows of h (embedding gather * text_scale, zeros) and leaves the image rows alone.
+ */
+int pg_merge_scan(const long long* input_ids, const long long* attn_mask, int* pos, int* src_scratch, int* dst_row, int* err_flag,
+                  int B, int S, int N, long long image_token, long long pad_token, void* stream);
+int pg_merge_text(const long long* input_ids, const int* src_scratch, const void* embed, float* h, int B, int S, int D, int N,
+                  float text_scale, void* stream);
 
 /* Decode-step embedding with the same merge rules at q_len = 1; tokens are int32 on the device; img may be NULL. */
 int pg_embed_tokens(const int* tokens, const void* embed, const float* img, float* h, int B, int D, int N,

@@ -42,13 +42,14 @@ SIGNATURES = {
     "pg_resample_h_u8": [p, p, i32, i32, i32, p, p, i32, p],
     "pg_resample_v_u8_norm": [p, p, i32, i32, i32, p, p, i32, p, p],
     "pg_im2col": [p, p, i32, i32, i32, i32, i32, i32, p],
-    "pg_add_pos_emb": [p, p, i32, i32, i32, p],
     "pg_attention_prefill": [p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_attention_prefill_varlen": [p, p, p, p, p, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, f32, p],
     "pg_rope_kv_append": [p, i32, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, p, p],
     "pg_attention_decode_fused": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, f32, p],
     "pg_kv_gather": [p, p, p, i32, i32, i32, i32, i32, i32, p],
     "pg_merge_embeddings": [p, p, p, p, p, p, p, p, i32, i32, i32, i32, i64, i64, f32, f32, p],
+    "pg_merge_scan": [p, p, p, p, p, p, i32, i32, i32, i64, i64, p],
+    "pg_merge_text": [p, p, p, p, i32, i32, i32, i32, f32, p],
     "pg_embed_tokens": [p, p, p, p, i32, i32, i32, f32, f32, i64, i64, p],
     "pg_argmax": [p, i64, p, i32, i32, p],
     "pg_sample_top_p": [p, i64, p, p, i32, i32, f32, f32, u64, p, p],
@@ -65,7 +66,7 @@ class GemmFusion(C.Structure):
     """Mirror of PgGemmFusion (include/paligemma_b200.h)."""
     _fields_ = [
         ("zero_buf", p), ("zero_count", i64),
-        ("stats", p), ("stats_ld", i64), ("stat_c", f32),
+        ("stats", p), ("stats_ld", i64), ("stat_c", f32), ("resid_row_mod", i32), ("out_row_map", p),
     ]
 
 
@@ -118,8 +119,11 @@ def require_device():
 # ------------------------------------------------------------------------------------------------------------------
 # thin typed wrappers (argument checking that needs tensor metadata lives here; kernels check the rest)
 # ------------------------------------------------------------------------------------------------------------------
-def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, swap=-1, split_k=1, features=None):
-    """out[t,f] (mode-dependent) from x [T,K] bf16 and w [F,K] bf16 (nn.Linear layout)."""
+def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, swap=-1, split_k=1, features=None, resid_row_mod=0,
+         out_row_map=None):
+    """out[t,f] (mode-dependent) from x [T,K] bf16 and w [F,K] bf16 (nn.Linear layout).  resid_row_mod = N > 0: `resid` is an
+    [N, F] table and token t takes row t % N (position embeddings).  out_row_map int32 [T]: token t goes to row out_row_map[t]
+    of `out` (projector rows scattered to their `<image>` positions)."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda and w.is_cuda
     assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1 and x.shape[1] == w.shape[1]
     T, K = x.shape
@@ -128,6 +132,18 @@ def gemm(x, w, out, *, mode, bias=None, resid=None, act_gelu=False, scale=1.0, s
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     if resid is not None:
         assert resid.dtype == torch.float32 and resid.stride(-1) == 1
+    if resid_row_mod or out_row_map is not None:
+        fu = GemmFusion()
+        if resid_row_mod:
+            assert resid is not None and resid.shape[0] >= resid_row_mod
+            fu.resid_row_mod = int(resid_row_mod)
+        if out_row_map is not None:
+            assert out_row_map.dtype == torch.int32 and out_row_map.numel() >= T and out_row_map.is_contiguous()
+            fu.out_row_map = out_row_map.data_ptr()
+        check(lib().pg_gemm_bf16_fused(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
+                                       ptr(resid), 0 if resid is None else resid.stride(0), T, F, K, mode, int(act_gelu), float(scale),
+                                       swap, split_k, C.addressof(fu), stream()), "pg_gemm_bf16_fused")
+        return out
     check(lib().pg_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), ptr(bias),
                              ptr(resid), 0 if resid is None else resid.stride(0), T, F, K, mode, int(act_gelu), float(scale),
                              swap, split_k, stream()), "pg_gemm_bf16")

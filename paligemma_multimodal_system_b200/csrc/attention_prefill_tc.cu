@@ -23,15 +23,9 @@
 // softmax of tile j+1 runs: the tensor pipe only idles when the softmax (MUFU exp2) is the longer stage (dh = 72).
 // Zero padding comes from TMA: columns beyond dh (72 -> 80) and key / query rows beyond the sequence are out-of-bounds
 // box elements and arrive as zeros; padded keys are masked to -inf before the softmax.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"
-
-#ifndef PG_ATTN_PP_DEFAULT
-#define PG_ATTN_PP_DEFAULT 0
-#endif
 
 namespace pg {
 namespace ap {
@@ -120,34 +114,22 @@ PG_DEVINL float exp2_mufu(float x) {
   return y;
 }
 
-// 2^x on the FMA / ALU pipes only (no MUFU, no F2I -- both live on the XU pipe, which is what saturates at dh <= 128:
-// ncu shows sm__inst_executed_pipe_xu_realtime at 100 % with the tensor pipe at 24 %).  Round-to-nearest range reduction by
-// the 1.5*2^23 trick (the integer part lands in the low mantissa bits), degree-4 polynomial of 2^f on [-0.5, 0.5]
-// (relative error 4e-5, far below the bf16 rounding the result goes through), 2^n by an exponent-field add.
-PG_DEVINL float exp2_fma(float x) {
-  const float xc = fmaxf(x, -125.0f);
-  const float t = xc + 12582912.0f;
-  const float f = xc - (t - 12582912.0f);
-  float p = 0.00961813f;
-  p = fmaf(p, f, 0.05550411f);
-  p = fmaf(p, f, 0.24022651f);
-  p = fmaf(p, f, 0.69314718f);
-  p = fmaf(p, f, 1.0f);
-  const float r = __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-  return x < -125.0f ? 0.f : r;  // masked keys carry -inf and must weigh exactly nothing
-}
-
-// PP = how many of the four score pairs of every 8-key chunk take the FMA-pipe exponential (0 = all on the MUFU).
+// (Moving a share of the exponentials to the FMA pipe -- a polynomial 2^x -- was measured: no gain at a quarter, -7 % at half;
+//  the variant is gone.)
 // QT = query tiles (128 rows each) per CTA.  QT = 2 (dh <= 128): both tiles run against the SAME K / V tiles in shared
 // memory -- the kernel is bound by K/V delivery through the crossbar (profiles/r01d_prefill_attn72_ncu_full.csv), and two
 // query tiles halve the K/V bytes per FLOP; softmax warps 2-5 own tile 0, warps 6-9 tile 1 (no exchange between them).
-template <int DH, int SW, int PP, int QT>
+template <int DH, int SW, int QT>
 __global__ void __launch_bounds__(64 + 128 * SW * QT, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
   static_assert(SW * QT <= 2, "eight softmax warps at most");
   using C = Cfg<DH, QT>;
   constexpr int BM = C::BM, BN = C::BN, DHP = C::DHP, NKB = C::NKB, KST = C::KST, VST = C::VST;
+  // dh = 72 is padded to 80 columns: column 72 of every V tile is set to 1.0 in shared memory, so that O[:, 72] accumulates
+  // the row sums of the (bf16) probabilities on the tensor core and the softmax warps -- bound by instruction issue, ~4.5
+  // instructions per score -- drop the FADD per score.  The lazy rescale of O carries the column along.
+  constexpr bool TCSUM = DHP > DH;
   constexpr uint32_t IDESC_S = make_idesc_bf16(BM, BN);
   constexpr uint32_t IDESC_O = make_idesc_bf16(BM, DHP, 0, 1);  // B (= V) is MN-major
   extern __shared__ __align__(1024) uint8_t smem_ap[];
@@ -228,7 +210,64 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if (lane == 0) {
+    if constexpr (TCSUM) {
+      // whole warp: every lane plants its share of the ones column into the V tile that just landed, lane 0 issues
+      auto issue_s = [&](int j) {
+        const int ks = j % KST, sb = j & 1;
+        mbar_wait(k_full(ks), (j / KST) & 1);
+        const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
+#pragma unroll
+        for (int qt = 0; qt < QT; ++qt) {
+          mbar_wait(s_empty(qt, sb), ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + C::COL_S + (qt * 2 + sb) * BN;
+#pragma unroll
+          for (int k = 0; k < DHP / 16; ++k) {
+            const uint64_t adesc = make_sdesc_k_sw128(sbase + qt * C::Q_BYTES + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
+            const uint64_t bdesc = make_sdesc_k_sw128(kaddr + (k >> 2) * C::KV_BOX) + 2 * (k & 3);
+            umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(qt, sb));
+        }
+        umma_commit(k_empty(ks));
+      };
+      mbar_wait(q_full, 0);
+      if (lane == 0) issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (lane == 0 && j + 1 < n_tiles) issue_s(j + 1);
+        const int vs = j % VST, pb = j & 1;
+        mbar_wait(v_full(vs), (j / VST) & 1);
+        const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
+        {
+          // column DH (= 72) lives in box DH / 64, 16-byte chunk (DH % 64) / 8, element DH % 8 of key row r (128B swizzle)
+          constexpr uint32_t BOX = DH / 64, CH = (DH % 64) / 8, EL = DH % 8;
+          for (int r = lane; r < BN; r += 32) {
+            const uint32_t addr = vaddr + BOX * C::KV_BOX + r * 128 + ((CH ^ (r & 7)) << 4) + EL * 2;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(0x3F80)) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int qt = 0; qt < QT; ++qt) {
+            mbar_wait(p_full(qt, pb), (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + C::COL_O + qt * C::O_STRIDE;
+            const uint32_t paddr = sbase + C::OFF_P + (qt * 2 + pb) * C::P_BYTES;
+#pragma unroll
+            for (int k = 0; k < BN / 16; ++k) {
+              const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
+              const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);
+              umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(o_done(qt));
+          }
+          umma_commit(v_empty(vs));
+        }
+        __syncwarp();
+      }
+    } else if (lane == 0) {
       auto issue_s = [&](int j) {  // S_j = Q K_j^T of every query tile into its S buffer j % 2
         const int ks = j % KST, sb = j & 1;
         mbar_wait(k_full(ks), (j / KST) & 1);
@@ -337,8 +376,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
           //  as well, so it added XU work instead of removing it)
           const float x0 = fmaf(s[cc * 8 + 2 * e], p.sl2, -m_new), x1 = fmaf(s[cc * 8 + 2 * e + 1], p.sl2, -m_new);
-          const float p0 = e < PP ? exp2_fma(x0) : exp2_mufu(x0), p1 = e < PP ? exp2_fma(x1) : exp2_mufu(x1);
-          sum += p0 + p1;
+          const float p0 = exp2_mufu(x0), p1 = exp2_mufu(x1);
+          if constexpr (!TCSUM) sum += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
         }
         const int c = half * (HB / 8) + cc;  // chunk index inside the whole tile row
@@ -368,7 +407,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (lane == 0) mbar_arrive(p_full(qt, sb));
     }
     // ---- epilogue: O / l -> bf16 ----
-    if constexpr (SW == 2) {  // total row sum = sum over both halves
+    if constexpr (SW == 2 && !TCSUM) {  // total row sum = sum over both halves
       pair_sync();            // the partner has read the last tile's maximum: the exchange area is free
       xch[half * 128 + r] = l_run;
       pair_sync();
@@ -376,6 +415,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     mbar_wait(o_done(qt), (n_tiles - 1) & 1);
     tc_fence_after();
+    if constexpr (TCSUM) {  // the row sum is column DH of the accumulator (ones column of V); any warp of the quadrant may read it
+      uint32_t v[16];
+      tmem_ld16(lane_addr + col_o + (DH / 16) * 16, v);
+      tmem_ld_wait();
+      l_run = __uint_as_float(v[DH % 16]);
+    }
     const float inv = 1.0f / l_run;
     const bool row_ok = row < p.rows;
     bf16* orow = p.o + b * p.o_bs + h * p.o_head_off + static_cast<long long>(row / p.group) * p.o_ts +
@@ -427,20 +472,20 @@ static int make_tmap_nd(CUtensorMap* m, const void* ptr, int rank, const long lo
   return r == CUDA_SUCCESS ? PG_OK : PG_ERR_TMAP;
 }
 
-template <int DH, int SW, int PP, int QT>
+template <int DH, int SW, int QT>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int B, int H, cudaStream_t st) {
   using C = Cfg<DH, QT>;
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, PP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_prefill_tc_kernel<DH, SW, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
       cudaGetLastError();
       return PG_ERR_CUDA;
     }
     configured[dev] = true;
   }
   dim3 grid((p.rows + C::BM * QT - 1) / (C::BM * QT), H, B);
-  attn_prefill_tc_kernel<DH, SW, PP, QT><<<grid, 64 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
+  attn_prefill_tc_kernel<DH, SW, QT><<<grid, 64 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
   pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
@@ -494,10 +539,10 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   // softmax warps per TMEM lane quadrant: two (column halves) for the one-tile dh <= 128 variant, else one
   const int sw = qt == 2 ? 1 : (dh > 128 ? 1 : 2);
 #define PG_AP_LAUNCH1(DHV)                                                           \
-  if (sw == 1) return ap::launch<DHV, 1, 0, 1>(tq, tk, tv, p, B, H, st);             \
-  return ap::launch<DHV, 2, 0, 1>(tq, tk, tv, p, B, H, st);
+  if (sw == 1) return ap::launch<DHV, 1, 1>(tq, tk, tv, p, B, H, st);             \
+  return ap::launch<DHV, 2, 1>(tq, tk, tv, p, B, H, st);
 #define PG_AP_LAUNCH2(DHV)                                                           \
-  if (qt == 2) return ap::launch<DHV, 1, 0, 2>(tq, tk, tv, p, B, H, st);
+  if (qt == 2) return ap::launch<DHV, 1, 2>(tq, tk, tv, p, B, H, st);
   switch (dh) {
     case 64: PG_AP_LAUNCH2(64) PG_AP_LAUNCH1(64)
     case 72: PG_AP_LAUNCH2(72) PG_AP_LAUNCH1(72)

@@ -1,4 +1,4 @@
-// HBM-bound row kernels around the GEMMs: LayerNorm, GemmaRMSNorm, im2col, positional add, embedding merge,
+// HBM-bound row kernels around the GEMMs: LayerNorm, GemmaRMSNorm, im2col, embedding merge,
 // RoPE + paged KV append, KV gather, weight packing.  All are single-pass, 16-byte vectorised where the layout allows.
 #include "common.cuh"
 #include "paligemma_b200.h"
@@ -181,17 +181,6 @@ __global__ void im2col_kernel(const float* __restrict__ px, bf16* __restrict__ o
   out[idx] = __float2bfloat16(v);
 }
 
-__global__ void add_pos_emb_kernel(float* __restrict__ x, const float* __restrict__ pos, int N, int D4, long long total4) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= total4) return;
-  const long long row = idx / D4;
-  const int c = static_cast<int>(idx % D4);
-  float4 a = reinterpret_cast<float4*>(x)[idx];
-  const float4 p = reinterpret_cast<const float4*>(pos)[(row % N) * D4 + c];
-  a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
-  reinterpret_cast<float4*>(x)[idx] = a;
-}
-
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 2;
   if (i + 1 < n) {
@@ -222,7 +211,8 @@ __global__ void pack_gate_up_kernel(const bf16* __restrict__ gate, const bf16* _
 // pass 1: one block per batch row; src[b,s] = j >= 0 (j-th image token) | -1 text | -2 pad; pos = cumsum(mask), 1 at mask==0
 __global__ void __launch_bounds__(1024) merge_scan_kernel(const long long* __restrict__ ids, const long long* __restrict__ mask,
                                                           int* __restrict__ src, int* __restrict__ pos, int* __restrict__ err,
-                                                          int S, int N, long long image_token, long long pad_token) {
+                                                          int* __restrict__ dst_row, int S, int N, long long image_token,
+                                                          long long pad_token) {
   __shared__ int wsum_img[32], wsum_msk[32];
   __shared__ int carry_img, carry_msk;
   const int b = blockIdx.x;
@@ -248,6 +238,8 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(const long long* __res
     if (s < S) {
       const int j = oi + xi - is_img;  // exclusive count of image tokens
       src[static_cast<long long>(b) * S + s] = (id == pad_token) ? -2 : (is_img ? j : -1);
+      // inverse map for the projector GEMM that scatters its rows: image feature j of row b lands on merged row b*S + s
+      if (dst_row != nullptr && is_img && id != pad_token && j < N) dst_row[static_cast<long long>(b) * N + j] = b * S + s;
       pos[static_cast<long long>(b) * S + s] = (mk == 0) ? 1 : (om + xm);
     }
     __syncthreads();
@@ -261,11 +253,12 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(const long long* __res
 __global__ void __launch_bounds__(256) merge_gather_kernel(const long long* __restrict__ ids, const int* __restrict__ src,
                                                            const bf16* __restrict__ embed, const float* __restrict__ img,
                                                            float* __restrict__ h, int S, int D, int N, float text_scale,
-                                                           float img_scale) {
+                                                           float img_scale, int skip_image) {
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / S);
   const int sidx = src[tok];
   float4* dst = reinterpret_cast<float4*>(h + tok * D);
+  if (sidx >= 0 && skip_image) return;  // the projector GEMM has written this row (pg_gemm_bf16_fused out_row_map)
   if (sidx == -2) {
     for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else if (sidx >= 0) {
@@ -477,13 +470,6 @@ extern "C" int pg_im2col(const float* pixels, void* patches, int B, int C, int H
   PG_RET();
 }
 
-extern "C" int pg_add_pos_emb(float* x, const float* pos, int B, int N, int D, void* stream) {
-  if (B <= 0 || N <= 0 || D <= 0 || (D % 4)) return PG_ERR_ARG;
-  const long long total4 = static_cast<long long>(B) * N * (D / 4);
-  add_pos_emb_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, PG_ST(stream)>>>(x, pos, N, D / 4, total4);
-  PG_RET();
-}
-
 extern "C" int pg_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   if (n <= 0) return PG_ERR_ARG;
   const long long pairs = (n + 1) / 2;
@@ -504,11 +490,26 @@ extern "C" int pg_merge_embeddings(const long long* input_ids, const long long* 
                                    long long image_token, long long pad_token, float text_scale, float img_scale,
                                    void* stream) {
   if (B <= 0 || S <= 0 || D <= 0 || (D % 4)) return PG_ERR_ARG;
-  merge_scan_kernel<<<B, 1024, 0, PG_ST(stream)>>>(input_ids, attn_mask, src_scratch, pos, err_flag, S, N, image_token, pad_token);
+  merge_scan_kernel<<<B, 1024, 0, PG_ST(stream)>>>(input_ids, attn_mask, src_scratch, pos, err_flag, nullptr, S, N, image_token, pad_token);
   if (cudaGetLastError() != cudaSuccess) return PG_ERR_CUDA;
   pg_count_launch(1);
   merge_gather_kernel<<<B * S, 256, 0, PG_ST(stream)>>>(input_ids, src_scratch, static_cast<const bf16*>(embed), img, h, S, D, N,
-                                                        text_scale, img_scale);
+                                                        text_scale, img_scale, 0);
+  PG_RET();
+}
+
+extern "C" int pg_merge_scan(const long long* input_ids, const long long* attn_mask, int* pos, int* src_scratch, int* dst_row,
+                             int* err_flag, int B, int S, int N, long long image_token, long long pad_token, void* stream) {
+  if (B <= 0 || S <= 0 || N < 0 || !input_ids || !attn_mask || !pos || !src_scratch || !err_flag) return PG_ERR_ARG;
+  merge_scan_kernel<<<B, 1024, 0, PG_ST(stream)>>>(input_ids, attn_mask, src_scratch, pos, err_flag, dst_row, S, N, image_token, pad_token);
+  PG_RET();
+}
+
+extern "C" int pg_merge_text(const long long* input_ids, const int* src_scratch, const void* embed, float* h, int B, int S, int D,
+                             int N, float text_scale, void* stream) {
+  if (B <= 0 || S <= 0 || D <= 0 || (D % 4) || !input_ids || !src_scratch || !embed || !h) return PG_ERR_ARG;
+  merge_gather_kernel<<<B * S, 256, 0, PG_ST(stream)>>>(input_ids, src_scratch, static_cast<const bf16*>(embed), nullptr, h, S, D, N,
+                                                        text_scale, 0.f, 1);
   PG_RET();
 }
 

@@ -55,6 +55,9 @@ struct GemmArgs {
   const float* bias;
   const float* resid;
   long long ldr;
+  const int* out_row_map;  // token-major fp32 epilogues: token t is written to output row out_row_map[t] (projector -> merged rows)
+  int resid_mod;  // > 0 (token-major kernels): the residual row of token t is t % resid_mod (a [resid_mod, features] table
+                  // broadcast over the batch: the position embeddings added to the patch embeddings, modeling_siglip.py:289-298)
   int n_fast;  // tile raster order (decode_tile)
   int f32_coalesced;  // token-major fp32 epilogue through the shared-memory transposition (alignment checked by the host)
   long long* trace;  // optional profiling stamps (clock64) written by CTA 0
@@ -371,8 +374,10 @@ PG_DEVINL void rowmajor_tile_epilogue(const GemmArgs& args, uint32_t taddr, int 
   const bool has_bias = args.bias != nullptr && first_split;
   const bool gelu = MODE == PG_EPI_BF16 && args.act_gelu != 0;
   __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(tok) * args.ldo;
-  float* out_f = reinterpret_cast<float*>(args.out) + static_cast<long long>(tok) * args.ldo;
-  const float* res = (MODE == PG_EPI_F32 && args.resid != nullptr) ? args.resid + static_cast<long long>(tok) * args.ldr : nullptr;
+  const int orow = (MODE == PG_EPI_F32 && args.out_row_map != nullptr && tok < args.tokens) ? __ldg(args.out_row_map + tok) : tok;
+  float* out_f = reinterpret_cast<float*>(args.out) + static_cast<long long>(orow) * args.ldo;
+  const float* res = (MODE == PG_EPI_F32 && args.resid != nullptr)
+                         ? args.resid + static_cast<long long>(args.resid_mod > 0 ? tok % args.resid_mod : tok) * args.ldr : nullptr;
   // 16-byte vector access is possible when the row bases are 16 B aligned (n0 and the step are multiples of 16 columns)
   const bool vec_ok = MODE == PG_EPI_BF16 ? ((reinterpret_cast<uintptr_t>(out_bf) & 15) == 0)
                                           : (((reinterpret_cast<uintptr_t>(out_f) & 15) == 0) &&
@@ -493,7 +498,8 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int row = row_base + 4 * k + sub;
-      dst[k] = (col_ok && row < args.tokens) ? *reinterpret_cast<const float4*>(res + static_cast<long long>(row) * args.ldr + col)
+      const int rrow = args.resid_mod > 0 ? row % args.resid_mod : row;
+      dst[k] = (col_ok && row < args.tokens) ? *reinterpret_cast<const float4*>(res + static_cast<long long>(rrow) * args.ldr + col)
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
@@ -537,7 +543,8 @@ PG_DEVINL void rowmajor_tile_epilogue_f32_coalesced(const GemmArgs& args, uint32
         float4 o4;
         o4.x = fmaf(v.x, scale, b4.x) + rr[k].x; o4.y = fmaf(v.y, scale, b4.y) + rr[k].y;
         o4.z = fmaf(v.z, scale, b4.z) + rr[k].z; o4.w = fmaf(v.w, scale, b4.w) + rr[k].w;
-        *reinterpret_cast<float4*>(out + static_cast<long long>(row) * args.ldo + col) = o4;
+        const int orow = args.out_row_map != nullptr ? __ldg(args.out_row_map + row) : row;
+        *reinterpret_cast<float4*>(out + static_cast<long long>(orow) * args.ldo + col) = o4;
       }
     }
     if (res != nullptr && sl + 1 < nsl) {
@@ -958,8 +965,16 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
   GemmArgs a = {};
   a.tokens = tokens; a.features = features; a.K = K; a.split_k = split_k; a.mode = mode; a.act_gelu = act_gelu;
   a.scale = scale; a.out = out; a.ldo = ldo; a.bias = bias; a.resid = resid; a.ldr = ldr;
-  if (fu != nullptr) {
-    if (!swap) return PG_ERR_ARG;  // the fusions below belong to the decode (swap-AB) kernels
+  if (fu != nullptr && fu->resid_row_mod > 0) {
+    if (swap || resid == nullptr || mode != PG_EPI_F32) return PG_ERR_ARG;  // a token-major fp32 epilogue feature
+    a.resid_mod = fu->resid_row_mod;
+  }
+  if (fu != nullptr && fu->out_row_map != nullptr) {
+    if (swap || resid != nullptr || mode != PG_EPI_F32) return PG_ERR_ARG;  // token-major fp32 epilogue, no in-place residual
+    a.out_row_map = fu->out_row_map;
+  }
+  if (fu != nullptr && (fu->zero_count > 0 || fu->stats != nullptr)) {
+    if (!swap) return PG_ERR_ARG;  // these belong to the decode (swap-AB) kernels
     if (fu->zero_count > 0) {
       if (fu->zero_buf == nullptr || (fu->zero_count % 4) != 0 || (reinterpret_cast<uintptr_t>(fu->zero_buf) & 15)) return PG_ERR_ARG;
       a.zero_buf = fu->zero_buf; a.zero_count = fu->zero_count;

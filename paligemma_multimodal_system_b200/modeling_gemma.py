@@ -32,7 +32,8 @@ class KVCache:
         self.v_pages = None
         self.page_table = None
         self.counters = None  # int32 [3, B]: pos, slot, kv_len  (device)
-        self.image_feats = None  # projected image features of the request (decode-time <image> token parity)
+        self.image_feats = None  # projected image features of the request (decode-time <image> token parity): [B, n >= 1, D]
+        self.image_feats_scaled = False  # True: the rows already carry hidden_size**-0.5 * sqrt(hidden) (written by _embed_prompt)
         self._len = 0
         self._layer_len: List[int] = []
         self._geom = None  # (B, L, Hkv, dh)

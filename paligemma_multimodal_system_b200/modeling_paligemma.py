@@ -137,10 +137,55 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         return h, pos
 
     @torch.no_grad()
+    def _embed_prompt(self, input_ids, attention_mask, pixel_values, validate=True, first_image_row=None):
+        """Prefill inputs of the decoder in one pass: vision tower -> projector -> merged, scaled embeddings.
+        _merge_input_ids_with_image_features (modeling_paligemma.py:201-251) runs as two halves AROUND the projector GEMM: a scan
+        of the ids (position ids, per-token source, the merged row of every image feature) first, then the projector
+        (modeling_paligemma.py:57-65) writes its rows, times hidden_size**-0.5 * sqrt(hidden) (:288 and modeling_gemma.py:510-511),
+        straight to their `<image>` positions through its epilogue's row map, and a gather fills the text / pad rows.  No fp32
+        [B, N, D] image-feature tensor exists.  Returns h fp32 [B*S, D], pos int32 [B*S] (+ the device error flag when
+        validate=False: CUDA-graph capture).  first_image_row [B, 1, D] receives every request's first projected, scaled feature row
+        (what a decode step needs when the sampled token is `<image>`, modeling_paligemma.py:116-121)."""
+        L, lm = _lib.lib(), self.language_model
+        pk = lm._packed or lm.pack()
+        if self._proj_w is None:
+            self._proj_w = _bf16(self.multi_modal_projector.linear.weight)
+        B, S = input_ids.shape
+        D, V = self.text_config.hidden_size, self.text_config.vocab_size
+        dev = torch.device("cuda")
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        mask = attention_mask.to(device=dev).to(torch.int64).contiguous()
+        if validate and bool(((ids < 0) | (ids >= V)).any()):
+            raise IndexError("input_ids out of range for the embedding table")
+        feats = self.vision_tower.forward_features(pixel_values, out_bf16=True)  # [B*N, Dv] bf16
+        N = feats.shape[0] // B
+        h = torch.empty(B * S + 1, D, device=dev, dtype=torch.float32)  # (+ one sink row for features without a slot)
+        pos = torch.empty(B * S, device=dev, dtype=torch.int32)
+        src = torch.empty(B * S, device=dev, dtype=torch.int32)
+        dst = torch.full((B * N,), B * S, device=dev, dtype=torch.int32)
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        _lib.check(L.pg_merge_scan(ids.data_ptr(), mask.data_ptr(), pos.data_ptr(), src.data_ptr(), dst.data_ptr(), err.data_ptr(), B, S, N,
+                                   self.dummy_image_token_id, self.pad_token_id, _lib.stream()), "pg_merge_scan")
+        img_scale = (self.config.projection_dim ** -0.5) * (D ** 0.5)
+        _lib.gemm(feats, self._proj_w, h, mode=_lib.EPI_F32, bias=self._proj_b, scale=img_scale, swap=0,
+                  out_row_map=dst)
+        h = h[: B * S]
+        _lib.check(L.pg_merge_text(ids.data_ptr(), src.data_ptr(), pk["embed"].data_ptr(), h.data_ptr(), B, S, D, N, D ** 0.5,
+                                   _lib.stream()), "pg_merge_text")
+        if first_image_row is not None:
+            first_image_row.view(B, D).copy_(h.index_select(0, dst.view(B, N)[:, 0].clamp(max=B * S - 1).long()))
+        if not validate:
+            return h, pos, err
+        if int(err.item()) != 0:
+            raise ValueError(f"every row of input_ids must hold exactly {N} image tokens (id {self.dummy_image_token_id})")
+        return h, pos
+
+    @torch.no_grad()
     def _decode_step(self, tokens_i32, kv_cache, bufs, B, inv_temperature=1.0):
         D = self.text_config.hidden_size
-        return self.language_model.decode_step(bufs, kv_cache, B, tokens_i32, kv_cache.image_feats,
-                                               (self.config.projection_dim ** -0.5) * (D ** 0.5), self.pad_token_id,
+        # image_feats rows written by _embed_prompt already carry the scale
+        scale = 1.0 if getattr(kv_cache, "image_feats_scaled", False) else (self.config.projection_dim ** -0.5) * (D ** 0.5)
+        return self.language_model.decode_step(bufs, kv_cache, B, tokens_i32, kv_cache.image_feats, scale, self.pad_token_id,
                                                self.dummy_image_token_id, inv_temperature)
 
     def _sample(self, logits, out_i32, B, do_sample, inv_t, top_p, seed, step, stats=None, seed_dev=None):
@@ -171,10 +216,10 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         c = self.text_config
         decode = kv_cache is not None and kv_cache.num_items() > 0
         if not decode:
-            img = self.image_features(pixel_values)
-            h, pos = self._merge(input_ids, attention_mask, img)
+            first = torch.empty(B, 1, c.hidden_size, device="cuda", dtype=torch.float32) if kv_cache is not None else None
+            h, pos = self._embed_prompt(input_ids, attention_mask, pixel_values, first_image_row=first)
             if kv_cache is not None:
-                kv_cache.image_feats = img
+                kv_cache.image_feats, kv_cache.image_feats_scaled = first, True
             logits = lm.prefill(h, pos, B, S, kv_cache, last_only=last_only)
         else:
             assert S == 1, "Generation Phase more than one token CAN'T be input"
@@ -207,7 +252,7 @@ class PaliGemmaForConditionalGeneration(nn.Module):
             stt = dict(kv=kv, nxt=torch.empty(B, device=dev, dtype=torch.int32), cur=torch.empty(B, device=dev, dtype=torch.int32),
                        hist=torch.zeros(T, B, device=dev, dtype=torch.int32), step=torch.zeros(1, device=dev, dtype=torch.int32),
                        seed=torch.zeros(1, device=dev, dtype=torch.int64),
-                       img=torch.empty(B, c.num_image_tokens, c.hidden_size, device=dev, dtype=torch.float32), graph=None, graph_k=None)
+                       img=torch.empty(B, 1, c.hidden_size, device=dev, dtype=torch.float32), graph=None, graph_k=None)
             if len(self._graphs) >= 4:  # bound the number of cached geometries (each owns a KV cache)
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = stt
@@ -224,9 +269,8 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         N = self.text_config.num_image_tokens
 
         def run(ids_t, mask_t, px_t):
-            img = stt["img"].copy_(self.image_features(px_t))
-            kv.image_feats = img
-            h, pos, err = self._merge(ids_t, mask_t, img, validate=False)
+            h, pos, err = self._embed_prompt(ids_t, mask_t, px_t, validate=False, first_image_row=stt["img"])
+            kv.image_feats, kv.image_feats_scaled = stt["img"], True
             return lm.prefill(h, pos, B, S, kv, last_only=True).view(B, V), err
 
         pf = stt.get("prefill")
@@ -295,11 +339,9 @@ class PaliGemmaForConditionalGeneration(nn.Module):
         graph_prefill = use_cuda_graph and lens is None and B * S <= 1100 and pixel_values.is_cuda and attention_mask is not None
         if graph_prefill:
             logits = self._prefill_graphed(stt, kv, input_ids, pixel_values, attention_mask, B, S, V)
-            img = stt["img"]
         else:
-            img = stt["img"].copy_(self.image_features(pixel_values))  # static buffer: the decode graph reads it
-            kv.image_feats = img
-            h, pos = self._merge(input_ids, attention_mask, img)
+            h, pos = self._embed_prompt(input_ids, attention_mask, pixel_values, first_image_row=stt["img"])  # static: the decode graph reads it
+            kv.image_feats, kv.image_feats_scaled = stt["img"], True
             logits = lm.prefill(h, pos, B, S, kv, last_only=True, lens=lens).view(B, V)
         if ev:
             ev[1].record()

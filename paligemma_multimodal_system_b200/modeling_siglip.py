@@ -163,8 +163,8 @@ class SiglipVisionModel(nn.Module):
         patches = torch.empty(M, pk["Kp"], device=dev, dtype=torch.bfloat16)
         _lib.check(L.pg_im2col(px.data_ptr(), patches.data_ptr(), B, C, H, W, P, pk["Kp"], st), "pg_im2col")
         x = torch.empty(M, Dv, device=dev, dtype=torch.float32)
-        _lib.gemm(patches, pk["patch_w"], x, mode=_lib.EPI_F32, bias=pk["patch_b"], swap=0)
-        _lib.check(L.pg_add_pos_emb(x.data_ptr(), pk["pos"].data_ptr(), B, N, Dv, st), "pg_add_pos_emb")
+        # conv-as-GEMM with bias and the position embeddings (row n of the table for token b*N + n) in one epilogue
+        _lib.gemm(patches, pk["patch_w"], x, mode=_lib.EPI_F32, bias=pk["patch_b"], resid=pk["pos"], resid_row_mod=N, swap=0)
         h = torch.empty(M, Dv, device=dev, dtype=torch.bfloat16)
         qkv = torch.empty(M, 3 * Dv, device=dev, dtype=torch.bfloat16)
         att = torch.empty(M, Dv, device=dev, dtype=torch.bfloat16)

@@ -161,7 +161,7 @@ class ContinuousBatcher:
         # at q_len = 1, modeling_paligemma.py:116-121): one row per slot / per page set is all that has to be kept
         self.img = torch.zeros(self.B, 1, c.hidden_size, device=dev, dtype=torch.float32)
         self.img_sets = torch.zeros(n_sets, c.hidden_size, device=dev, dtype=torch.float32)
-        self.kv.image_feats = self.img
+        self.kv.image_feats, self.kv.image_feats_scaled = self.img, True  # rows come from _embed_prompt, already scaled
         self._set_idle(list(range(self.B)))
         self.bufs = self.lm.decode_buffers(self.B, private=True)  # the captured graph owns these addresses
         self.graph = None
@@ -256,9 +256,9 @@ class ContinuousBatcher:
         sets_t = torch.tensor([r.page_set for r in reqs], device="cuda", dtype=torch.int64)
         lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
         self.stats["t_prefill_prep_s"] += time.perf_counter() - t_prep  # host batching + H2D of the pixels
-        img = model.image_features(px)
-        self.img_sets.index_copy_(0, sets_t, img[:, 0].contiguous())
-        h, pos = model._merge(ids.cuda(), mask.cuda(), img)
+        first = torch.empty(g, 1, c.hidden_size, device="cuda", dtype=torch.float32)
+        h, pos = model._embed_prompt(ids.cuda(), mask.cuda(), px, first_image_row=first)
+        self.img_sets.index_copy_(0, sets_t, first[:, 0])
         logits = self.lm.prefill(h, pos, g, S, self.kv, last_only=True, lens=lens_t,
                                  page_rows=self.home_table.index_select(0, sets_t)).view(g, c.vocab_size)
         if self.admit_logits is not None:

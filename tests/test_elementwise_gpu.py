@@ -53,15 +53,21 @@ def test_im2col_matches_conv2d():
     assert torch.count_nonzero(patches[:, C * P * P:]) == 0
 
 
-def test_add_pos_emb():
+@pytest.mark.parametrize("B,N,D,K", [(3, 256, 1152, 640), (2, 1024, 256, 592), (1, 300, 64, 64)])
+def test_patch_gemm_adds_position_embeddings_in_its_epilogue(B, N, D, K):
+    """x[b*N + n, :] = patches @ W^T + bias + pos[n, :] (modeling_siglip.py:258-263,289-298): the position-embedding add is the
+    fp32 `residual` of the patch GEMM, its row taken modulo the number of patches."""
     from paligemma_multimodal_system_b200 import _lib
-    B, N, D = 3, 256, 1152
-    x = torch.randn(B * N, D, device="cuda")
-    pos = torch.randn(N, D, device="cuda")
-    ref = (x.view(B, N, D) + pos).view(B * N, D)
-    _lib.check(_lib.lib().pg_add_pos_emb(x.data_ptr(), pos.data_ptr(), B, N, D, _lib.stream()), "pos")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    patches = (torch.randn(B * N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(D, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(D, device="cuda", generator=g)
+    pos = torch.randn(N, D, device="cuda", generator=g)
+    out = torch.full((B * N, D), float("nan"), device="cuda")
+    _lib.gemm(patches, w, out, mode=_lib.EPI_F32, bias=bias, resid=pos, resid_row_mod=N, swap=0)
     torch.cuda.synchronize()
-    assert torch.equal(x, ref)
+    ref = ((patches.float() @ w.float().t() + bias).view(B, N, D) + pos).view(B * N, D)
+    _close(out, ref, 2e-3, "patch GEMM + bias + position embeddings")
 
 
 def test_merge_embeddings_and_positions():
@@ -175,3 +181,56 @@ def test_rmsnorm_warp_per_row(rows, D):
     torch.cuda.synchronize()
     ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * (1.0 + w)
     assert (y.float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6  # one bf16 rounding
+
+
+def test_projector_rows_scattered_by_the_gemm_epilogue():
+    """pg_merge_scan + projector GEMM with out_row_map + pg_merge_text == pg_merge_embeddings on materialised image features
+    (_merge_input_ids_with_image_features, modeling_paligemma.py:201-251): ragged image-token positions, pads, text."""
+    from paligemma_multimodal_system_b200 import _lib
+    L = _lib.lib()
+    B, N, T, D, Dv, V = 3, 256, 7, 256, 128, 1281
+    S = N + T
+    img_tok, pad = 1024, 0
+    g = torch.Generator(device="cuda").manual_seed(4)
+    ids = torch.randint(1, 1024, (B, S), device="cuda", generator=g)
+    ids[:, :N] = img_tok
+    ids[1] = torch.cat([ids[1, N:N + 3], torch.full((N,), img_tok, device="cuda"), ids[1, N + 3:]])  # image tokens not at the front
+    ids[2, -2:] = pad
+    mask = (ids != pad).long()
+    embed = (torch.randn(V, D, device="cuda", generator=g)).bfloat16()
+    feats = (torch.randn(B * N, Dv, device="cuda", generator=g) * 0.5).bfloat16()
+    wp = (torch.randn(D, Dv, device="cuda", generator=g) * 0.1).bfloat16()
+    bias = torch.randn(D, device="cuda", generator=g)
+    text_scale, img_scale = D ** 0.5, 0.93
+    # reference: materialise the projected features, then the one-call merge
+    img = torch.empty(B * N, D, device="cuda")
+    _lib.gemm(feats, wp, img, mode=_lib.EPI_F32, bias=bias, swap=0)
+    h_ref = torch.empty(B * S, D, device="cuda")
+    pos_ref = torch.empty(B * S, device="cuda", dtype=torch.int32)
+    src = torch.empty(B * S, device="cuda", dtype=torch.int32)
+    err = torch.zeros(1, device="cuda", dtype=torch.int32)
+    _lib.check(L.pg_merge_embeddings(ids.data_ptr(), mask.data_ptr(), embed.data_ptr(), img.data_ptr(), h_ref.data_ptr(), pos_ref.data_ptr(),
+                                     src.data_ptr(), err.data_ptr(), B, S, D, N, img_tok, pad, text_scale, img_scale, _lib.stream()), "merge")
+    # fused: scan -> projector scatters -> text rows
+    h = torch.full((B * S + 1, D), float("nan"), device="cuda")
+    pos = torch.empty(B * S, device="cuda", dtype=torch.int32)
+    src2 = torch.empty(B * S, device="cuda", dtype=torch.int32)
+    dst = torch.full((B * N,), B * S, device="cuda", dtype=torch.int32)
+    err2 = torch.zeros(1, device="cuda", dtype=torch.int32)
+    _lib.check(L.pg_merge_scan(ids.data_ptr(), mask.data_ptr(), pos.data_ptr(), src2.data_ptr(), dst.data_ptr(), err2.data_ptr(), B, S, N,
+                               img_tok, pad, _lib.stream()), "scan")
+    _lib.gemm(feats, wp, h, mode=_lib.EPI_F32, bias=bias, scale=img_scale, swap=0, out_row_map=dst)
+    _lib.check(L.pg_merge_text(ids.data_ptr(), src2.data_ptr(), embed.data_ptr(), h.data_ptr(), B, S, D, N, text_scale, _lib.stream()), "text")
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0 and int(err2.item()) == 0
+    assert torch.equal(pos, pos_ref) and torch.equal(src, src2)
+    assert sorted(dst.tolist()) == sorted((ids.view(-1) == img_tok).nonzero().view(-1).tolist())
+    assert not torch.isnan(h[: B * S]).any()
+    assert (h[: B * S] - h_ref).abs().max().item() <= 1e-5 * h_ref.abs().max().item()  # (acc + bias) * s vs ((acc + bias)) * s: one rounding
+    # a row with too few image tokens raises the flag; its orphan features go to the sink row
+    ids[0, 5] = 7
+    dst.fill_(B * S)
+    _lib.check(L.pg_merge_scan(ids.data_ptr(), mask.data_ptr(), pos.data_ptr(), src2.data_ptr(), dst.data_ptr(), err2.data_ptr(), B, S, N,
+                               img_tok, pad, _lib.stream()), "scan")
+    torch.cuda.synchronize()
+    assert int(err2.item()) == 1 and int((dst == B * S).sum()) == 1
