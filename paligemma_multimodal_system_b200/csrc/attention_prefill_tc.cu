@@ -332,13 +332,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(s_full(qt, sb), (j >> 1) & 1);
       tc_fence_after();
       float s[HB];
+      {
+        // every 16-column slice is requested before the one wait: the slices' TMEM round trips overlap instead of queueing
+        // (ncu at 4096 keys: tensor pipe 28 %, XU 45 %, issue 33 % -- nothing saturated, the softmax warps sit in latencies)
+        uint32_t v[HB / 16][16];
 #pragma unroll
-      for (int c0 = 0; c0 < HB; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(lane_addr + col_s + sb * BN + half * HB + c0, v);
+        for (int c0 = 0; c0 < HB; c0 += 16) tmem_ld16(lane_addr + col_s + sb * BN + half * HB + c0, v[c0 / 16]);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s[c0 + i] = __uint_as_float(v[i]);  // raw scores: the scale rides on the FFMA below
+        for (int i = 0; i < HB; ++i) s[i] = __uint_as_float(v[i / 16][i % 16]);  // raw scores: the scale rides on the FFMA below
       }
       tc_fence_before();
       __syncwarp();
@@ -352,9 +354,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int i = 0; i < HB; ++i)
           if (i >= nvalid) s[i] = -INFINITY;
       }
-      float mx = -INFINITY;
+      float mx;
+      {
+        // eight independent running maxima, then a tree: a single FMNMX chain over HB scores is HB dependent instructions
+        float m8[8];
 #pragma unroll
-      for (int i = 0; i < HB; ++i) mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < 8; ++i) m8[i] = s[i];
+#pragma unroll
+        for (int i = 8; i < HB; ++i) m8[i & 7] = fmaxf(m8[i & 7], s[i]);
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      }
       mx *= p.sl2;
       if constexpr (SW == 2) {  // row maximum over both halves (buffer sb is rewritten two tiles later, one barrier apart)
         xch[(sb * 2 + half) * 128 + r] = mx;
