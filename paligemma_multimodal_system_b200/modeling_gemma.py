@@ -306,7 +306,7 @@ class GemmaForCausalLM(nn.Module):
         # few-token prefills (latency path) keep narrower GEMM tiles and the separate RoPE / append launch
         fused = self.fused_qkv_rope
         if fused is None:
-            fused = False and dh in (64, 256) and ((T + 127) // 128) * (Hq + 2 * Hkv) >= 96  # (auto OFF until validated on the GPU)
+            fused = dh in (64, 256) and ((T + 127) // 128) * (Hq + 2 * Hkv) >= 96
         if fused:
             # q, k, v are column slices of `qkv` (token pitch W): the attention's tensor maps take the strides
             q, k, v = qkv, qkv[:, Hq * dh:], qkv[:, (Hq + Hkv) * dh:]
