@@ -25,6 +25,7 @@ SIGNATURES = {
     "pg_num_sms": [],
     "pg_launch_count": [],
     "pg_set_pdl": [i32],
+    "pg_prefetch_l2": [p, i64, i32, i32, p],
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_gemm_bn": [i32],
     "pg_debug_set_attn_trace": [p],

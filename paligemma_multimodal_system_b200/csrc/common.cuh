@@ -132,6 +132,9 @@ PG_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared
 PG_DEVINL void prefetch_l2_bulk(const void* ptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
+PG_DEVINL void prefetch_l2_bulk_hint(const void* ptr, uint32_t bytes, uint64_t hint) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ptr), "r"(bytes), "l"(hint) : "memory");
+}
 
 // PDL (programmatic dependent launch)
 PG_DEVINL void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -539,6 +539,33 @@ extern "C" int pg_rope_kv_append(const void* qkv, int qkv_is_f32, const int* pos
   PG_RET();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// L2 weight prefetch for the decode chain.  A decode layer streams 220 MB of weights, but for the ~24 us of its attention
+// block (norm, q/k/v, attention, o_proj, norm: seven kernel boundaries' worth of latency) the HBM pins idle.  This kernel
+// -- launched on a FORKED branch of the step's CUDA graph, so its launch is off the critical path -- asks the bulk-copy
+// engine to pull a contiguous weight range into L2 and exits; the GEMM that consumes the range later finds it there.
+// One 32-lane CTA per SM, every lane issues cp.async.bulk.prefetch.L2 for `chunk`-byte pieces (no registers, no shared
+// memory: co-resides with anything).  Never changes results.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) prefetch_l2_kernel(const char* __restrict__ p, long long bytes, int chunk, int evict_last) {
+  const long long n = (bytes + chunk - 1) / chunk;
+  for (long long c = static_cast<long long>(blockIdx.x) + static_cast<long long>(threadIdx.x) * gridDim.x; c < n;
+       c += static_cast<long long>(gridDim.x) * 32) {
+    const long long off = c * chunk;
+    const long long len = min(static_cast<long long>(chunk), bytes - off);
+    if (evict_last) prefetch_l2_bulk_hint(p + off, static_cast<uint32_t>(len & ~15ll), kEvictLast);
+    else prefetch_l2_bulk(p + off, static_cast<uint32_t>(len & ~15ll));
+  }
+}
+
+extern "C" int pg_prefetch_l2(const void* ptr, long long bytes, int ctas, int evict_last, void* stream) {
+  if (ptr == nullptr || bytes < 16 || (reinterpret_cast<uintptr_t>(ptr) & 15) || ctas < 0) return PG_ERR_ARG;
+  const int chunk = 16384;
+  pg_count_launch(1);
+  prefetch_l2_kernel<<<ctas == 0 ? num_sms() : ctas, 32, 0, PG_ST(stream)>>>(static_cast<const char*>(ptr), bytes, chunk, evict_last);
+  PG_RET();
+}
+
 extern "C" int pg_kv_gather(const void* pages, const int* page_table, void* dense, int B, int len, int Hkv, int dh,
                             int page_size, int max_pages, void* stream) {
   if (B <= 0 || len <= 0) return PG_ERR_ARG;

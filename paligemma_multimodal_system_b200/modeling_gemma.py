@@ -393,6 +393,17 @@ class GemmaForCausalLM(nn.Module):
             out[k] = t
         return out
 
+    # decode-step L2 weight prefetch (decode_layers): bytes of each layer's gate||up weights pulled into L2 during its
+    # attention block, and the number of 32-thread CTAs (= SMs whose bulk-copy engine streams, ~80 GB/s each) that pace it
+    l2_prefetch_bytes = 64 * 1000 * 1000
+    l2_prefetch_ctas = 64
+
+    def _prefetch_stream(self):
+        s = getattr(self, "_pf_stream", None)
+        if s is None or s.device != torch.device("cuda", torch.cuda.current_device()):
+            s = self._pf_stream = torch.cuda.Stream()
+        return s
+
     @torch.no_grad()
     def decode_layers(self, bufs, kv_cache: KVCache, B, inv_temperature: float = 1.0):
         """One decode step over all layers (modeling_gemma.py:385-418 at q_len == 1); reads bufs['h'] (fp32 embeddings),
@@ -422,9 +433,20 @@ class GemmaForCausalLM(nn.Module):
             # one CTA per output tile: the fp32 red.add has a single writer per element, so the step is bitwise
             # reproducible run to run (the split-K partials otherwise arrive in a different order every launch)
             sp_qkv = sp_o = sp_down = 1
+        # L2 weight prefetch on a forked branch (pg_prefetch_l2): while the attention block of a layer (q/k/v, attention, o_proj,
+        # norm: ~17 us of kernel-boundary latency with the HBM pins idle) runs, the bulk-copy engines of a few SMs pull the
+        # first `pf_bytes` of the layer's gate||up weights into L2.  Measured on the 64-sequence chain: 61.6 -> 58.9 us per
+        # layer (profiles/r02g_decode_l2_prefetch_sweep.txt); forked AFTER the q/k/v launch so that the stream does not
+        # queue ahead of the q/k/v weights and the KV pages, joined once at the end of the step.
+        pf_bytes = min(self.l2_prefetch_bytes, 2 * F * D * 2) & ~15
+        cur = torch.cuda.current_stream()
+        side = self._prefetch_stream() if pf_bytes >= 16 else None
         for li, lw in enumerate(pk["layers"]):
             _lib.rmsnorm(h, lw["ln1"], hn, eps=eps)
             _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
+            if side is not None:
+                side.wait_stream(cur)
+                _lib.check(L.pg_prefetch_l2(lw["gu_w"].data_ptr(), pf_bytes, self.l2_prefetch_ctas, 0, side.cuda_stream), "pg_prefetch_l2")
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
@@ -433,6 +455,8 @@ class GemmaForCausalLM(nn.Module):
             _lib.rmsnorm(h, lw["ln2"], hn, eps=eps)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)
             _lib.gemm(mid, lw["down_w"], h, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_down)
+        if side is not None:
+            cur.wait_stream(side)  # join (the last prefetch finished a layer ago)
         _lib.rmsnorm(h, pk["norm_w"], hn, eps=eps)
         _lib.gemm_fused(hn, pk["head_w"], bufs["logits"], mode=_lib.EPI_F32, bias=pk["head_b"], stats=bufs["stats"],
                         inv_temperature=inv_temperature)
