@@ -534,7 +534,9 @@ def main():
         k_gbs = k_bytes / (k_ms * 1e-3) / 1e9
         cap = ncu_capture_of_dominant_kernel() if B == 64 else None
         # per decode step: embed + 7 per layer (norm, qkv, attention, o, norm, gate||up, down) + final norm + head + sampler + advance
-        graph_kernels = 7 * cfg["text_config"]["num_hidden_layers"] + 5
+        #   + one pg_prefetch_l2 launch per layer on the forked branch (L2 weight prefetch)
+        pf_on = model.language_model.l2_prefetch_bytes >= 16
+        graph_kernels = (8 if pf_on else 7) * cfg["text_config"]["num_hidden_layers"] + 5
         flops_img = algorithmic_flops_per_image(cfg, S)
         line = {
             "metric": "decode_tokens_per_s", "value": decode_tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,

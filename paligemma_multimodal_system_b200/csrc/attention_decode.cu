@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(256) attn_decode_v3_kernel(const __grid_consta
   // byte offset of element (row r, column c) inside a swizzled K (or V) page
   auto swz = [&](int r, int c) -> int { return (c >> 6) * BOX_BYTES + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
 
+  // the page that receives the new token's key / value: known before the wait (the table belongs to earlier kernels), so the
+  // owning rank does not pay a second dependent L2 round trip after it
+  const int new_page = owns_new ? __ldg(ptab + new_tile) : 0;
   // (measured, not kept: computing sincos before the wait, and signalling the rank merge through per-rank mbarriers
   //  instead of the cluster barrier -- the cluster-scope release of the pushed partials costs the ~1.5 us, not the barrier)
   griddep_wait();  // the qkv row of the new token
@@ -182,8 +185,7 @@ __global__ void __launch_bounds__(256) attn_decode_v3_kernel(const __grid_consta
       }
     }
     if (do_k || do_v) {
-      const int page = __ldg(ptab + new_tile);
-      const long long off = (static_cast<long long>(page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
+      const long long off = (static_cast<long long>(new_page) * BLOCK_N + (new_slot - new_tile * BLOCK_N)) * kv_ts + hk * DH;
       if (do_k) {
         const bf16 k1 = __float2bfloat16(kx1 * cs - kx2 * sn), k2 = __float2bfloat16(kx2 * cs + kx1 * sn);
         p.k_pages[off + i] = k1; p.k_pages[off + i + HALF] = k2;  // KVCache.update (modeling_gemma.py:18-57)

@@ -9,6 +9,7 @@ Compute path per layer (all through the C ABI of include/paligemma_b200.h):
 The residual stream is fp32 (as in the reference); GEMM operands are bf16.
 """
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -394,9 +395,8 @@ class GemmaForCausalLM(nn.Module):
         return out
 
     # decode-step L2 weight prefetch (decode_layers): bytes of each layer's gate||up weights pulled into L2 during its
-    # attention block, and the number of 32-thread CTAs (= SMs whose bulk-copy engine streams, ~80 GB/s each) that pace it
-    l2_prefetch_bytes = 64 * 1000 * 1000
-    l2_prefetch_ctas = 64
+    # attention block (0 disables: A/B runs)
+    l2_prefetch_bytes = int(float(os.environ.get("PG_L2_PREFETCH_MB", "64")) * 1e6)
 
     def _prefetch_stream(self):
         s = getattr(self, "_pf_stream", None)
@@ -435,22 +435,32 @@ class GemmaForCausalLM(nn.Module):
             sp_qkv = sp_o = sp_down = 1
         # L2 weight prefetch on a forked branch (pg_prefetch_l2): while the attention block of a layer (q/k/v, attention, o_proj,
         # norm: ~17 us of kernel-boundary latency with the HBM pins idle) runs, the bulk-copy engines of a few SMs pull the
-        # first `pf_bytes` of the layer's gate||up weights into L2.  Measured on the 64-sequence chain: 61.6 -> 58.9 us per
-        # layer (profiles/r02g_decode_l2_prefetch_sweep.txt); forked AFTER the q/k/v launch so that the stream does not
-        # queue ahead of the q/k/v weights and the KV pages, joined once at the end of the step.
-        pf_bytes = min(self.l2_prefetch_bytes, 2 * F * D * 2) & ~15
+        # head of the layer's gate||up weights into L2.  Measured per layer (profiles/r02g_decode_l2_prefetch_sweep.txt):
+        # 64 x 324 keys 61.6 -> 58.9 us, 1 x 324 51.9 -> 48.5, 32 x 1092 63.9 -> 61.2, 8 x 4164 63.6 -> 63.1.  The stream
+        # must not queue ahead of the loads on the critical path: it is forked AFTER the q/k/v launch (64 MB, 32 SMs) when
+        # the KV pages of a layer are small, and after the attention launch (48 MB, 64 SMs) when attention itself streams
+        # tens of MB; joined once at the end of the step.
+        pf_late = B * kv_cache.capacity * Hkv * dh * 4 > 32e6
+        pf_bytes = min(self.l2_prefetch_bytes * 3 // 4 if pf_late else self.l2_prefetch_bytes, 2 * F * D * 2) & ~15
+        pf_ctas = 64 if pf_late else 32
         cur = torch.cuda.current_stream()
         side = self._prefetch_stream() if pf_bytes >= 16 else None
+
+        def prefetch(lw):
+            side.wait_stream(cur)
+            _lib.check(L.pg_prefetch_l2(lw["gu_w"].data_ptr(), pf_bytes, pf_ctas, 0, side.cuda_stream), "pg_prefetch_l2")
+
         for li, lw in enumerate(pk["layers"]):
             _lib.rmsnorm(h, lw["ln1"], hn, eps=eps)
             _lib.gemm(hn, lw["qkv_w"], qkv, mode=_lib.EPI_ATOMIC_F32, swap=1, split_k=sp_qkv)
-            if side is not None:
-                side.wait_stream(cur)
-                _lib.check(L.pg_prefetch_l2(lw["gu_w"].data_ptr(), pf_bytes, self.l2_prefetch_ctas, 0, side.cuda_stream), "pg_prefetch_l2")
+            if side is not None and not pf_late:
+                prefetch(lw)
             _lib.check(L.pg_attention_decode_fused(
                 qkv.data_ptr(), pos.data_ptr(), kvl.data_ptr(), pk["inv_freq"].data_ptr(), kv_cache.k_pages[li].data_ptr(),
                 kv_cache.v_pages[li].data_ptr(), kv_cache.page_table.data_ptr(), att.data_ptr(), B, Hq, Hkv, dh, PAGE,
                 kv_cache.k_pages.shape[1], max_pages, scale, st), "pg_attention_decode_fused")
+            if side is not None and pf_late:
+                prefetch(lw)
             _lib.gemm_fused(att, lw["o_w"], h, mode=_lib.EPI_ATOMIC_F32, split_k=sp_o, zero_buf=qkv)
             _lib.rmsnorm(h, lw["ln2"], hn, eps=eps)
             _lib.gemm(hn, lw["gu_w"], mid, mode=_lib.EPI_GEGLU, swap=1)

@@ -84,6 +84,14 @@ def graph_time(name, fn, reps=5):
 
 print(f"==== B={B} kv={kvlen}")
 graph_time("LAYER baseline", lambda i: layer(i))
+for ctas in (32, 64, 148):
+    for mb in (48, 64, 80):
+        graph_time(f"G {mb} MB forked after qkv, {ctas} CTAs", lambda i: layer(i, ((2, "g", mb, ctas, 0),)))
+for ctas in (64, 148):
+    for mb in (32, 48, 64):
+        graph_time(f"G {mb} MB forked after attention, {ctas} CTAs", lambda i: layer(i, ((3, "g", mb, ctas, 0),)))
+graph_time("G 32 MB after qkv (32) + 32 MB after attention (148)", lambda i: layer(i, ((2, "g", 32, 32, 0), (3, "g", 32, 148, 32))))
+sys.exit(0)
 for el in (0, 1):
     graph_time(f"G 64 MB after qkv (64), evict_last={el}", lambda i: layer(i, ((2, "g", 64, 64, 0, el),)))
     for at, nm in ((0, "layer start"), (2, "after qkv"), (3, "after attention")):
