@@ -28,6 +28,7 @@ SIGNATURES = {
     "pg_prefetch_l2": [p, i64, i32, i32, p],
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_gemm_bn": [i32],
+    "pg_debug_set_gemm_pair": [i32, i32],
     "pg_debug_set_attn_trace": [p],
     "pg_debug_set_sampler_cluster": [i32],
     "pg_debug_topp_retries": [],
@@ -90,6 +91,8 @@ def lib():
         _lib = l
         if os.environ.get("PG_PDL", "1") == "0":
             l.pg_set_pdl(0)
+        if os.environ.get("PG_GEMM_PAIR", "1") == "0":  # A/B runs: one-CTA prefill GEMM only
+            l.pg_debug_set_gemm_pair(0, 0)
     return _lib
 
 

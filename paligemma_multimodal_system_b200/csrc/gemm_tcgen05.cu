@@ -630,6 +630,72 @@ PG_DEVINL void geglu_swap_epilogue(const GemmArgs& args, uint32_t taddr, float* 
   geglu_swap_epilogue_group<BN>(args, taddr, xch, bar, q, lane, et, j_base, m_blk);
 }
 
+// Epilogue of one token-major 128 x BN accumulator tile (TMEM lanes = tokens): the per-call-site variants of the prefill GEMMs.
+// Shared by the one-CTA kernel and the CTA-pair kernel (whose two CTAs each own 128 of the pair's 256 token rows).
+// EPI8: eight epilogue warps, two per TMEM lane quadrant, each takes half of the tile's columns.
+template <int BN, bool EPI8, bool ROPE>
+PG_DEVINL void token_major_epilogue(const GemmArgs& args, uint32_t taddr, int m_blk, int n_blk, bool first_split, int warp, int lane,
+                                    uint32_t xch_base) {
+  const int q = warp & 3;
+  const int rl = q * 32 + lane;
+  const int mode = args.mode;
+  __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(args.out);
+  const int tok = m_blk * BM + rl;
+  const bool row_ok = tok < args.tokens;
+  // eight epilogue warps: two per TMEM lane quadrant, each takes half of the tile's columns
+  const int half = EPI8 ? ((warp - 2) >> 2) : 0;
+  const uint32_t wstage = xch_base + (warp - 2) * 4096;  // this warp's transposition tile
+  const int rows_valid = max(0, min(32, args.tokens - (m_blk * BM + q * 32)));
+  // column range of this warp: halves of >= 64 columns (BN = 64: the first warp of the pair takes everything)
+  const int cb = !EPI8 ? 0 : (BN >= 128 ? half * (BN / 2) : (half == 0 ? 0 : BN));
+  const int ce = !EPI8 ? BN : (BN >= 128 ? cb + BN / 2 : BN);
+  if constexpr (ROPE) {
+    qkv_rope_tile_epilogue<BN>(args, taddr, tok, n_blk, wstage, rows_valid, lane, m_blk * BM + q * 32);
+  } else if (mode == PG_EPI_GEGLU) {
+    // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c.  The 64 bf16
+    // results of a block (one 128-byte row per token) leave through the warp transposition tile as full lines.
+    const bool al = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo % 8) == 0);
+#pragma unroll 1
+    for (int blk = ((EPI8 && BN >= 256) ? half : 0); blk < ((EPI8 && BN >= 256) ? half + 1 : (half == 0 ? BN / 128 : 0)); ++blk) {
+      const int f0 = n_blk * (BN / 2) + blk * 64;
+      if (f0 >= args.features / 2) break;  // warp-uniform (features % 128 == 0)
+      uint32_t pk[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t g[16], u[16];
+        tmem_ld16(taddr + blk * 128 + c0, g);
+        tmem_ld16(taddr + blk * 128 + 64 + c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = gelu_tanh_fast(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
+          float b = gelu_tanh_fast(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
+          pk[(c0 / 2 + i) & 31] = pack_bf16(a, b);
+        }
+      }
+      if (al) {
+        warp_store_rows_128B(wstage, lane, pk, reinterpret_cast<char*>(out_bf + static_cast<long long>(m_blk * BM + q * 32) * args.ldo + f0),
+                             args.ldo * 2, rows_valid, true);
+      } else if (row_ok) {
+        __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(dst + 2 * i) = pk[i];
+      }
+    }
+  } else if (mode == PG_EPI_BF16) {
+    rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
+  } else if (mode == PG_EPI_F32) {
+    // (measured: pulling the NEXT tile's residual rows into L2 from here does not help: o_proj 926 -> 824 TFLOP/s)
+    if (args.f32_coalesced)
+      rowmajor_tile_epilogue_f32_coalesced<BN>(args, taddr, m_blk * BM, n_blk * BN, first_split,
+                                               wstage, q, lane, cb / 32, ce / 32);
+    else
+      rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
+  } else {
+    rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
+  }
+}
+
 // SPLITK = true: swap-AB kernel specialised for the split-K red.add epilogue with EIGHT epilogue warps (two per TMEM lane
 // quadrant, half of the token columns each).  With one CTA per SM (qkv / o_proj: ~144 CTAs) the 64 dependent red
 // instructions per thread are the serial tail of the launch; two warps per quadrant halve it.  Everything but the
@@ -811,60 +877,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                                                     half * HALF_COLS, (half + 1) * HALF_COLS);
         }
       } else if constexpr (!SWAP) {
-        const int tok = t.m_blk * BM + rl;
-        const bool row_ok = tok < args.tokens;
-        // eight epilogue warps: two per TMEM lane quadrant, each takes half of the tile's columns
-        const int half = SPLITK ? ((warp - 2) >> 2) : 0;
-        const uint32_t wstage = smem_base + STAGES * STAGE_BYTES + (warp - 2) * 4096;  // this warp's transposition tile
-        const int rows_valid = max(0, min(32, args.tokens - (t.m_blk * BM + q * 32)));
-        // column range of this warp: halves of >= 64 columns (BN = 64: the first warp of the pair takes everything)
-        const int cb = !SPLITK ? 0 : (BN >= 128 ? half * (BN / 2) : (half == 0 ? 0 : BN));
-        const int ce = !SPLITK ? BN : (BN >= 128 ? cb + BN / 2 : BN);
-        if constexpr (ROPE) {
-          qkv_rope_tile_epilogue<BN>(args, taddr, tok, t.n_blk, wstage, rows_valid, lane, t.m_blk * BM + q * 32);
-        } else if (mode == PG_EPI_GEGLU) {
-          // columns: [g0..g63 | u0..u63] per 128-column block; out feature = n_blk*BN/2 + blk*64 + c.  The 64 bf16
-          // results of a block (one 128-byte row per token) leave through the warp transposition tile as full lines.
-          const bool al = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo % 8) == 0);
-#pragma unroll 1
-          for (int blk = ((SPLITK && BN >= 256) ? half : 0); blk < ((SPLITK && BN >= 256) ? half + 1 : (half == 0 ? BN / 128 : 0)); ++blk) {
-            const int f0 = t.n_blk * (BN / 2) + blk * 64;
-            if (f0 >= args.features / 2) break;  // warp-uniform (features % 128 == 0)
-            uint32_t pk[32];
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-              uint32_t g[16], u[16];
-              tmem_ld16(taddr + blk * 128 + c0, g);
-              tmem_ld16(taddr + blk * 128 + 64 + c0, u);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float a = gelu_tanh_fast(__uint_as_float(g[2 * i])) * __uint_as_float(u[2 * i]);
-                float b = gelu_tanh_fast(__uint_as_float(g[2 * i + 1])) * __uint_as_float(u[2 * i + 1]);
-                pk[(c0 / 2 + i) & 31] = pack_bf16(a, b);
-              }
-            }
-            if (al) {
-              warp_store_rows_128B(wstage, lane, pk, reinterpret_cast<char*>(out_bf + static_cast<long long>(t.m_blk * BM + q * 32) * args.ldo + f0),
-                                   args.ldo * 2, rows_valid, true);
-            } else if (row_ok) {
-              __nv_bfloat16* dst = out_bf + static_cast<long long>(tok) * args.ldo + f0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(dst + 2 * i) = pk[i];
-            }
-          }
-        } else if (mode == PG_EPI_BF16) {
-          rowmajor_tile_epilogue<BN, PG_EPI_BF16>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
-        } else if (mode == PG_EPI_F32) {
-          // (measured: pulling the NEXT tile's residual rows into L2 from here does not help: o_proj 926 -> 824 TFLOP/s)
-          if (args.f32_coalesced)
-            rowmajor_tile_epilogue_f32_coalesced<BN>(args, taddr, t.m_blk * BM, t.n_blk * BN, first_split,
-                                                     wstage, q, lane, cb / 32, ce / 32);
-          else
-            rowmajor_tile_epilogue<BN, PG_EPI_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
-        } else {
-          rowmajor_tile_epilogue<BN, PG_EPI_ATOMIC_F32>(args, taddr, tok, t.n_blk * BN, first_split, wstage, rows_valid, lane, cb, ce);
-        }
+        token_major_epilogue<BN, SPLITK, ROPE>(args, taddr, t.m_blk, t.n_blk, first_split, warp, lane, smem_base + STAGES * STAGE_BYTES);
       } else {
         // SWAP: this thread owns weight row (feature) fr; columns are tokens
         const int fr = t.m_blk * BM + rl;
@@ -899,11 +912,174 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (prefill, token-major, 256 x 256 output tile per pair of SMs): tcgen05.mma.cta_group::2.
+// Each CTA of a 2-CTA cluster stages its 128 token rows of A and HALF of the 256 weight rows of B per k-block (32 KB per
+// stage instead of 48 KB: a third less L2 -> shared-memory traffic per FLOP, which is what the power-capped prefill pays
+// for), the leader issues 256 x 256 x 16 UMMAs that read both CTAs' shared memory, and every CTA's tensor memory receives its
+// own 128 x 256 fp32 accumulator, which its epilogue warps drain exactly like a tile of the one-CTA kernel.
+//   full[s]   (leader)     : 1 arrival (leader's expect_tx of 64 KB) + the bytes of BOTH CTAs' TMA loads
+//   empty[s]  (both CTAs)  : the leader's tcgen05.commit, multicast to the pair
+//   tfull[a]  (both CTAs)  : the leader's tcgen05.commit after the last k-block of a tile, multicast
+//   tempty[a] (leader)     : 2 x NEPI arrivals, the epilogue warps of both CTAs
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + (PAIR_BN / 2) * BK * 2;  // 32 KB
+constexpr int PAIR_STAGES = (232448 - 256 - 8 * 4096) / PAIR_STAGE_BYTES;  // 6
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + 8 * 4096 + 256;
+
+template <bool EPI8, bool ROPE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI8 ? 320 : NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmArgs args) {
+  constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES, STAGE_BYTES = PAIR_STAGE_BYTES;
+  constexpr int NEPI = EPI8 ? 8 : 4;
+  constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t xch_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = xch_base + 8 * 4096;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + STAGES * STAGE_BYTES + 8 * 4096 + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = rank == 0;
+  const int m_blocks = (args.tokens + 2 * BM - 1) / (2 * BM);  // 256-token blocks
+  const int n_blocks = (args.features + BN - 1) / BN;
+  const int total_kb = (args.K + BK - 1) / BK;
+  const int num_tiles = m_blocks * n_blocks;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * NEPI);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr_addr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before either signals the other's
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // =================================== TMA producer (both CTAs) ===================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      griddep_wait();
+      griddep_launch_dependents();
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, 1, args.n_fast);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmapA, full_bar(stage), kb * BK, (2 * t.m_blk + rank) * BM, kEvictNormal);
+          tma_load_2d_pair(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN + rank * (BN / 2), kEvictNormal);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================== MMA issuer (leader CTA only) ===============================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_sdesc_k_sw128(sa);
+          const uint64_t bdesc = make_sdesc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));
+          if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== epilogue warps (both CTAs) =================================
+    const int q = warp & 3;
+    griddep_wait();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileInfo t = decode_tile(tile, m_blocks, n_blocks, total_kb, 1, args.n_fast);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      token_major_epilogue<BN, EPI8, ROPE>(args, taddr, 2 * t.m_blk + rank, t.n_blk, true, warp, lane, xch_base);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its tensor memory until the very end
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <bool EPI8, bool ROPE>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_tiles, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    if (cudaFuncSetAttribute(gemm_pair_kernel<EPI8, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM) != cudaSuccess) {
+      cudaGetLastError();
+      return PG_ERR_CUDA;
+    }
+    configured[dev] = true;
+  }
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
+  return launch_kernel(gemm_pair_kernel<EPI8, ROPE>, dim3(grid), dim3(EPI8 ? 320 : NUM_THREADS), PAIR_SMEM, st, ta, tb, a) == cudaSuccess
+             ? PG_OK : PG_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_idx = 0;
 extern "C" int pg_debug_set_gemm_trace(long long* p) { g_gemm_trace = p; g_gemm_trace_idx = 0; return 0; }
+static int g_pair_mode = 1;        // 0: never use the CTA-pair kernel (A/B runs)
+static int g_pair_min_tiles = 74;  // at least one 256 x 256 tile per pair of SMs
+extern "C" int pg_debug_set_gemm_pair(int mode, int min_tiles) {
+  g_pair_mode = mode;
+  if (min_tiles > 0) g_pair_min_tiles = min_tiles;
+  return 0;
+}
 static int g_force_bn = 0;  // tuning sweeps only: 64 / 128 / 256 overrides the token-major kernel's N tile, 0 = automatic
 extern "C" int pg_debug_set_gemm_bn(int bn) {
   if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return PG_ERR_ARG;
@@ -1030,6 +1206,13 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
       if (g_force_bn) BN = g_force_bn;
     }
     if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
+    // many tokens: a PAIR of CTAs per 256 x 256 tile (cta_group::2), each staging half of the weight tile
+    const int pair_tiles = ((tokens + 2 * BM - 1) / (2 * BM)) * ((features + 255) / 256);
+    // (measured per call site, profiles/r02h_gemm_pair_ab.txt: +2..16 % everywhere but the gelu epilogue of fc1, -3 %)
+    if (g_pair_mode != 0 && BN == 256 && split_k == 1 && pair_tiles >= g_pair_min_tiles && !(mode == PG_EPI_BF16 && act_gelu)) {
+      if ((rc = make_tmap_2d(&tb, w, features, K, ldw, PAIR_BN / 2)) != PG_OK) return rc;
+      return K <= 1536 ? launch_pair<true, false>(ta, tb, a, pair_tiles, st) : launch_pair<false, false>(ta, tb, a, pair_tiles, st);
+    }
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
     const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;
     // short reduction (K <= 1536: the SigLIP projections): the epilogue outlasts the main loop, so it gets eight warps
@@ -1068,5 +1251,10 @@ extern "C" int pg_gemm_qkv_rope(const void* x, long long ldx, const void* w, lon
   if ((rc = make_tmap_2d(&tb, w, features, K, ldw, dh)) != PG_OK) return rc;
   const int tiles = ((tokens + BM - 1) / BM) * (Hq + 2 * Hkv);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int pair_tiles = ((tokens + 2 * BM - 1) / (2 * BM)) * (Hq + 2 * Hkv);
+  if (dh == 256 && g_pair_mode != 0 && pair_tiles >= g_pair_min_tiles) {  // CTA pair: 256 tokens x one head per tile
+    if ((rc = make_tmap_2d(&tb, w, features, K, ldw, PAIR_BN / 2)) != PG_OK) return rc;
+    return launch_pair<false, true>(ta, tb, a, pair_tiles, st);
+  }
   return dh == 256 ? launch<256, false, false, true>(ta, tb, a, tiles, st) : launch<64, false, false, true>(ta, tb, a, tiles, st);
 }

@@ -4,7 +4,7 @@ gate||up slices of 16..128 MB: cold (18 matrices in rotation), hot (same matrix 
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from paligemma_multimodal_system_b200 import _lib
-B, D = 64, 2048
+B, D = int(os.environ.get("MB_B", 64)), 2048
 dev = "cuda"
 hn = (torch.randn(B, D, device=dev) * 0.02).bfloat16()
 

@@ -1,5 +1,5 @@
-"""Prefill time per image at the three BASELINE geometries (3B widths, HBM-resident inputs, CUDA events), with the q/k/v
-projection's RoPE + KV-append epilogue off / on.   python profiles/tools/prefill_bench.py [224 448 896]"""
+"""Prefill time per image at the three BASELINE geometries (3B widths, HBM-resident inputs, CUDA events), with the
+CTA-pair (cta_group::2) GEMM off / on.   python profiles/tools/prefill_bench.py [224 448 896]"""
 import os
 import sys
 
@@ -18,14 +18,15 @@ for size in sizes:
     model, _ = build_gpu_model(cfg)
     inp = {k: v.cuda() for k, v in make_inputs(cfg, batch=B, prompt_len=PROMPT_LEN, seed=100).items()}
     S = inp["input_ids"].shape[1]
-    for fused in (False, True, False, True):
-        model.language_model.fused_qkv_rope = fused
+    from paligemma_multimodal_system_b200 import _lib
+    for fused in (False, True, False, True):  # (A/B switch reused: False = one-CTA GEMM only, True = CTA-pair GEMM)
+        _lib.lib().pg_debug_set_gemm_pair(1 if fused else 0, 0)
         kv = KVCache()
         for _ in range(2):
             model.forward(inp["input_ids"], inp["pixel_values"], inp["attention_mask"], kv_cache=None, last_only=True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 4
+        reps = 8
         e0.record()
         for _ in range(reps):
             kv = KVCache(reserve_tokens=8)
@@ -34,6 +35,6 @@ for size in sizes:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps / B
         fl = algorithmic_flops_per_image(cfg, S)
-        print(f"{size} px x {B}: fused_qkv_rope={fused}: {ms:.3f} ms/image = {fl / ms / 1e9:.0f} TFLOP/s = {fl / ms / 1e9 / tf_peak:.3f} of sustained peak", flush=True)
+        print(f"{size} px x {B}: gemm_pair={fused}: {ms:.3f} ms/image = {fl / ms / 1e9:.0f} TFLOP/s = {fl / ms / 1e9 / tf_peak:.3f} of sustained peak", flush=True)
     del model
     torch.cuda.empty_cache()
