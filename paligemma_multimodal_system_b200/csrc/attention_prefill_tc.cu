@@ -38,6 +38,8 @@ struct Params {
   long long o_bs, o_ts, o_hs, o_head_off;
   float sl2;  // softmax scale * log2(e)
   const int* key_lens;  // optional [B]: problem b only attends to its first key_lens[b] keys (ragged prompts); else nullptr
+  int stagger;          // QT = 2 (tuning): clock cycles the softmax group of query tile 1 idles after its first S tile is ready
+  long long* trace;     // optional clock64 stamps of CTA (0,0,0): [role][tile][event], see profiles/tools/attn_prefill_trace.py
 };
 
 template <int DH, int QT>
@@ -120,7 +122,7 @@ PG_DEVINL float exp2_mufu(float x) {
 // memory -- the kernel is bound by K/V delivery through the crossbar (profiles/r01d_prefill_attn72_ncu_full.csv), and two
 // query tiles halve the K/V bytes per FLOP; softmax warps 2-5 own tile 0, warps 6-9 tile 1 (no exchange between them).
 template <int DH, int SW, int QT>
-__global__ void __launch_bounds__(64 + 128 * SW * QT, 1)
+__global__ void __launch_bounds__(96 + 128 * SW * QT, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Params p) {
   static_assert(SW * QT <= 2, "eight softmax warps at most");
@@ -153,6 +155,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // profiling stamps (tiles 0..31 of CTA (0,0,0)): role 0 = MMA issuer, 1 = softmax warp 2, 2 = softmax warp 6; 8 events per tile
+  const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  auto stamp = [&](int role, int j, int ev) {
+    if (tr_on && j < 32) p.trace[(role * 32 + j) * 8 + ev] = clock64();
+  };
   // ragged batches: keys [key_lens[b], keys) of problem b exist in memory (padding tokens, finite values) but weigh nothing
   const int n_keys = p.key_lens ? max(1, min(p.keys, __ldg(p.key_lens + b))) : p.keys;
   const int n_tiles = (n_keys + BN - 1) / BN;
@@ -210,17 +217,20 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if constexpr (TCSUM) {
-      // whole warp: every lane plants its share of the ones column into the V tile that just landed, lane 0 issues
-      auto issue_s = [&](int j) {
-        const int ks = j % KST, sb = j & 1;
-        mbar_wait(k_full(ks), (j / KST) & 1);
-        const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
+    // All 32 lanes run the loop and ONE elected lane issues: with uniform control flow the compiler keeps the descriptors
+    // and TMEM addresses in uniform registers.  (Under `if (lane == 0)` every tcgen05.mma paid an ELECT + R2UR.BROADCAST
+    // chain per operand, ~115 clk per instruction: the issuer, not the softmax or the tensor pipe, paced the kernel --
+    // profiles/r02h_attn_prefill_trace_before.txt.)
+    auto issue_s = [&](int j) {  // S_j = Q K_j^T of every query tile into its S buffer j % 2
+      const int ks = j % KST, sb = j & 1;
+      mbar_wait(k_full(ks), (j / KST) & 1);
+      const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
 #pragma unroll
-        for (int qt = 0; qt < QT; ++qt) {
-          mbar_wait(s_empty(qt, sb), ((j >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + C::COL_S + (qt * 2 + sb) * BN;
+      for (int qt = 0; qt < QT; ++qt) {
+        mbar_wait(s_empty(qt, sb), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + C::COL_S + (qt * 2 + sb) * BN;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < DHP / 16; ++k) {
             const uint64_t adesc = make_sdesc_k_sw128(sbase + qt * C::Q_BYTES + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
@@ -228,78 +238,47 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
           }
           umma_commit(s_full(qt, sb));
-        }
-        umma_commit(k_empty(ks));
-      };
-      mbar_wait(q_full, 0);
-      if (lane == 0) issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (lane == 0 && j + 1 < n_tiles) issue_s(j + 1);
-        const int vs = j % VST, pb = j & 1;
-        mbar_wait(v_full(vs), (j / VST) & 1);
-        const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
-        {
-          // column DH (= 72) lives in box DH / 64, 16-byte chunk (DH % 64) / 8, element DH % 8 of key row r (128B swizzle)
-          constexpr uint32_t BOX = DH / 64, CH = (DH % 64) / 8, EL = DH % 8;
-          for (int r = lane; r < BN; r += 32) {
-            const uint32_t addr = vaddr + BOX * C::KV_BOX + r * 128 + ((CH ^ (r & 7)) << 4) + EL * 2;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(0x3F80)) : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int qt = 0; qt < QT; ++qt) {
-            mbar_wait(p_full(qt, pb), (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + C::COL_O + qt * C::O_STRIDE;
-            const uint32_t paddr = sbase + C::OFF_P + (qt * 2 + pb) * C::P_BYTES;
-#pragma unroll
-            for (int k = 0; k < BN / 16; ++k) {
-              const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
-              const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);
-              umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(o_done(qt));
-          }
-          umma_commit(v_empty(vs));
+          if (qt == QT - 1) umma_commit(k_empty(ks));
         }
         __syncwarp();
       }
-    } else if (lane == 0) {
-      auto issue_s = [&](int j) {  // S_j = Q K_j^T of every query tile into its S buffer j % 2
-        const int ks = j % KST, sb = j & 1;
-        mbar_wait(k_full(ks), (j / KST) & 1);
-        const uint32_t kaddr = sbase + C::OFF_K + ks * C::KV_BYTES;
-#pragma unroll
-        for (int qt = 0; qt < QT; ++qt) {
-          mbar_wait(s_empty(qt, sb), ((j >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + C::COL_S + (qt * 2 + sb) * BN;
-#pragma unroll
-          for (int k = 0; k < DHP / 16; ++k) {
-            const uint64_t adesc = make_sdesc_k_sw128(sbase + qt * C::Q_BYTES + (k >> 2) * C::Q_BOX) + 2 * (k & 3);
-            const uint64_t bdesc = make_sdesc_k_sw128(kaddr + (k >> 2) * C::KV_BOX) + 2 * (k & 3);
-            umma_f16(d_tmem, adesc, bdesc, IDESC_S, k > 0 ? 1u : 0u);
-          }
-          umma_commit(s_full(qt, sb));
+    };
+    // The S issuer (this warp) and the P V issuer (the last warp) are separate instruction streams: a tcgen05.mma blocks its
+    // issuing thread while the tensor pipe's queue is full, so one stream serialised S_{j+1}, its barrier round trips, the
+    // ones column and P_j V_j into 2300 clk per 128-key tile -- longer than the softmax it was supposed to hide behind.
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      stamp(0, j, 0);
+      issue_s(j);
+      stamp(0, j, 1);
+    }
+  } else if (warp == 2 + 4 * SW * QT) {
+    // ============================== P V issuer ================================
+    for (int j = 0; j < n_tiles; ++j) {
+      const int vs = j % VST, pb = j & 1;
+      mbar_wait(v_full(vs), (j / VST) & 1);
+      stamp(0, j, 2);
+      const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
+      if constexpr (TCSUM) {
+        // every lane plants its share of the ones column into the V tile that just landed:
+        // column DH (= 72) lives in box DH / 64, 16-byte chunk (DH % 64) / 8, element DH % 8 of key row r (128B swizzle)
+        constexpr uint32_t BOX = DH / 64, CH = (DH % 64) / 8, EL = DH % 8;
+        for (int r = lane; r < BN; r += 32) {
+          const uint32_t addr = vaddr + BOX * C::KV_BOX + r * 128 + ((CH ^ (r & 7)) << 4) + EL * 2;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(0x3F80)) : "memory");
         }
-        umma_commit(k_empty(ks));
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        const int vs = j % VST, pb = j & 1;
-        mbar_wait(v_full(vs), (j / VST) & 1);
-        const uint32_t vaddr = sbase + C::OFF_V + vs * C::KV_BYTES;
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      stamp(0, j, 3);
 #pragma unroll
-        for (int qt = 0; qt < QT; ++qt) {
-          mbar_wait(p_full(qt, pb), (j >> 1) & 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + C::COL_O + qt * C::O_STRIDE;
-          const uint32_t paddr = sbase + C::OFF_P + (qt * 2 + pb) * C::P_BYTES;
+      for (int qt = 0; qt < QT; ++qt) {
+        mbar_wait(p_full(qt, pb), (j >> 1) & 1);
+        if (qt == 0) stamp(0, j, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + C::COL_O + qt * C::O_STRIDE;
+        const uint32_t paddr = sbase + C::OFF_P + (qt * 2 + pb) * C::P_BYTES;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BN / 16; ++k) {
             const uint64_t adesc = make_sdesc_k_sw128(paddr + (k >> 2) * C::P_BOX) + 2 * (k & 3);
@@ -307,11 +286,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(o_done(qt));
+          if (qt == QT - 1) umma_commit(v_empty(vs));
         }
-        umma_commit(v_empty(vs));
+        __syncwarp();
       }
+      stamp(0, j, 5);
     }
-    __syncwarp();
   } else {
     // ============================== softmax / epilogue ========================
     constexpr int HB = BN / SW;         // score columns of a tile owned by one thread
@@ -329,7 +309,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t p_row = sbase + C::OFF_P + qt * 2 * C::P_BYTES + r * 128;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
+      const int trole = warp == 2 ? 1 : (warp == 6 ? 2 : 3);
+      if (trole < 3) stamp(trole, j, 0);
       mbar_wait(s_full(qt, sb), (j >> 1) & 1);
+      if constexpr (QT == 2) {
+        if (j == 0 && qt == 1 && p.stagger > 0) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger) {}
+        }
+      }
+      if (trole < 3) stamp(trole, j, 1);
       tc_fence_after();
       float s[HB];
       {
@@ -344,6 +333,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
+      if (trole < 3) stamp(trole, j, 2);
       if (lane == 0) mbar_arrive(s_empty(qt, sb));  // the S buffer may be overwritten by S_{j+2}
       // The softmax warps are bound by instruction issue (ncu: ~9 instructions per score, XU pipe 39 %, tensor pipe 24 %), so
       // the per-score work is kept to FMNMX, FFMA, MUFU, FADD and half an F2FP: keys are only masked in the one tile that
@@ -370,6 +360,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         pair_sync();
         mx = fmaxf(mx, xch[(sb * 2 + (half ^ 1)) * 128 + r]);
       }
+      if (trole < 3) stamp(trole, j, 3);
       // lazy running maximum: only move it when it grew by more than 8 (log2 units); probabilities stay <= 2^8
       const bool need = mx > m_used + 8.0f;
       const float m_new = need ? mx : m_used;
@@ -377,15 +368,22 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       m_used = m_new;
       float sum = 0.f;
       const uint32_t pdst = p_row + sb * C::P_BYTES;
+      // Three separate passes over the thread's HB scores (exponent arguments, then the MUFU exponentials back to back, then
+      // pack + store): interleaved chunk by chunk, each exp2 -> pack -> store chain exposed the ~40 clk MUFU latency with two
+      // or three exponentials in flight (900 clk per 64 scores for a warp ALONE on its sub-partition's MUFU pipe, which
+      // could do them in 512 -- profiles/r02h_attn_prefill_trace_qt2.txt).
+#pragma unroll
+      for (int i = 0; i < HB; ++i) s[i] = fmaf(s[i], p.sl2, -m_new);
+      // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
+      //  as well, so it added XU work instead of removing it)
+#pragma unroll
+      for (int i = 0; i < HB; ++i) s[i] = exp2_mufu(s[i]);
 #pragma unroll
       for (int cc = 0; cc < HB / 8; ++cc) {  // 16-byte chunks of 8 keys
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
-          //  as well, so it added XU work instead of removing it)
-          const float x0 = fmaf(s[cc * 8 + 2 * e], p.sl2, -m_new), x1 = fmaf(s[cc * 8 + 2 * e + 1], p.sl2, -m_new);
-          const float p0 = exp2_mufu(x0), p1 = exp2_mufu(x1);
+          const float p0 = s[cc * 8 + 2 * e], p1 = s[cc * 8 + 2 * e + 1];
           if constexpr (!TCSUM) sum += p0 + p1;
           pk[e] = pack_bf16(p0, p1);
         }
@@ -394,6 +392,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       }
       l_run = l_run * alpha + sum;  // (SW == 2: the sum over this thread's columns only; the halves are added at the end)
+      if (trole < 3) stamp(trole, j, 4);
       if (j > 0) {
         mbar_wait(o_done(qt), (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
         if (__any_sync(0xffffffffu, need)) {  // (both warps of a quadrant see the same maxima, hence the same decision)
@@ -410,10 +409,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tmem_st_wait();
         }
       }
+      if (trole < 3) stamp(trole, j, 5);
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(qt, sb));
+      if (trole < 3) stamp(trole, j, 6);
     }
     // ---- epilogue: O / l -> bf16 ----
     if constexpr (SW == 2 && !TCSUM) {  // total row sum = sum over both halves
@@ -494,13 +495,23 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     configured[dev] = true;
   }
   dim3 grid((p.rows + C::BM * QT - 1) / (C::BM * QT), H, B);
-  attn_prefill_tc_kernel<DH, SW, QT><<<grid, 64 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
+  attn_prefill_tc_kernel<DH, SW, QT><<<grid, 96 + 128 * SW * QT, C::SMEM, st>>>(tq, tk, tv, p);
   pg_count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 }  // namespace ap
 }  // namespace pg
+
+static int g_force_qt = 0, g_stagger = 500, g_force_sw = 0;
+static long long* g_trace = nullptr;
+extern "C" int pg_debug_set_attn_prefill_trace(long long* device_buffer) { g_trace = device_buffer; return 0; }
+extern "C" int pg_debug_set_attn_prefill(int force_qt, int stagger_clk) {  // tuning sweeps (dh <= 128): query tiles per CTA (0 = automatic), stagger
+  g_force_qt = force_qt & 3;
+  g_force_sw = (force_qt >> 4) & 3;  // bits 4-5: softmax warps per TMEM lane quadrant of the one-tile variant (0 = automatic)
+  if (stagger_clk >= 0) g_stagger = stagger_clk;
+  return 0;
+}
 
 // Returns PG_OK when the problem was launched on the tcgen05 kernel, 1 when the shape / strides are not supported by it
 // (the caller then uses the mma.sync kernel), or a negative error.
@@ -526,10 +537,10 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
     const int box[5] = {64, group, 128 / group, 1, 1};
     if ((rc = ap::make_tmap_nd(&tq, q, 5, dims, strides, box)) != PG_OK) return rc == PG_ERR_ARG ? 1 : rc;
   }
-  // query tiles per CTA.  Two tiles (64-key steps) win while a head has few key tiles
-  // -- fewer, fuller CTAs: SigLIP 224 px 0.107 -> 0.088 ms, 448 px 0.389 -> 0.366 ms per layer -- and lose slightly at 4096 keys
-  // (1.158 vs 1.190 ms), where the 128-key steps of the one-tile variant amortise the per-step barrier traffic better.
-  const int qt = dh > 128 ? 1 : (rows > 128 && keys <= 2048 ? 2 : 1);
+  // query tiles per CTA (dh <= 128).  Two tiles share every K / V tile and give each SM sub-partition two INDEPENDENT softmax
+  // warps (one per query tile) instead of two halves of one row in lock step: with the S and P V issuers split into two
+  // warps, 4096 keys run at 1.02 ms vs 1.21 ms for the one-tile variant (profiles/r02h_attn72_variants.txt).
+  const int qt = dh > 128 ? 1 : (g_force_qt ? g_force_qt : (rows > 128 ? 2 : 1));
   const int BN = (dh > 128 || qt == 2) ? 64 : 128;
   {
     const long long dims[4] = {dh, keys, H, B};
@@ -544,9 +555,11 @@ int pg_attention_prefill_tc(const void* q, const void* k, const void* v, void* o
   p.o_bs = o_bs; p.o_ts = o_ts; p.o_hs = o_hs; p.o_head_off = o_head_off;
   p.sl2 = scale * 1.4426950408889634f;
   p.key_lens = key_lens;
+  p.trace = g_trace;
+  p.stagger = g_stagger;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // softmax warps per TMEM lane quadrant: two (column halves) for the one-tile dh <= 128 variant, else one
-  const int sw = qt == 2 ? 1 : (dh > 128 ? 1 : 2);
+  const int sw = qt == 2 ? 1 : (g_force_sw ? g_force_sw : (dh > 128 ? 1 : 2));
 #define PG_AP_LAUNCH1(DHV)                                                           \
   if (sw == 1) return ap::launch<DHV, 1, 1>(tq, tk, tv, p, B, H, st);             \
   return ap::launch<DHV, 2, 1>(tq, tk, tv, p, B, H, st);
