@@ -45,7 +45,7 @@ NEW_TOKENS = 128
 TEMPERATURE, TOP_P = 0.8, 0.9
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 DOMINANT_KERNEL = "gemm_tcgen05_kernel<64, 1, 1, 0>"  # swap-AB (weights on the UMMA M axis), 64 token columns, 8 epilogue warps
-TRAFFIC_CAPTURE = os.path.join(ROOT, "profiles", "r02_decode_gemm_ncu_full.csv")
+TRAFFIC_CAPTURE = os.path.join(ROOT, "profiles", "r02i_decode_gemm_ncu_full.csv")
 
 
 def algorithmic_bytes_per_decode_step(cfg, batch, kv_len_avg):

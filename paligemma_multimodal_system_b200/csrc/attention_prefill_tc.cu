@@ -27,6 +27,10 @@
 #include "paligemma_b200.h"
 #include "tmap.cuh"
 
+#ifndef PG_AP_POLY8
+#define PG_AP_POLY8 3
+#endif
+
 namespace pg {
 namespace ap {
 
@@ -116,8 +120,21 @@ PG_DEVINL float exp2_mufu(float x) {
   return y;
 }
 
-// (Moving a share of the exponentials to the FMA pipe -- a polynomial 2^x -- was measured: no gain at a quarter, -7 % at half;
-//  the variant is gone.)
+// 2^x on the FMA / ALU pipes for a share of the scores (dh <= 128, where the MUFU pipe -- 16 exp2 per clock per SM -- is the
+// longest stage of the softmax): round-to-nearest split x = n + f by the 1.5 * 2^23 magic add (no F2I: conversions run on
+// the XU pipe too), cubic for 2^f on [-0.5, 0.5] (relative error < 1e-4, more than an order of magnitude below the bf16 rounding of the
+// probability that follows), n added into the exponent field.  x <= 8 by the lazy maximum; x = -inf (masked keys) clamps to
+// 2^-126, which rounds to a bf16 denormal that weighs nothing.
+// (Round 1 measured this as "no gain": at that time the single MMA-issuing thread, not the softmax, paced the kernel.)
+PG_DEVINL float exp2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05518874f, 0.24261212f);  // minimax cubic of 2^f on [-0.5, 0.5]: max relative error 7.5e-5
+  p = fmaf(p, f, 0.69325641f);
+  p = fmaf(p, f, 0.99992746f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 // QT = query tiles (128 rows each) per CTA.  QT = 2 (dh <= 128): both tiles run against the SAME K / V tiles in shared
 // memory -- the kernel is bound by K/V delivery through the crossbar (profiles/r01d_prefill_attn72_ncu_full.csv), and two
 // query tiles halve the K/V bytes per FLOP; softmax warps 2-5 own tile 0, warps 6-9 tile 1 (no exchange between them).
@@ -132,6 +149,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // the row sums of the (bf16) probabilities on the tensor core and the softmax warps -- bound by instruction issue, ~4.5
   // instructions per score -- drop the FADD per score.  The lazy rescale of O carries the column along.
   constexpr bool TCSUM = DHP > DH;
+  // scores per 8 whose exponential runs on the FMA pipe (exp2_fma): MUFU and FMA / issue time balance near 3 of 8 for dh <= 128;
+  // dh = 256 has four times the tensor work per score and is not softmax-bound
+  constexpr int POLY8 = DH <= 128 ? PG_AP_POLY8 : 0;
   constexpr uint32_t IDESC_S = make_idesc_bf16(BM, BN);
   constexpr uint32_t IDESC_O = make_idesc_bf16(BM, DHP, 0, 1);  // B (= V) is MN-major
   extern __shared__ __align__(1024) uint8_t smem_ap[];
@@ -377,7 +397,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // (an earlier variant with floorf / float->int range reduction was 40 % SLOWER: those conversions run on the XU pipe
       //  as well, so it added XU work instead of removing it)
 #pragma unroll
-      for (int i = 0; i < HB; ++i) s[i] = exp2_mufu(s[i]);
+      for (int i = 0; i < HB; ++i) s[i] = (POLY8 > 0 && (i & 7) >= 8 - POLY8) ? exp2_fma(s[i]) : exp2_mufu(s[i]);
 #pragma unroll
       for (int cc = 0; cc < HB / 8; ++cc) {  // 16-byte chunks of 8 keys
         uint32_t pk[4];

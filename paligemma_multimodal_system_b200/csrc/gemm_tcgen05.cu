@@ -13,6 +13,8 @@
 //   SWAP = false (prefill, many tokens):  UMMA M = 128 tokens,   N = BN features
 //   SWAP = true  (decode, tokens <= 128): UMMA M = 128 features, N = BN tokens  (weight streaming, HBM bound),
 //                                         optional split-K with fp32 red.global.add into the output
+#include <cmath>
+
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"
@@ -88,9 +90,26 @@ struct TileInfo {
 // every feature tile of a few token tiles, so each A tile is fetched from DRAM once and the (small) weight matrix stays
 // L2 resident: down_proj / fc2 re-read their 0.1-0.5 GB activation matrix once per feature tile otherwise (ncu: 4.1 GB
 // of DRAM reads for a 0.6 GB problem).
+// banded (n_fast = 2 + band): both operands exceed what L2 keeps -- gate||up at prefill sizes: 134 MB of activations AND 134 MB
+// of weights; m-fast re-read the activation matrix once per feature tile (ncu: 10.9 GB of DRAM reads for a 0.27 GB problem).
+// The token tiles are walked in bands of `band` tiles (~32 MB of activations, L2 resident while every feature tile passes),
+// so the weights are streamed once per band and the activations once.
 PG_DEVINL TileInfo decode_tile(int tile, int m_blocks, int n_blocks, int total_kb, int split_k, int n_fast = 0) {
   TileInfo t;
   int rest;
+  if (n_fast >= 2) {
+    const int band = n_fast - 2;  // >= 1
+    const int per_band = band * n_blocks;
+    const int b = tile / per_band;
+    const int in_band = tile - b * per_band;
+    const int m0 = b * band;
+    const int mb = min(band, m_blocks - m0);
+    t.m_blk = m0 + in_band % mb;
+    t.n_blk = in_band / mb;
+    t.kb0 = 0;
+    t.kb1 = total_kb;
+    return t;
+  }
   if (n_fast) {
     t.n_blk = tile % n_blocks;
     rest = tile / n_blocks;
@@ -1073,10 +1092,12 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_idx = 0;
 extern "C" int pg_debug_set_gemm_trace(long long* p) { g_gemm_trace = p; g_gemm_trace_idx = 0; return 0; }
+static int g_band_mode = 1;        // 0: never use the banded raster (A/B runs)
 static int g_pair_mode = 1;        // 0: never use the CTA-pair kernel (A/B runs)
 static int g_pair_min_tiles = 74;  // at least one 256 x 256 tile per pair of SMs
 extern "C" int pg_debug_set_gemm_pair(int mode, int min_tiles) {
-  g_pair_mode = mode;
+  g_pair_mode = mode & 1;
+  g_band_mode = (mode & 2) ? 0 : 1;  // bit 1: banded raster off
   if (min_tiles > 0) g_pair_min_tiles = min_tiles;
   return 0;
 }
@@ -1164,13 +1185,19 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
     }
   }
   a.n_fast = 0;
-  if (!swap && split_k == 1) {  // DRAM traffic estimate of the two raster orders (100 MB of the 126 MB L2 usable)
-    const double l2 = 100e6, A = 2.0 * tokens * K, Bw = 2.0 * features * K;
+  double band_rows = 0;  // banded raster: token rows per band (converted to tiles of the kernel that is chosen below)
+  if (!swap && split_k == 1) {  // DRAM traffic estimate of the raster orders
+    // an operand stays L2 resident while the other one streams through only if it is well below the 126 MB: 48 MB budget
+    // (measured: a 68 MB activation matrix under a 134 MB weight stream was re-read 7 times)
+    const double l2 = 48e6, A = 2.0 * tokens * K, Bw = 2.0 * features * K;
     const int mb = (tokens + BM - 1) / BM;
     const int nb256 = (features + 255) / 256;
     const double m_fast = (A > l2 ? A * nb256 : A) + Bw;
     const double n_fast = A + (Bw > l2 ? Bw * ((static_cast<double>(mb) * nb256 + 147) / 148) : Bw);
+    const double rows32 = 32e6 / (2.0 * K);  // token rows whose activations fill 32 MB
+    const double banded = A + Bw * ceil(tokens / rows32);
     a.n_fast = n_fast < 0.8 * m_fast ? 1 : 0;
+    if (banded < 0.8 * (a.n_fast ? n_fast : m_fast) && tokens > rows32 && g_band_mode != 0) band_rows = rows32;
   }
   a.f32_coalesced = (!swap && mode == PG_EPI_F32 && (features % 4) == 0 && (ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
@@ -1210,9 +1237,11 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
     const int pair_tiles = ((tokens + 2 * BM - 1) / (2 * BM)) * ((features + 255) / 256);
     // (measured per call site, profiles/r02h_gemm_pair_ab.txt: +2..16 % everywhere but the gelu epilogue of fc1, -3 %)
     if (g_pair_mode != 0 && BN == 256 && split_k == 1 && pair_tiles >= g_pair_min_tiles && !(mode == PG_EPI_BF16 && act_gelu)) {
+      if (band_rows > 0) a.n_fast = 2 + (static_cast<int>(band_rows) / (2 * BM) > 0 ? static_cast<int>(band_rows) / (2 * BM) : 1);
       if ((rc = make_tmap_2d(&tb, w, features, K, ldw, PAIR_BN / 2)) != PG_OK) return rc;
       return K <= 1536 ? launch_pair<true, false>(ta, tb, a, pair_tiles, st) : launch_pair<false, false>(ta, tb, a, pair_tiles, st);
     }
+    if (band_rows > 0) a.n_fast = 2 + (static_cast<int>(band_rows) / BM > 0 ? static_cast<int>(band_rows) / BM : 1);
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
     const int tiles = ((tokens + BM - 1) / BM) * ((features + BN - 1) / BN) * split_k;
     // short reduction (K <= 1536: the SigLIP projections): the epilogue outlasts the main loop, so it gets eight warps

@@ -18,7 +18,7 @@ shapes = [("siglip qkv   bf16+bias", T1, 3456, 1152, "bf16b"), ("siglip out   f3
           ("gemma qkv    bf16", T2, 2560, 2048, "bf16"), ("gemma o      f32+resid", T2, 2048, 2048, "f32r"),
           ("gemma gu     geglu", T2, 32768, 2048, "geglu"), ("gemma down   f32+resid", T2, 2048, 16384, "f32r"),
           ("ragged       bf16+bias", 16384 + 77, 3456 + 8, 1152, "bf16b")]
-tot = [0.0, 0.0]
+tot = [0.0, 0.0, 0.0, 0.0]
 for name, T, F, K, kind in shapes:
     x, w = rnd(T, K), rnd(F, K)
     bias = torch.randn(F, device="cuda")
@@ -32,7 +32,7 @@ for name, T, F, K, kind in shapes:
             return lambda: _lib.gemm_residual(x, w, out, bias=bias if "siglip" in name else None)
         return lambda: _lib.gemm(x, w, out, mode=_lib.EPI_F32, swap=0)
     outs, mss = [], []
-    for pair in (0, 1):
+    for pair in (2, 3, 0, 1):  # bit 0: CTA pair, bit 1: banded raster OFF
         L.pg_debug_set_gemm_pair(pair, 0)
         if kind in ("bf16b", "bf16", "gelu"): out = torch.zeros(T, F, device="cuda", dtype=torch.bfloat16)
         elif kind == "geglu": out = torch.zeros(T, F // 2, device="cuda", dtype=torch.bfloat16)
@@ -42,9 +42,9 @@ for name, T, F, K, kind in shapes:
         fn(); torch.cuda.synchronize()
         outs.append(out.clone())
         mss.append(t(fn))
-    same = torch.equal(outs[0], outs[1])
+    same = all(torch.equal(outs[0], o) for o in outs[1:])
     fl = 2.0 * T * F * K
-    tot[0] += mss[0]; tot[1] += mss[1]
-    print(f"{name:30s} T={T} F={F:6d} K={K:6d}: one-CTA {mss[0] * 1e3:8.1f} us {fl / mss[0] / 1e9:6.0f} TF/s | pair {mss[1] * 1e3:8.1f} us {fl / mss[1] / 1e9:6.0f} TF/s | bitwise equal {same}"
-          + ("" if same else f"  max diff {(outs[0].float() - outs[1].float()).abs().max().item():.3e}"), flush=True)
-print(f"sum: one-CTA {tot[0] * 1e3:.1f} us, pair {tot[1] * 1e3:.1f} us")
+    for i in range(4): tot[i] += mss[i]
+    print(f"{name:30s} T={T} F={F:6d} K={K:6d}: one-CTA {mss[0] * 1e3:8.1f} us {fl / mss[0] / 1e9:5.0f} TF/s | pair {mss[1] * 1e3:8.1f} us {fl / mss[1] / 1e9:5.0f} | one-CTA banded {mss[2] * 1e3:8.1f} us {fl / mss[2] / 1e9:5.0f} | pair banded {mss[3] * 1e3:8.1f} us {fl / mss[3] / 1e9:5.0f} | bitwise equal {same}", flush=True)
+print("sum: " + ", ".join(f"{n} {t * 1e3:.1f} us" for n, t in zip(("one-CTA", "pair", "one-CTA banded", "pair banded"), tot)))
+L.pg_debug_set_gemm_pair(1, 0)

@@ -20,7 +20,7 @@ for size in sizes:
     S = inp["input_ids"].shape[1]
     from paligemma_multimodal_system_b200 import _lib
     for fused in (False, True, False, True):  # (A/B switch reused: False = one-CTA GEMM only, True = CTA-pair GEMM)
-        _lib.lib().pg_debug_set_gemm_pair(1 if fused else 0, 0)
+        _lib.lib().pg_debug_set_gemm_pair(1 if fused else 3, 0)  # bit 1 set = banded raster OFF
         kv = KVCache()
         for _ in range(2):
             model.forward(inp["input_ids"], inp["pixel_values"], inp["attention_mask"], kv_cache=None, last_only=True)
@@ -35,6 +35,6 @@ for size in sizes:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps / B
         fl = algorithmic_flops_per_image(cfg, S)
-        print(f"{size} px x {B}: gemm_pair={fused}: {ms:.3f} ms/image = {fl / ms / 1e9:.0f} TFLOP/s = {fl / ms / 1e9 / tf_peak:.3f} of sustained peak", flush=True)
+        print(f"{size} px x {B}: banded_raster={fused}: {ms:.3f} ms/image = {fl / ms / 1e9:.0f} TFLOP/s = {fl / ms / 1e9 / tf_peak:.3f} of sustained peak", flush=True)
     del model
     torch.cuda.empty_cache()
