@@ -786,7 +786,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     if (lane == 0) {
       // weights are streamed once in decode (evict first); activations are re-read by every CTA (evict last)
       const uint64_t hintA = SWAP ? kEvictFirst : kEvictNormal;
-      const uint64_t hintB = SWAP ? kEvictLast : kEvictNormal;
+      const uint64_t hintB = (SWAP || args.n_fast == 1) ? kEvictLast : kEvictNormal;
       int stage = 0;
       uint32_t phase = 0;
       // The weight operand never depends on the previous kernel: with programmatic dependent launch its first
@@ -1000,6 +1000,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // feature tiles first (n_fast = 1): the weight matrix is the L2-resident operand (evict last), the activations pass through
+      // (evict-first on the activations is WRONG here: the CTAs of the feature tiles that share a token tile read it at slightly
+      //  different times, and an evict-first line is gone before the second reader arrives -- measured 2.97 -> 6.99 GB)
+      const uint64_t hintA = kEvictNormal;
+      const uint64_t hintB = args.n_fast == 1 ? kEvictLast : kEvictNormal;
       griddep_wait();
       griddep_launch_dependents();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -1008,8 +1013,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmapA, full_bar(stage), kb * BK, (2 * t.m_blk + rank) * BM, kEvictNormal);
-          tma_load_2d_pair(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN + rank * (BN / 2), kEvictNormal);
+          tma_load_2d_pair(sa, &tmapA, full_bar(stage), kb * BK, (2 * t.m_blk + rank) * BM, hintA);
+          tma_load_2d_pair(sa + A_TILE_BYTES, &tmapB, full_bar(stage), kb * BK, t.n_blk * BN + rank * (BN / 2), hintB);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1274,6 +1279,7 @@ extern "C" int pg_gemm_qkv_rope(const void* x, long long ldx, const void* w, lon
   a.rope_pos = pos; a.rope_inv_freq = inv_freq; a.rope_hq = Hq; a.rope_hkv = Hkv;
   a.k_pages = static_cast<__nv_bfloat16*>(k_pages); a.v_pages = static_cast<__nv_bfloat16*>(v_pages);
   a.page_table = page_table; a.slot_base = slot_base; a.tokens_per_seq = tokens_per_seq; a.max_pages = max_pages;
+  a.n_fast = 1;  // every head of a few token tiles at a time: the activations are read once (token tiles first re-read them once per head)
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap_2d(&ta, x, tokens, K, ldx, BM)) != PG_OK) return rc;
