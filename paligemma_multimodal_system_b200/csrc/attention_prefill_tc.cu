@@ -68,7 +68,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int COL_S = 0, COL_O = 2 * QT * BN;  // S: [QT][2 buffers][BN] columns, then O: [QT] accumulators
   static constexpr int O_STRIDE = QT == 2 ? 128 : DHP;  // (two accumulators: each starts on a 128-column boundary)
-  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 7 * QT;
+  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 8 * QT;
   static_assert(2 * QT * BN + (QT - 1) * O_STRIDE + DHP <= 512, "TMEM budget");
   static_assert(8 * NBAR + 8 <= 256, "barrier area");
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -112,6 +112,23 @@ PG_DEVINL uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t box_bytes) {
   return d;
 }
 
+
+// Waits for two barrier phases with both try_waits in flight together (their latencies overlap instead of adding up).
+PG_DEVINL void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred PA, PB;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 PA, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 PB, [%3], %4;\n\t"
+      "and.pred PA, PA, PB;\n\t"
+      "selp.u32 %0, 1, 0, PA;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+      : "memory");
+  if (ok) return;
+  mbar_wait(bar_a, par_a);
+  mbar_wait(bar_b, par_b);
+}
 
 // One MUFU ex2 per score (ftz; -inf -> +0, so masked keys weigh exactly nothing).
 PG_DEVINL float exp2_mufu(float x) {
@@ -159,7 +176,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if ((sbase & 1023u) != 0) __trap();
   const uint32_t bar0 = sbase + C::OFF_BAR;
   // barriers: q_full, k_full[KST], k_empty[KST], v_full[VST], v_empty[VST], then per query tile s_full[2], s_empty[2],
-  // p_full[2] and o_done
+  // p_full[2] and o_done[2]
   constexpr int S0 = 1 + 2 * KST + 2 * VST;
   const uint32_t q_full = bar0;
   auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
@@ -169,7 +186,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   auto s_full = [&](int qt, int s) { return bar0 + 8u * (S0 + qt * 2 + s); };
   auto s_empty = [&](int qt, int s) { return bar0 + 8u * (S0 + 2 * QT + qt * 2 + s); };
   auto p_full = [&](int qt, int s) { return bar0 + 8u * (S0 + 4 * QT + qt * 2 + s); };
-  auto o_done = [&](int qt) { return bar0 + 8u * (S0 + 6 * QT + qt); };
+  auto o_done = [&](int qt, int s) { return bar0 + 8u * (S0 + 6 * QT + qt * 2 + s); };  // P_j V_j complete: barrier j % 2
   const uint32_t tmem_slot = bar0 + 8u * C::NBAR;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_ap + C::OFF_BAR + 8 * C::NBAR);
 
@@ -196,7 +213,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_init(s_full(qt, s), 1); mbar_init(s_empty(qt, s), 4 * SW);
         mbar_init(p_full(qt, s), 4 * SW);
       }
-      mbar_init(o_done(qt), 1);
+      mbar_init(o_done(qt, 0), 1);
+      mbar_init(o_done(qt, 1), 1);
     }
     mbar_fence_init();
   }
@@ -305,7 +323,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const uint64_t bdesc = make_sdesc_mn_sw128(vaddr + k * 2048, C::KV_BOX);  // 16 keys = two 8-row groups
             umma_f16(d_tmem, adesc, bdesc, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(o_done(qt));
+          umma_commit(o_done(qt, pb));
           if (qt == QT - 1) umma_commit(v_empty(vs));
         }
         __syncwarp();
@@ -331,7 +349,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int sb = j & 1;
       const int trole = warp == 2 ? 1 : (warp == 6 ? 2 : 3);
       if (trole < 3) stamp(trole, j, 0);
-      mbar_wait(s_full(qt, sb), (j >> 1) & 1);
+      // S_j is ready AND P_{j-2} V_{j-2} has completed (its P buffer is the one this tile writes): both barrier round trips
+      // (~150 clk each even when the phase completed long ago) are in flight together.  P_{j-1} V_{j-1}, which the old loop
+      // waited for at the end of every tile, only matters to the rare O rescale below.
+      if (j >= 2) mbar_wait2(s_full(qt, sb), (j >> 1) & 1, o_done(qt, sb), ((j - 2) >> 1) & 1);
+      else mbar_wait(s_full(qt, sb), (j >> 1) & 1);
       if constexpr (QT == 2) {
         if (j == 0 && qt == 1 && p.stagger > 0) {
           const long long t0 = clock64();
@@ -414,8 +436,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       l_run = l_run * alpha + sum;  // (SW == 2: the sum over this thread's columns only; the halves are added at the end)
       if (trole < 3) stamp(trole, j, 4);
       if (j > 0) {
-        mbar_wait(o_done(qt), (j - 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched, P buffer j-1 is free
         if (__any_sync(0xffffffffu, need)) {  // (both warps of a quadrant see the same maxima, hence the same decision)
+          mbar_wait(o_done(qt, (j - 1) & 1), ((j - 1) >> 1) & 1);  // P_{j-1} V_{j-1} has completed: O may be touched
           tc_fence_after();
 #pragma unroll 1
           for (int c0 = half * 16; c0 < DHP; c0 += 16 * SW) {  // the halves take alternate 16-column slices of O
@@ -443,7 +465,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       pair_sync();
       l_run += xch[(half ^ 1) * 128 + r];
     }
-    mbar_wait(o_done(qt), (n_tiles - 1) & 1);
+    mbar_wait(o_done(qt, (n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
     if constexpr (TCSUM) {  // the row sum is column DH of the accumulator (ones column of V); any warp of the quadrant may read it
       uint32_t v[16];
