@@ -203,3 +203,89 @@ def test_qkv_projection_with_rope_and_kv_append_epilogue(B, S, Hq, Hkv, dh, K, c
         # nothing outside the appended slots was touched
         touched = (k_pages != 7.0).any(-1).sum().item()
         assert touched == B * S, (touched, B * S)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CTA-pair kernel (tcgen05.mma.cta_group::2) and banded raster: same arithmetic in the same order as the one-CTA kernel
+# ---------------------------------------------------------------------------------------------------------------------
+def _with_gemm_mode(mode, fn):
+    """mode bit 0: CTA-pair kernel allowed, bit 1: banded raster OFF (pg_debug_set_gemm_pair)."""
+    from paligemma_multimodal_system_b200 import _lib
+    L = _lib.lib()
+    L.pg_debug_set_gemm_pair(mode, 0)
+    try:
+        return fn()
+    finally:
+        L.pg_debug_set_gemm_pair(1, 0)
+
+
+@pytest.mark.parametrize("T,F,K,kind", [
+    (19000, 1152, 1152, "f32r"),      # short K: eight epilogue warps, fp32 residual in place, token tail
+    (18944 + 77, 3456 + 8, 1152, "bf16b"),  # ragged tokens AND features (TMA zero fill + masked stores)
+    (19000, 2048, 4304, "f32r"),      # long K, feature tiles first
+    (19200, 8192, 2048, "geglu"),     # gate||up: both operands beyond the L2 budget -> banded raster
+    (19000, 2560, 2048, "bf16"),
+    (18999, 2048, 1152, "f32"),
+])
+def test_gemm_cta_pair_bitwise_equal_to_one_cta_kernel(T, F, K, kind):
+    """gemm_pair_kernel (256 x 256 tile on a 2-CTA cluster) == gemm_tcgen05_kernel<256> bit for bit, with and without the
+    banded tile order, and both within tolerance of the fp32 reference."""
+    from paligemma_multimodal_system_b200 import _lib
+    x, w = _mk(T, F, K, 21)
+    bias = torch.randn(F, device="cuda")
+    res0 = torch.randn(T, F, device="cuda") if kind == "f32r" else None
+
+    def run():
+        if kind in ("bf16b", "bf16"):
+            out = torch.full((T, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _lib.gemm(x, w, out, mode=_lib.EPI_BF16, bias=bias if kind == "bf16b" else None, swap=0)
+        elif kind == "geglu":
+            out = torch.full((T, F // 2), float("nan"), device="cuda", dtype=torch.bfloat16)
+            _lib.gemm(x, w, out, mode=_lib.EPI_GEGLU, swap=0)
+        elif kind == "f32r":
+            out = res0.clone()
+            _lib.gemm(x, w, out, mode=_lib.EPI_F32, bias=bias, resid=out, swap=0)
+        else:
+            out = torch.full((T, F), float("nan"), device="cuda")
+            _lib.gemm(x, w, out, mode=_lib.EPI_F32, swap=0)
+        torch.cuda.synchronize()
+        return out
+
+    outs = [_with_gemm_mode(m, run) for m in (2, 3, 0, 1)]  # one-CTA, pair, one-CTA banded, pair banded
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    acc = _ref(x, w)
+    if kind == "bf16b":
+        _close(outs[0], acc + bias, 1e-2, "pair bf16+bias")
+    elif kind == "bf16":
+        _close(outs[0], acc, 1e-2, "pair bf16")
+    elif kind == "f32r":
+        _close(outs[0], acc + bias + res0, 2e-3, "pair f32 resid")
+    elif kind == "f32":
+        _close(outs[0], acc, 2e-3, "pair f32")
+    else:
+        g = acc.view(T, F // 128, 2, 64)
+        ref = (torch.nn.functional.gelu(g[:, :, 0], approximate="tanh") * g[:, :, 1]).reshape(T, F // 2)
+        _close(outs[0], ref, 2e-2, "pair geglu")
+
+
+def test_l2_prefetch_never_changes_results_and_validates_arguments():
+    """pg_prefetch_l2 only asks the copy engines for cache lines: the GEMM that follows sees the same weights."""
+    from paligemma_multimodal_system_b200 import _lib
+    L = _lib.lib()
+    x, w = _mk(64, 4096, 2048, 5)
+    out0 = torch.empty(64, 4096, device="cuda", dtype=torch.bfloat16)
+    out1 = torch.empty_like(out0)
+    _lib.gemm(x, w, out0, mode=_lib.EPI_BF16, swap=1)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    _lib.check(L.pg_prefetch_l2(w.data_ptr(), w.numel() * 2, 32, 0, side.cuda_stream), "pf")
+    _lib.check(L.pg_prefetch_l2(w.data_ptr(), (w.numel() * 2 - 4096) & ~15, 0, 1, side.cuda_stream), "pf")  # ragged length, all SMs, evict-last
+    _lib.gemm(x, w, out1, mode=_lib.EPI_BF16, swap=1)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert torch.equal(out0, out1)
+    assert L.pg_prefetch_l2(0, 1024, 0, 0, _lib.stream()) != 0          # null pointer
+    assert L.pg_prefetch_l2(w.data_ptr() + 2, 1024, 0, 0, _lib.stream()) != 0  # misaligned
+    assert L.pg_prefetch_l2(w.data_ptr(), 8, 0, 0, _lib.stream()) != 0      # shorter than one 16-byte piece
+    assert L.pg_prefetch_l2(w.data_ptr(), 1024, -1, 0, _lib.stream()) != 0  # negative grid

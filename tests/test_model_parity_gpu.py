@@ -274,3 +274,27 @@ def test_prefill_with_rope_and_kv_append_in_the_qkv_epilogue(regime):
         _check(logits[r], ref_l[r], regime, f"decode over pages written by the fused prefill, row {r}")
     assert model.generate(ids, px, mask, 8).cpu().tolist() == ref_t.tolist()
     model.language_model.fused_qkv_rope = None
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_decode_l2_prefetch_branch_changes_nothing(late, monkeypatch):
+    """The forked L2 weight prefetch of decode_layers (pg_prefetch_l2 on a side stream / graph branch) is a scheduling aid:
+    tokens and logits of a generate() job are bitwise identical with and without it, eagerly and through the CUDA graphs,
+    for both fork points (after the q/k/v launch; after the attention launch for large KV caches)."""
+    from paligemma_multimodal_system_b200.modeling_gemma import GemmaForCausalLM, KVCache
+    sd = make_state_dict(TINY_CONFIG, "R1", seed=5)
+    inp = make_inputs(TINY_CONFIG, batch=3, prompt_len=6, seed=2)
+    args = (inp["input_ids"].cuda(), inp["pixel_values"].cuda(), inp["attention_mask"].cuda(), 20)
+    if late:  # make every cache look large to the policy
+        monkeypatch.setattr(KVCache, "capacity", property(lambda self: 0 if self.page_table is None else 1 << 20))
+    outs = []
+    for pf_bytes in (0, 1 << 20):
+        monkeypatch.setattr(GemmaForCausalLM, "l2_prefetch_bytes", pf_bytes)
+        model = build_model(TINY_CONFIG, sd)
+        model.language_model.deterministic_decode = True  # no split-K: bitwise reproducible logits
+        for graph in (False, True):
+            toks = model.generate(*args, do_sample=False, use_cuda_graph=graph)
+            toks2, logits = model.generate(*args, do_sample=False, use_cuda_graph=False, return_logits=True)
+            outs.append((toks.clone(), toks2.clone(), logits.clone()))
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
