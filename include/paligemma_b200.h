@@ -42,6 +42,7 @@ long long pg_launch_count(void);
 int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
+int pg_debug_set_rmsnorm_early_trigger(int on); /* A/B runs: the decode RMSNorm triggers its dependents before / after its own dependency wait */
 int pg_debug_set_gemm_pair(int mode, int min_tiles); /* A/B runs: mode 0 disables the CTA-pair (cta_group::2) prefill GEMM; min_tiles > 0 sets its threshold */
 int pg_debug_set_attn_prefill_trace(long long* device_buffer); /* profiling aid: clock64 stamps of CTA (0,0,0) of the tcgen05 prefill attention, 3 roles x 32 tiles x 8 events */
 int pg_debug_set_attn_prefill(int force_qt, int stagger_clk); /* tuning sweeps of the dh <= 128 prefill attention: query tiles per CTA (0 = automatic), start offset of the second softmax group */

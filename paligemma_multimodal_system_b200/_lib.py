@@ -28,6 +28,7 @@ SIGNATURES = {
     "pg_prefetch_l2": [p, i64, i32, i32, p],
     "pg_debug_set_gemm_trace": [p],
     "pg_debug_set_gemm_bn": [i32],
+    "pg_debug_set_rmsnorm_early_trigger": [i32],
     "pg_debug_set_attn_prefill": [i32, i32],
     "pg_debug_set_attn_prefill_trace": [p],
     "pg_debug_set_gemm_pair": [i32, i32],

@@ -64,12 +64,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // GemmaRMSNorm (modeling_gemma.py:172-181): fp32, x * rsqrt(mean(x^2) + eps) * (1 + w)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      bf16* __restrict__ y, int D, float eps) {
+                                                      bf16* __restrict__ y, int D, float eps, int early_trigger) {
   extern __shared__ float row[];
   float* red = row + D;
   const long long r = blockIdx.x;
+  // early_trigger (decode chain): trigger BEFORE the wait, so that the GEMM consuming this norm becomes resident -- barriers,
+  // TMEM, tensor maps, first weight stages -- while the producer of x is still running, one kernel earlier than with the usual
+  // wait-then-trigger order.  Safe: the consumer's own griddepcontrol.wait waits for THIS kernel to complete, which has
+  // waited for its producer; before its wait the consumer only touches weights.
+  if (early_trigger && threadIdx.x == 0) griddep_launch_dependents();
   griddep_wait();
-  if (threadIdx.x == 0) griddep_launch_dependents();
+  if (!early_trigger && threadIdx.x == 0) griddep_launch_dependents();
   const float4* xr = reinterpret_cast<const float4*>(x + r * D);
   float ss = 0.f;
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
@@ -452,6 +457,9 @@ extern "C" int pg_layernorm(const float* x, const float* gamma, const float* bet
   PG_RET();
 }
 
+static int g_rmsnorm_early_trigger = 1;
+extern "C" int pg_debug_set_rmsnorm_early_trigger(int on) { g_rmsnorm_early_trigger = on; return 0; }
+
 extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows, int D, float eps, void* stream) {
   if (rows <= 0 || D <= 0 || (D % 4) != 0 || D > 8192) return PG_ERR_ARG;
   if (rows >= 1024 && (D % 128) == 0 && D <= 2048 &&
@@ -460,7 +468,7 @@ extern "C" int pg_rmsnorm(const float* x, const float* w, void* y_bf16, int rows
     PG_RET();
   }
   return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), (D + 33) * sizeof(float), PG_ST(stream), x, w,
-                       static_cast<bf16*>(y_bf16), D, eps) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
+                       static_cast<bf16*>(y_bf16), D, eps, g_rmsnorm_early_trigger) == cudaSuccess ? PG_OK : PG_ERR_CUDA;
 }
 
 extern "C" int pg_im2col(const float* pixels, void* patches, int B, int C, int H, int W, int P, int Kpad, void* stream) {

@@ -804,6 +804,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
       }
       if (tr) args.trace[1] = clock64();  // weights prefetch issued
+      // (triggering before the wait, as the decode RMSNorm does, changes nothing here: measured for q/k/v, o, gate||up, down)
       griddep_wait();
       if (tr) args.trace[2] = clock64();  // previous kernel complete
       griddep_launch_dependents();
