@@ -560,7 +560,8 @@ def main():
                                    "next launch's weight prefetch overlaps the running one), cold L2 (2.4 GB of weights in rotation)",
                          "ncu_isolated_us": cap["isolated_us"] if cap else None, "traffic_source": cap["file"] if cap else None},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
-                              "algorithmic_bytes": step_bytes, "kernels_per_layer": 7},
+                              "algorithmic_bytes": step_bytes, "kernels_per_layer": 7,
+                              "l2_prefetch_branch": bool(pf_on)},
             "roofline_prefill": {"bound": "tensor", "achieved": flops_img / (pre_ms / (K * B) * 1e-3) / 1e12,
                                  "peak": tf_peak, "unit": "TFLOP/s",
                                  "frac": flops_img / (pre_ms / (K * B) * 1e-3) / 1e12 / tf_peak,

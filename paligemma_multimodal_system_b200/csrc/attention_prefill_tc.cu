@@ -6,23 +6,24 @@
 // dh = 256; the G query heads of one KV head are stacked as consecutive rows of one problem, which replaces repeat_kv
 // modeling_gemma.py:185-196).
 //
-// One CTA = 128 query rows (one TMEM lane each) against all keys of its (batch, kv head), key tiles of BN keys:
+// One CTA = QT tiles of 128 query rows (one TMEM lane each) against all keys of its (batch, kv head), key tiles of BN keys:
 //   warp 0      TMA producer: Q once (5-D tensor map: dh, group, token, head, batch), then K / V tiles through two rings
-//   warp 1      tcgen05.mma issuer:  S_j = Q K_j^T  (M=128, N=BN, K=dh; both operands K-major, 128B swizzle)
-//                                    O  += P_j V_j  (M=128, N=dh, K=BN; P K-major from shared memory, V MN-major: the
-//                                                    [keys, dh] tile exactly as TMA delivers it)
+//   warp 1      S issuer:    S_j = Q K_j^T  (M=128, N=BN, K=dh; both operands K-major, 128B swizzle), double-buffered in TMEM
+//   last warp   P V issuer:  O  += P_j V_j  (M=128, N=dh, K=BN; P K-major from shared memory, V MN-major: the [keys, dh]
+//               tile exactly as TMA delivers it).  Two issuing warps because a tcgen05.mma blocks its issuing thread while
+//               the tensor pipe's queue is full; both run all 32 lanes with uniform control flow and elect.sync around the
+//               instruction, so that descriptors and TMEM addresses live in uniform registers.
 //   warps 2..   softmax: thread = query row; S is read from TMEM (tcgen05.ld), P = exp2(s - m) goes to shared memory as
-//               bf16 in the swizzled A-operand layout, the row sum stays in registers.  The running maximum is only
-//               advanced when it grew by more than 2^8 (the O accumulator in TMEM then gets rescaled in place), which
-//               keeps the accumulator round trip off the common path.  SW = 1: four warps (one per TMEM lane quadrant),
-//               a thread owns all BN columns of its row.  SW = 2: eight warps, two per quadrant, each thread owns half of
-//               the columns of its row (the two halves exchange their tile maxima through shared memory and one 64-thread
-//               named barrier per tile): the softmax is bound by instruction issue of ONE warp per SM sub-partition
-//               (~6 instructions per score), and the second set of warps doubles the issue slots it gets.
-// S is double buffered in TMEM, so S_{j+1} is computed while the softmax of tile j runs, and P_j V_j runs while the
-// softmax of tile j+1 runs: the tensor pipe only idles when the softmax (MUFU exp2) is the longer stage (dh = 72).
+//               bf16 in the swizzled A-operand layout.  The running maximum is only advanced when it grew by more than 2^8
+//               (the O accumulator in TMEM then gets rescaled in place), which keeps the accumulator round trip off the
+//               common path.  dh <= 128: QT = 2 -- warps 2-5 own query tile 0, warps 6-9 tile 1, sharing every K / V tile;
+//               3 of 8 exponentials run on the FMA pipe (exp2_fma), the row sums of dh = 72 come from the tensor core (a
+//               ones column in the padded V tile).  dh = 256: QT = 1, four softmax warps (SW = 1).  SW = 2 (eight warps, two
+//               column halves of one row exchanging their maxima through shared memory) remains for single-tile problems.
+// S_{j+1} is computed while the softmax of tile j runs, and P_j V_j runs while the softmax of tile j+1 runs.
 // Zero padding comes from TMA: columns beyond dh (72 -> 80) and key / query rows beyond the sequence are out-of-bounds
 // box elements and arrive as zeros; padded keys are masked to -inf before the softmax.
+// Timelines of one CTA (clock64 stamps, Params::trace): profiles/tools/attn_prefill_trace.py, profiles/r02h_attn_prefill_trace_*.txt.
 #include "common.cuh"
 #include "paligemma_b200.h"
 #include "tmap.cuh"

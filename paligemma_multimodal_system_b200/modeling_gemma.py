@@ -408,7 +408,7 @@ class GemmaForCausalLM(nn.Module):
     def decode_layers(self, bufs, kv_cache: KVCache, B, inv_temperature: float = 1.0):
         """One decode step over all layers (modeling_gemma.py:385-418 at q_len == 1); reads bufs['h'] (fp32 embeddings),
         leaves fp32 logits in bufs['logits'].  Seven launches per layer: RMSNorm, QKV GEMM, fused RoPE + KV append +
-        attention, O GEMM, RMSNorm, gate||up GEGLU GEMM, down GEMM; the three small-output GEMMs split K over CTAs and
+        attention, O GEMM, RMSNorm, gate||up GEGLU GEMM, down GEMM (+ one L2 weight prefetch on a forked stream, see below); the three small-output GEMMs split K over CTAs and
         red.add their fp32 partials straight into the residual stream / the zeroed `qkv` accumulator, which the o_proj launch
         resets for the next layer.  (Folding the norms into the GEMMs -- the consumer converting the fp32 residual stream into its
         own bf16 operand tiles -- was built and measured: slower)
