@@ -43,7 +43,7 @@ int pg_set_pdl(int on);
 /* Profiling aid: when non-NULL, CTA 0 of launch i writes 6 clock64 stamps to buffer[8*(i%64) ..] (device). */
 int pg_debug_set_gemm_trace(long long* device_buffer);
 int pg_debug_set_rmsnorm_early_trigger(int on); /* A/B runs: the decode RMSNorm triggers its dependents before / after its own dependency wait */
-int pg_debug_set_gemm_pair(int mode, int min_tiles); /* A/B runs: mode bit 0 = CTA-pair (cta_group::2) prefill GEMM allowed, bit 1 = banded tile raster OFF (default mode 1); min_tiles > 0 sets the pair kernel's tile-count threshold */
+int pg_debug_set_gemm_pair(int mode, int min_tiles); /* A/B runs: mode bit 0 = CTA-pair (cta_group::2) prefill GEMM allowed, bit 1 = banded tile raster OFF, bits 2-3 = epilogue warps of the pair kernel (1 = eight, 2 = four, 0 = automatic) (default mode 1); min_tiles > 0 sets the pair kernel's tile-count threshold */
 int pg_debug_set_attn_prefill_trace(long long* device_buffer); /* profiling aid: clock64 stamps of CTA (0,0,0) of the tcgen05 prefill attention, 3 roles x 32 tiles x 8 events */
 int pg_debug_set_attn_prefill(int force_qt, int stagger_clk); /* tuning sweeps of the prefill attention: force_qt bits 0-1 = query tiles per CTA for dh <= 128, bits 4-5 = softmax warps per TMEM lane quadrant of the one-tile variant (0 = automatic); stagger_clk >= 0 = start offset of the second softmax group */
 int pg_debug_set_gemm_bn(int bn); /* tuning sweeps: force the N tile (64 / 128 / 256) of the token-major GEMM, 0 = automatic */

@@ -1098,11 +1098,13 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_idx = 0;
 extern "C" int pg_debug_set_gemm_trace(long long* p) { g_gemm_trace = p; g_gemm_trace_idx = 0; return 0; }
+static int g_epi8_mode = 0;  // tuning: 1 = eight epilogue warps for every pair GEMM, 2 = four, 0 = by K
 static int g_band_mode = 1;        // 0: never use the banded raster (A/B runs)
 static int g_pair_mode = 1;        // 0: never use the CTA-pair kernel (A/B runs)
 static int g_pair_min_tiles = 74;  // at least one 256 x 256 tile per pair of SMs
 extern "C" int pg_debug_set_gemm_pair(int mode, int min_tiles) {
   g_pair_mode = mode & 1;
+  g_epi8_mode = (mode >> 2) & 3;
   g_band_mode = (mode & 2) ? 0 : 1;  // bit 1: banded raster off
   if (min_tiles > 0) g_pair_min_tiles = min_tiles;
   return 0;
@@ -1245,7 +1247,10 @@ extern "C" int pg_gemm_bf16_fused(const void* x, long long ldx, const void* w, l
     if (g_pair_mode != 0 && BN == 256 && split_k == 1 && pair_tiles >= g_pair_min_tiles && !(mode == PG_EPI_BF16 && act_gelu)) {
       if (band_rows > 0) a.n_fast = 2 + (static_cast<int>(band_rows) / (2 * BM) > 0 ? static_cast<int>(band_rows) / (2 * BM) : 1);
       if ((rc = make_tmap_2d(&tb, w, features, K, ldw, PAIR_BN / 2)) != PG_OK) return rc;
-      return K <= 1536 ? launch_pair<true, false>(ta, tb, a, pair_tiles, st) : launch_pair<false, false>(ta, tb, a, pair_tiles, st);
+      // eight epilogue warps where the epilogue outlasts the main loop: short K, and the fp32 residual epilogue (8 bytes of
+      // residual traffic per element) up to K = 2048 -- o_proj 142 -> 122 us at 16.6k tokens; gate||up and K >= 4304 prefer four
+      const bool epi8 = g_epi8_mode == 1 ? true : (g_epi8_mode == 2 ? false : (K <= 1536 || (mode == PG_EPI_F32 && K <= 2048)));
+      return epi8 ? launch_pair<true, false>(ta, tb, a, pair_tiles, st) : launch_pair<false, false>(ta, tb, a, pair_tiles, st);
     }
     if (band_rows > 0) a.n_fast = 2 + (static_cast<int>(band_rows) / BM > 0 ? static_cast<int>(band_rows) / BM : 1);
     if ((rc = make_tmap_2d(&tb, w, features, K, ldw, BN)) != PG_OK) return rc;
