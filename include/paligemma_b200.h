@@ -264,8 +264,9 @@ int pg_advance_decode_slots(const int* next, int* tok_ring, int ring, int* cur_t
  * pull the contiguous range [ptr, ptr + bytes) -- the weights of a LATER GEMM of the decode step (modeling_gemma.py:205-218
  * gate/up/down projections) -- into L2 and returns at once.  Meant for a forked branch of the step's CUDA graph, while the
  * attention block leaves the HBM idle.  `ctas` (0 = one per SM) paces the stream: every CTA keeps one SM's bulk-copy engine busy
- * (~80 GB/s), so a small grid is a background stream that leaves HBM bandwidth to the critical-path loads.  ptr 16-byte aligned.
- * Never changes results. */
+ * (~80 GB/s), so a small grid is a background stream that leaves HBM bandwidth to the critical-path loads.  evict_last != 0
+ * tags the lines L2::evict_last (measured: no benefit for the gate/up weights, kept for experiments).  ptr 16-byte aligned,
+ * bytes >= 16 (rounded down to a multiple of 16).  Never changes results. */
 int pg_prefetch_l2(const void* ptr, long long bytes, int ctas, int evict_last, void* stream);
 
 #ifdef __cplusplus
